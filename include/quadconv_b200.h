@@ -1,0 +1,180 @@
+/*
+ * quadconv_b200.h -- C ABI of libquadconv_b200.so (hand-written sm_100a CUDA; no torch types).
+ *
+ * The reference (AlgorithmicDataReduction/PyTorch-QuadConv) has no FFI layer: its hot path is ATen
+ * calls made from torch_quadconv/quadconv.py and torch_quadconv/mesh_pool.py.  Each entry point
+ * below replaces the ATen composition at the cited reference lines; the Python nn.Module shells
+ * in pytorch_quadconv_b200/ (same constructor/forward signatures as the reference) bind them with
+ * ctypes (pytorch_quadconv_b200/_cabi.py).  INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch allocates), except where a
+ *     parameter is documented as host; kernels never allocate or free;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative QC_E* code; no exceptions;
+ *   - re-entrant, no global state apart from one-time cudaFuncSetAttribute calls.
+ *
+ * Internal data layouts (DESIGN.md "Data layout in HBM")
+ *   packed features  Xp[nblk][N][C][Bp]   fp32; batch innermost. Bp = min(32, pow2ceil(B)) lanes,
+ *                    nblk = ceil(B/32) batch blocks, padded batch lanes are zero.
+ *   CSR              seg_ptr[Ndst+1] int32, src_idx[P] int32 (pairs grouped by destination point)
+ *   phi              [P][HP] fp32: last hidden activation of the filter MLP per pair, times the
+ *                    quadrature weight of the pair's input point; HP = H rounded up to {4,8,16,32}.
+ */
+#ifndef QUADCONV_B200_H
+#define QUADCONV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QC_EINVAL (-1)   /* bad argument */
+#define QC_EUNSUP (-2)   /* shape outside what the kernels implement (stated in DESIGN.md) */
+#define QC_EWORKSPACE (-3)
+
+#define QC_MAX_MLP_LAYERS 8
+
+int qc_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  support-radius neighbour search.
+ * Replaces QuadConv._compute_eval_indices, torch_quadconv/quadconv.py:165-199 (dense [No,Ni,d]
+ * subtract + vector_norm (:153-154) + `<=` + torch.nonzero).  Bit-exact pair SET and ORDER:
+ * predicate sqrtf(fmaf(z2,z2,fmaf(z1,z1,z0*z0))) <= r32 on fp32 differences, rows ascending in
+ * the out index then the in index.  d in {1,2,3}.
+ *
+ * Two calls, because the number of pairs is data dependent (like torch.nonzero):
+ *   qc_search_count : bins the in-points into a uniform grid (cell edge >= r), counts the hits of
+ *                     every out-point -> row_counts[No]; also emits the cell-sorted processing
+ *                     orders order_out[No], order_in[Ni] used by the fused kernels for locality.
+ *   (caller: exclusive scan -> row_ptr[No+1] with qc_exclusive_scan_i32, reads P = row_ptr[No])
+ *   qc_search_fill  : writes eval_indices[P,2] int64 (reference layout), pair_row[P], pair_col[P]
+ *                     int32.
+ * `ws` must hold qc_search_workspace_bytes(No, Ni, d) bytes and be passed unchanged to both.
+ * ------------------------------------------------------------------------------------------ */
+size_t qc_search_workspace_bytes(int No, int Ni, int d);
+int qc_search_count(const float* out_pts, const float* in_pts, int No, int Ni, int d, float r32,
+                    void* ws, size_t ws_bytes, int* row_counts, int* order_out, int* order_in,
+                    void* stream);
+int qc_search_fill(const float* out_pts, const float* in_pts, int No, int Ni, int d, float r32,
+                   void* ws, size_t ws_bytes, const int* row_ptr, int64_t* eval_indices,
+                   int* pair_row, int* pair_col, void* stream);
+
+/* exclusive prefix sum, n <= 2^27; out has n+1 entries (out[n] = total). */
+int qc_exclusive_scan_i32(const int* in, int n, int* out, void* stream);
+
+/* Pair list given by the caller (a cached / loaded eval_indices Parameter, quadconv.py:186-188,
+ * :240-242): rebuild pair_row/pair_col/row_counts.  err_flag (device int) is set non-zero if the
+ * rows are not ascending in the out index or an index is out of range. */
+int qc_pairs_to_csr(const int64_t* eval_indices, int64_t P, int No, int Ni, int* row_counts,
+                    int* pair_row, int* pair_col, int* err_flag, void* stream);
+
+/* Transposed (CSC) view: for every in-point the pairs that read it, ascending pair id.
+ *   csc_counts[Ni] (out, zeroed by the call) ; caller scans -> csc_ptr[Ni+1] ;
+ *   qc_csc_fill writes csc_pair[P] (pair id) and csc_row[P] (out index of that pair).
+ * `cursor` is an int[Ni] scratch. Needed by the backward pass w.r.t. the input features, whose
+ * reduction runs over pairs grouped by INPUT point (autograd of quadconv.py:219, index gather). */
+int qc_csc_count(const int* pair_col, int64_t P, int Ni, int* csc_counts, void* stream);
+int qc_csc_fill(const int* pair_row, const int* pair_col, int64_t P, int Ni, const int* csc_ptr,
+                int* cursor, int* csc_pair, int* csc_row, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout conversion between the reference's [B,C,N] tensors (quadconv.py:238 docstring) and the
+ * packed [nblk][N][C][Bp] layout.  qc_unpack_features optionally adds bias[C][N]
+ * (quadconv.py:262-263) and/or accumulates the per-(c,n) batch sum of the source (d bias).
+ * ------------------------------------------------------------------------------------------ */
+int qc_pack_features(const float* x, int B, int C, int N, float* xp, void* stream);
+int qc_unpack_features(const float* xp, int B, int C, int N, const float* bias, float* x,
+                       void* stream);
+int qc_batch_sum(const float* x, int B, int C, int N, float* out /*[C][N]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2a  hidden layers of the filter MLP per pair.
+ * Replaces, per pair p: weights[idx1] gather (quadconv.py:247), eval_locs (quadconv.py:250-253),
+ * and every layer of self.filter except the last Linear (quadconv.py:130-145, utils/misc.py:18-19).
+ *   phi[p][h] = w[col[p]] * sin(W_L-1 ... sin(W_0 (out_pts[row[p]] - in_pts[col[p]])))[h]
+ * mlp_w[l] : device pointer to filter.{2l}.weight, row-major [dims[l+1]][dims[l]], l < n_hidden.
+ * dims[0] = d, dims[1..n_hidden] = filter_seq; every dim <= 32.  n_hidden may be 0 (phi = w * z).
+ * quad_w may be NULL (weights of one).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int n_hidden;
+    int dims[QC_MAX_MLP_LAYERS + 1];
+    const float* w[QC_MAX_MLP_LAYERS];
+} qc_mlp_t;
+
+int qc_pair_phi_fwd(const float* out_pts, const float* in_pts, const float* quad_w,
+                    const int* pair_row, const int* pair_col, int64_t P, int d,
+                    const qc_mlp_t* mlp /*host*/, int HP, float* phi, void* stream);
+
+/* Backward of the above.  dphi[P][HP] is d loss / d phi.  Accumulates (+=) into
+ *   d_mlp_w[l] (same shapes as mlp_w[l]) and d_quad_w[Ni] (may be NULL). */
+int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad_w,
+                    const int* pair_row, const int* pair_col, int64_t P, int d,
+                    const qc_mlp_t* mlp /*host*/, int HP, const float* dphi,
+                    float* const* d_mlp_w /*host array of device ptrs*/, float* d_quad_w,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2b/K3  fused last-MLP-layer + gather-contract-segmented-reduce.
+ * Replaces the last Linear of self.filter + reshape (quadconv.py:143,:91), the feature gather,
+ * einsum('n,nij,bin->bjn') and scatter_add_ of QuadConv._integrate (quadconv.py:213-227); the
+ * [P,Ci,Co] filter tensor, the gathered [B,Ci,P] features and the [B,Co,P] values never exist.
+ * Factorised (SURVEY.md hard-part 3b): for a destination point t with segment S(t)
+ *     T[t; b, c, h] = sum_{q in S(t)} phi[phi_idx[q]][h] * Xp[src_idx[q]][c][b]       (stage B)
+ *     Yp[t][j][b]   = sum_{c,h} T[t; b, c, h] * W2[(c*H + h)][j]                        (stage C)
+ * Forward:  dst = out points, src = in points, W2[(i*H+h)][j] = W_last[i*Co+j][h].
+ * d/d features: dst = in points (CSC), src = out points, X = packed grad_out,
+ *               W2[(j*H+h)][i] = W_last[i*Co+j][h]; with Zp = packed features the same pass
+ *               accumulates dW2[(c*H+h)][j] += sum_{t,b} T[t;b,c,h] * Zp[t][j][b]  (= d W_last).
+ * W2 / dW2 have row stride CyP = Cy rounded up to 4 (padding columns zero / ignored).
+ * order: processing order of destination points (NULL = identity).  phi_idx NULL = identity.
+ * B is the true batch size (Bp / nblk are derived as in the layout note above).
+ * ------------------------------------------------------------------------------------------ */
+int qc_contract(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, const int* src_idx,
+                const int* phi_idx, const float* phi, int H, int HP, const float* W2, int Cy,
+                const int* order, int Ndst, int B, float* Yp, const float* Zp, float* dW2,
+                void* stream);
+
+/* d loss / d phi (grouped by out point):
+ *     dT[t; b, c, h] = sum_j Gp[t][j][b] * W3[j][c][h]          W3[j][c][h] = W_last[c*Co+j][h]
+ *     dphi[q][h]    += sum_{b,c} Xp[src_idx[q]][c][b] * dT[t; b, c, h]       (q in S(t))
+ * W3 is [Cg][Cx][HP] (h padded with zeros).  dphi must be zeroed by the caller. */
+int qc_dphi(const float* Xp, int Nsrc, int Cx, const float* Gp, int Cg, const int* seg_ptr,
+            const int* src_idx, const float* W3, int H, int HP, const int* order, int Ndst, int B,
+            float* dphi, void* stream);
+
+/* Repack the last Linear weight W_last [Ci*Co][H] (filter.{2L}.weight, quadconv.py:143):
+ *   mode 0: W2[(i*H+h)*CoP + j]  (forward)        mode 1: W2[(j*H+h)*CiP + i]  (d features)
+ *   mode 2: W3[(j*Ci+i)*HP + h]  (d phi)
+ * and the inverse scatter of dW2 (mode 1 layout) back to dW_last (+=). */
+int qc_repack_wlast(const float* w_last, int Ci, int Co, int H, int HP, int mode, float* out,
+                    void* stream);
+int qc_unpack_dwlast(const float* dW2, int Ci, int Co, int H, float* d_w_last, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5/K6  Mesh_MaxPool.  Replaces scatter_reduce_(amax, include_self=False) (mesh_pool.py:88-89)
+ * and gather (mesh_pool.py:93) and their autograd.  Groups are given as CSR over the fine points:
+ * grp_ptr[Nout+1], grp_mem[Nin] (members of each group).  Empty groups produce 0 like the
+ * reference's zeros() initialisation.  Backward splits the gradient evenly between tied maxima
+ * (torch's amax rule).  x, out: [BC][N] fp32 row-major.
+ * ------------------------------------------------------------------------------------------ */
+int qc_segmax_fwd(const float* x, const int* grp_ptr, const int* grp_mem, int BC, int Nin, int Nout,
+                  float* out, void* stream);
+int qc_segmax_bwd(const float* x, const float* out, const float* grad_out, const int* group /*[Nin]*/,
+                  const int* grp_ptr, const int* grp_mem, int BC, int Nin, int Nout, float* grad_x,
+                  void* stream);
+int qc_gather_fwd(const float* x, const int* index /*[Nout]*/, int BC, int Nin, int Nout, float* out,
+                  void* stream);
+/* grad_x[r][g] = sum_{k in members(g)} grad_out[r][k]; grp_* is the CSR inverse of `index`. */
+int qc_gather_bwd(const float* grad_out, const int* grp_ptr, const int* grp_mem, int BC, int Nfine,
+                  int Ncoarse, float* grad_x, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUADCONV_B200_H */

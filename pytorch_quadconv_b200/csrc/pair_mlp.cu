@@ -1,0 +1,283 @@
+// pair_mlp.cu -- K2a: hidden layers of the filter MLP, one thread per (out,in) pair.
+//
+// Reference: per pair the reference gathers the quadrature weight (quadconv.py:247), forms the
+// offset eval_locs = P_out[idx0] - P_in[idx1] (quadconv.py:250-253) and pushes it through
+// self.filter = Sequential(Linear(bias=False), Sin, ..., Linear(bias=False)) (quadconv.py:130-145,
+// utils/misc.py:18-19).  The LAST Linear (h_L -> Ci*Co) is linear in its input, so it is folded
+// into the contraction kernel (contract.cu); this file evaluates everything before it:
+//     phi[p][h] = w[in(p)] * x_L[h],  x_0 = z_p,  x_{l+1} = sin(W_l x_l)
+// and its backward.  The hidden widths are tiny (4..32), so this is CUDA-core work: the weights sit
+// zero-padded in shared memory and are read as warp-uniform broadcasts; activations stay in
+// registers.  sinf/cosf are the accurate versions (no fast-math) to hold the 1e-5 fp32 bound.
+#include "common.cuh"
+
+namespace {
+
+struct MlpDev {
+    int n_hidden;
+    int dims[QC_MAX_MLP_LAYERS + 1];
+    const float* w[QC_MAX_MLP_LAYERS];
+    float* dw[QC_MAX_MLP_LAYERS];
+};
+
+template <int WMAX>
+__device__ __forceinline__ void load_weights(const MlpDev& m, float* Wsm)
+{
+    // Wsm[l][o*WMAX + k], zero padded
+    for (int l = 0; l < m.n_hidden; ++l) {
+        const int nin = m.dims[l], nout = m.dims[l + 1];
+        for (int t = threadIdx.x; t < WMAX * WMAX; t += blockDim.x) {
+            int o = t / WMAX, k = t % WMAX;
+            Wsm[l * WMAX * WMAX + t] = (o < nout && k < nin) ? m.w[l][o * nin + k] : 0.f;
+        }
+    }
+}
+
+template <int WMAX>
+__global__ void __launch_bounds__(128)
+k_pair_phi_fwd(const float* __restrict__ out_pts, const float* __restrict__ in_pts,
+               const float* __restrict__ quad_w, const int* __restrict__ pair_row,
+               const int* __restrict__ pair_col, int64_t P, int d, MlpDev m, int HP,
+               float* __restrict__ phi)
+{
+    extern __shared__ float smem[];
+    float* Wsm = smem;
+    load_weights<WMAX>(m, Wsm);
+    __syncthreads();
+    const int H = m.dims[m.n_hidden];
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+        const int r = pair_row[p], c = pair_col[p];
+        float a[WMAX];
+#pragma unroll
+        for (int k = 0; k < WMAX; ++k) a[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (k < d && k < WMAX) a[k] = __fsub_rn(out_pts[(size_t)r * d + k], in_pts[(size_t)c * d + k]);
+        for (int l = 0; l < m.n_hidden; ++l) {
+            const float* W = Wsm + l * WMAX * WMAX;
+            float t[WMAX];
+#pragma unroll
+            for (int o = 0; o < WMAX; ++o) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < WMAX; ++k) acc = fmaf(W[o * WMAX + k], a[k], acc);
+                t[o] = sinf(acc);
+            }
+#pragma unroll
+            for (int o = 0; o < WMAX; ++o) a[o] = t[o];
+        }
+        const float wq = quad_w ? quad_w[c] : 1.f;
+        float* dst = phi + (size_t)p * HP;
+#pragma unroll
+        for (int h = 0; h < WMAX; ++h)
+            if (h < HP) dst[h] = h < H ? wq * a[h] : 0.f;
+        // HP may exceed WMAX only when H <= WMAX < HP, which the host never configures
+    }
+}
+
+// Backward.  Block = 128 pairs per sweep.  Per layer the block stages (da, x) of its pairs in
+// shared memory and every thread owns a fixed set of dW[o][k] entries, so the weight gradient is
+// reduced without atomics inside the block; one atomicAdd per entry per block at the end.
+template <int WMAX>
+__global__ void __launch_bounds__(128)
+k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_pts,
+               const float* __restrict__ quad_w, const int* __restrict__ pair_row,
+               const int* __restrict__ pair_col, int64_t P, int d, MlpDev m, int HP,
+               const float* __restrict__ dphi, float* __restrict__ d_quad_w)
+{
+    constexpr int NT = 128;
+    extern __shared__ float smem[];
+    float* Wsm = smem;                                  // [n_hidden][WMAX*WMAX]
+    float* dWs = Wsm + m.n_hidden * WMAX * WMAX;        // [n_hidden][WMAX*WMAX]
+    float* da_s = dWs + m.n_hidden * WMAX * WMAX;       // [NT][WMAX]
+    float* x_s = da_s + NT * WMAX;                      // [NT][WMAX]
+    load_weights<WMAX>(m, Wsm);
+    for (int t = threadIdx.x; t < m.n_hidden * WMAX * WMAX; t += NT) dWs[t] = 0.f;
+    __syncthreads();
+    const int H = m.dims[m.n_hidden];
+    const int L = m.n_hidden;
+
+    for (int64_t base = (int64_t)blockIdx.x * NT; base < P; base += (int64_t)gridDim.x * NT) {
+        const int64_t p = base + threadIdx.x;
+        const bool valid = p < P;
+        // forward recompute, keeping every layer input and the cosine of every pre-activation
+        float xs[QC_MAX_MLP_LAYERS + 1][WMAX];
+        float cs[QC_MAX_MLP_LAYERS][WMAX];
+        int r = 0, c = 0;
+        if (valid) {
+            r = pair_row[p];
+            c = pair_col[p];
+        }
+#pragma unroll
+        for (int k = 0; k < WMAX; ++k) xs[0][k] = 0.f;
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < d && k < WMAX) xs[0][k] = __fsub_rn(out_pts[(size_t)r * d + k], in_pts[(size_t)c * d + k]);
+        }
+        for (int l = 0; l < L; ++l) {
+            const float* W = Wsm + l * WMAX * WMAX;
+#pragma unroll
+            for (int o = 0; o < WMAX; ++o) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < WMAX; ++k) acc = fmaf(W[o * WMAX + k], xs[l][k], acc);
+                float sv, cv;
+                sincosf(acc, &sv, &cv);
+                xs[l + 1][o] = sv;
+                cs[l][o] = cv;
+            }
+        }
+        const float wq = (valid && quad_w) ? quad_w[c] : 1.f;
+        float dx[WMAX];
+        float dwq = 0.f;
+#pragma unroll
+        for (int h = 0; h < WMAX; ++h) {
+            float g = (valid && h < H && h < HP) ? dphi[(size_t)p * HP + h] : 0.f;
+            dwq = fmaf(g, xs[L][h], dwq);
+            dx[h] = wq * g;
+        }
+        if (valid && d_quad_w) atomicAdd(&d_quad_w[c], dwq);
+
+        for (int l = L - 1; l >= 0; --l) {
+            const float* W = Wsm + l * WMAX * WMAX;
+            float da[WMAX];
+#pragma unroll
+            for (int o = 0; o < WMAX; ++o) {
+                da[o] = dx[o] * cs[l][o];
+                da_s[threadIdx.x * WMAX + o] = da[o];
+                x_s[threadIdx.x * WMAX + o] = xs[l][o];
+            }
+            __syncthreads();
+            // dW_l[o][k] += sum_q da[q][o] * x[q][k]
+            for (int t = threadIdx.x; t < WMAX * WMAX; t += NT) {
+                int o = t / WMAX, k = t % WMAX;
+                float acc = 0.f;
+#pragma unroll 8
+                for (int q = 0; q < NT; ++q) acc = fmaf(da_s[q * WMAX + o], x_s[q * WMAX + k], acc);
+                dWs[l * WMAX * WMAX + t] += acc;
+            }
+            if (l > 0) {
+#pragma unroll
+                for (int k = 0; k < WMAX; ++k) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int o = 0; o < WMAX; ++o) acc = fmaf(W[o * WMAX + k], da[o], acc);
+                    dx[k] = acc;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // flush
+    for (int l = 0; l < L; ++l) {
+        const int nin = m.dims[l], nout = m.dims[l + 1];
+        for (int t = threadIdx.x; t < WMAX * WMAX; t += NT) {
+            int o = t / WMAX, k = t % WMAX;
+            if (o < nout && k < nin) atomicAdd(&m.dw[l][o * nin + k], dWs[l * WMAX * WMAX + t]);
+        }
+    }
+}
+
+int pick_wmax(const qc_mlp_t* mlp, int d)
+{
+    int mx = d;
+    for (int l = 1; l <= mlp->n_hidden; ++l) mx = mlp->dims[l] > mx ? mlp->dims[l] : mx;
+    if (mx <= 4) return 4;
+    if (mx <= 8) return 8;
+    if (mx <= 16) return 16;
+    if (mx <= 32) return 32;
+    return -1;
+}
+
+int fill_dev(const qc_mlp_t* mlp, int d, MlpDev& m)
+{
+    if (mlp->n_hidden < 0 || mlp->n_hidden > QC_MAX_MLP_LAYERS) return QC_EUNSUP;
+    if (mlp->dims[0] != d) return QC_EINVAL;
+    m.n_hidden = mlp->n_hidden;
+    for (int l = 0; l <= QC_MAX_MLP_LAYERS; ++l) m.dims[l] = l <= mlp->n_hidden ? mlp->dims[l] : 0;
+    for (int l = 0; l < QC_MAX_MLP_LAYERS; ++l) {
+        m.w[l] = l < mlp->n_hidden ? mlp->w[l] : nullptr;
+        m.dw[l] = nullptr;
+    }
+    return 0;
+}
+
+template <int WMAX>
+int launch_fwd(const float* out_pts, const float* in_pts, const float* quad_w, const int* pair_row,
+               const int* pair_col, int64_t P, int d, const MlpDev& m, int HP, float* phi, cudaStream_t st)
+{
+    size_t smem = (size_t)(m.n_hidden > 0 ? m.n_hidden : 1) * WMAX * WMAX * 4;
+    QC_CUDA(cudaFuncSetAttribute(k_pair_phi_fwd<WMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 16);
+    k_pair_phi_fwd<WMAX><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, phi);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int WMAX>
+int launch_bwd(const float* out_pts, const float* in_pts, const float* quad_w, const int* pair_row,
+               const int* pair_col, int64_t P, int d, const MlpDev& m, int HP, const float* dphi,
+               float* d_quad_w, cudaStream_t st)
+{
+    size_t smem = ((size_t)2 * m.n_hidden * WMAX * WMAX + 2 * 128 * WMAX) * 4;
+    QC_CUDA(cudaFuncSetAttribute(k_pair_phi_bwd<WMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 4);
+    k_pair_phi_bwd<WMAX><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, d_quad_w);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qc_pair_phi_fwd(const float* out_pts, const float* in_pts, const float* quad_w,
+                    const int* pair_row, const int* pair_col, int64_t P, int d,
+                    const qc_mlp_t* mlp, int HP, float* phi, void* stream)
+{
+    if (P <= 0) return 0;
+    if (d < 1 || d > 3) return QC_EUNSUP;
+    MlpDev m;
+    int rc = fill_dev(mlp, d, m);
+    if (rc) return rc;
+    const int H = m.dims[m.n_hidden];
+    const int wmax = pick_wmax(mlp, d);
+    if (wmax < 0 || HP < H || HP > 32 || (HP & 3)) return QC_EUNSUP;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wsel = wmax > HP ? wmax : HP;  // the phi row (HP wide) is written from registers
+    switch (wsel) {
+        case 4: return launch_fwd<4>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, phi, st);
+        case 8: return launch_fwd<8>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, phi, st);
+        case 16: return launch_fwd<16>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, phi, st);
+        case 32: return launch_fwd<32>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, phi, st);
+    }
+    return QC_EUNSUP;
+}
+
+int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad_w,
+                    const int* pair_row, const int* pair_col, int64_t P, int d,
+                    const qc_mlp_t* mlp, int HP, const float* dphi, float* const* d_mlp_w,
+                    float* d_quad_w, void* stream)
+{
+    if (P <= 0) return 0;
+    if (d < 1 || d > 3) return QC_EUNSUP;
+    MlpDev m;
+    int rc = fill_dev(mlp, d, m);
+    if (rc) return rc;
+    for (int l = 0; l < m.n_hidden; ++l) m.dw[l] = d_mlp_w[l];
+    const int H = m.dims[m.n_hidden];
+    const int wmax = pick_wmax(mlp, d);
+    if (wmax < 0 || HP < H || HP > 32 || (HP & 3)) return QC_EUNSUP;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wsel = wmax > HP ? wmax : HP;
+    switch (wsel) {
+        case 4: return launch_bwd<4>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, d_quad_w, st);
+        case 8: return launch_bwd<8>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, d_quad_w, st);
+        case 16: return launch_bwd<16>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, d_quad_w, st);
+        case 32: return launch_bwd<32>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, d_quad_w, st);
+    }
+    return QC_EUNSUP;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// pool.cu -- K5/K6: Mesh_MaxPool as a segmented max (and its adjoint gather) with analytic
+// backward.  Reference: torch_quadconv/mesh_pool.py:88-89 (zeros + scatter_reduce_ amax,
+// include_self=False over an int64 [B,C,N] index) and :93 (gather), backward by autograd.
+// Here the group structure is one int32 CSR shared by every (batch, channel) row, so the
+// reduction is atomic-free and deterministic; ties split the gradient evenly like torch's amax.
+// Rows are [BC][N] with the point index innermost; threads walk the point index so stores are
+// coalesced and the member reads of a group hit nearby cache lines.
+#include "common.cuh"
+
+namespace {
+
+__global__ void k_segmax_fwd(const float* __restrict__ x, const int* __restrict__ grp_ptr,
+                             const int* __restrict__ grp_mem, int BC, int Nin, int Nout, float* __restrict__ out)
+{
+    const int64_t total = (int64_t)BC * Nout;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(t % Nout);
+        const int64_t r = t / Nout;
+        const int beg = grp_ptr[g], end = grp_ptr[g + 1];
+        float m = 0.f;  // empty group keeps the reference's zero initialisation
+        if (end > beg) {
+            m = -INFINITY;
+            for (int e = beg; e < end; ++e) m = fmaxf(m, __ldg(x + r * Nin + grp_mem[e]));
+        }
+        out[t] = m;
+    }
+}
+
+__global__ void k_segmax_bwd(const float* __restrict__ x, const float* __restrict__ out,
+                             const float* __restrict__ grad_out, const int* __restrict__ group,
+                             const int* __restrict__ grp_ptr, const int* __restrict__ grp_mem, int BC, int Nin,
+                             int Nout, float* __restrict__ grad_x)
+{
+    const int64_t total = (int64_t)BC * Nin;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t % Nin);
+        const int64_t r = t / Nin;
+        const int g = group[k];
+        const float m = out[r * Nout + g];
+        float gx = 0.f;
+        if (x[t] == m) {
+            int ties = 0;
+            for (int e = grp_ptr[g]; e < grp_ptr[g + 1]; ++e) ties += (__ldg(x + r * Nin + grp_mem[e]) == m);
+            gx = grad_out[r * Nout + g] / (float)ties;
+        }
+        grad_x[t] = gx;
+    }
+}
+
+__global__ void k_gather_fwd(const float* __restrict__ x, const int* __restrict__ index, int BC, int Nin,
+                             int Nout, float* __restrict__ out)
+{
+    const int64_t total = (int64_t)BC * Nout;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t % Nout);
+        const int64_t r = t / Nout;
+        out[t] = __ldg(x + r * Nin + index[k]);
+    }
+}
+
+__global__ void k_gather_bwd(const float* __restrict__ grad_out, const int* __restrict__ grp_ptr,
+                             const int* __restrict__ grp_mem, int BC, int Nfine, int Ncoarse, float* __restrict__ grad_x)
+{
+    const int64_t total = (int64_t)BC * Ncoarse;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(t % Ncoarse);
+        const int64_t r = t / Ncoarse;
+        float s = 0.f;
+        for (int e = grp_ptr[g]; e < grp_ptr[g + 1]; ++e) s += __ldg(grad_out + r * Nfine + grp_mem[e]);
+        grad_x[t] = s;
+    }
+}
+
+inline int grid_for(int64_t total) { return min(qc_ceil_div(total > 0 ? total : 1, 256), qc_num_sms() * 16); }
+
+}  // namespace
+
+extern "C" {
+
+int qc_segmax_fwd(const float* x, const int* grp_ptr, const int* grp_mem, int BC, int Nin, int Nout,
+                  float* out, void* stream)
+{
+    if (BC <= 0 || Nin <= 0 || Nout <= 0) return QC_EINVAL;
+    k_segmax_fwd<<<grid_for((int64_t)BC * Nout), 256, 0, (cudaStream_t)stream>>>(x, grp_ptr, grp_mem, BC, Nin, Nout, out);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+int qc_segmax_bwd(const float* x, const float* out, const float* grad_out, const int* group,
+                  const int* grp_ptr, const int* grp_mem, int BC, int Nin, int Nout, float* grad_x,
+                  void* stream)
+{
+    if (BC <= 0 || Nin <= 0 || Nout <= 0) return QC_EINVAL;
+    k_segmax_bwd<<<grid_for((int64_t)BC * Nin), 256, 0, (cudaStream_t)stream>>>(x, out, grad_out, group, grp_ptr, grp_mem, BC, Nin, Nout, grad_x);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+int qc_gather_fwd(const float* x, const int* index, int BC, int Nin, int Nout, float* out, void* stream)
+{
+    if (BC <= 0 || Nin <= 0 || Nout <= 0) return QC_EINVAL;
+    k_gather_fwd<<<grid_for((int64_t)BC * Nout), 256, 0, (cudaStream_t)stream>>>(x, index, BC, Nin, Nout, out);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+int qc_gather_bwd(const float* grad_out, const int* grp_ptr, const int* grp_mem, int BC, int Nfine,
+                  int Ncoarse, float* grad_x, void* stream)
+{
+    if (BC <= 0 || Nfine <= 0 || Ncoarse <= 0) return QC_EINVAL;
+    k_gather_bwd<<<grid_for((int64_t)BC * Ncoarse), 256, 0, (cudaStream_t)stream>>>(grad_out, grp_ptr, grp_mem, BC, Nfine, Ncoarse, grad_x);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

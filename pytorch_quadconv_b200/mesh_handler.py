@@ -1,0 +1,135 @@
+"""
+MeshHandler -- drop-in for torch_quadconv.MeshHandler (reference torch_quadconv/mesh_handler.py:20-212).
+
+This is the boundary object handed to `QuadConv.forward(mesh, x)` / `Mesh_MaxPool.forward(mesh, x)`.
+Same constructor, `construct(...)`, cursor (`reset/step/_get_index`) and accessor semantics, same
+state_dict keys (`_points.{l}`, `_adjacency.{l}`, `_weight_network.{0,2,4,6}.{weight,bias}`).
+Its internals are setup-time host code (scipy Delaunay, MFNUS coarsening) plus the tiny learned
+quadrature-weight network, which stays plain PyTorch autograd:
+the custom op returns d/d weights and autograd carries it into `_weight_network`.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+from scipy.spatial import Delaunay
+
+from .utils import quadrature
+
+
+class MeshHandler(nn.Module):
+
+    def __init__(self,
+                 input_points,
+                 input_weights=None,
+                 input_adjacency=None,
+                 weight_activation='Sigmoid',
+                 normalize_weights=False):
+        super().__init__()
+
+        if input_weights is not None:                            # mesh_handler.py:31-32
+            assert input_points.shape[0] == input_weights.shape[0]
+
+        self._points = nn.ParameterList([nn.Parameter(input_points, requires_grad=False)])
+        self.point_seq = None
+        self._downsample_map = []
+
+        self._weight_activation = getattr(nn, weight_activation)
+        self._normalize_weights = normalize_weights
+
+        if input_adjacency is not None:
+            adj = torch.as_tensor(input_adjacency).long()
+        else:                                                    # mesh_handler.py:47
+            adj = torch.from_numpy(Delaunay(input_points.detach().cpu().numpy()).simplices).long()
+        self._adjacency = nn.ParameterList([nn.Parameter(adj, requires_grad=False)])
+
+        self._spatial_dim = input_points.shape[1]
+        self._current_index = 0
+
+    # -- cursor (mesh_handler.py:55-66) ---------------------------------------------------------
+    def reset(self, mirror=False):
+        self._current_index = 0 + mirror * self._radix
+
+    def step(self):
+        self._current_index = (self._current_index + 1) % (self._num_levels)
+
+    def _get_index(self, offset=0):
+        return self._radix - abs(self._radix - (self._current_index + offset))
+
+    # -- accessors (mesh_handler.py:68-83) ------------------------------------------------------
+    def input_points(self):
+        return self._points[self._get_index()]
+
+    def output_points(self):
+        return self._points[self._get_index(1)]
+
+    def weights(self):
+        return self.weight_map(self._points[self._get_index()])
+
+    def adjacency(self):
+        return self._adjacency[self._get_index()]
+
+    def get_downsample_map(self, key_num):
+        return list(dsm for dsm in self._downsample_map if len(dsm) == key_num)[0]
+
+    # -- learned quadrature weights (mesh_handler.py:85-116) ------------------------------------
+    def build_weight_map(self, element_size=3, dimension=2, const=False):
+        if const:
+            weight_map = lambda points: torch.ones(points.shape[0], device=points.device)
+        else:
+            self._weight_network = nn.Sequential(
+                nn.Linear(element_size * dimension, 8),
+                self._weight_activation(),
+                nn.Linear(8, 8),
+                self._weight_activation(),
+                nn.Linear(8, 8),
+                self._weight_activation(),
+                nn.Linear(8, element_size),
+                self._weight_activation(),
+            )
+
+            def weight_map(points):
+                element_list = self.adjacency()
+                el_points = points[element_list].reshape(-1, element_size * dimension)
+                el_weights = self._weight_network(el_points)
+                weights = torch.zeros(points.shape[0], device=points.device)
+                # out-of-place scatter: same sums as the reference's scatter_add_ (mesh_handler.py:110)
+                return weights.scatter_add(0, element_list.reshape(-1), el_weights.reshape(-1))
+
+        self.weight_map = weight_map
+
+    # -- hierarchy construction (mesh_handler.py:161-212) ---------------------------------------
+    def construct(self, point_seq, mirror=False, quad_map='param_quad', weight_map=True, quad_args=None):
+        if quad_args is None:
+            quad_args = {"point_args": {}, "weight_args": {"const": False}}
+
+        if weight_map is True:
+            self.build_weight_map(**quad_args.get("weight_args", {"const": False}))
+
+        quad_fn = getattr(quadrature, quad_map)
+
+        assert point_seq[0] == self._points[0].shape[0]          # mesh_handler.py:171
+
+        self._num_meshes = len(point_seq)
+        self._num_levels = len(point_seq) - 1
+        self._radix = len(point_seq) - 1
+        self.point_seq = list(point_seq).copy()
+
+        for i, num_points in enumerate(point_seq[1:]):
+            points, weights, *elim_map = quad_fn(self._points[i].detach().cpu().clone(), num_points,
+                                                 **quad_args.get("point_args", {}))
+            points = np.asarray(points)
+            new = torch.from_numpy(points).to(self._points[0].device)
+            self._points.append(nn.Parameter(new, requires_grad=False))
+            if num_points != points.shape[0]:
+                self.point_seq[i + 1] = points.shape[0]
+            adj = torch.from_numpy(Delaunay(points).simplices).long().to(self._points[0].device)
+            self._adjacency.append(nn.Parameter(adj, requires_grad=False))
+            if len(elim_map) > 0:
+                self._downsample_map.append(elim_map[0])
+
+        if mirror:                                               # mesh_handler.py:209-210
+            self._num_levels *= 2
+
+        return self

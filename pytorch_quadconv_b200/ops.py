@@ -1,0 +1,405 @@
+"""
+torch.library custom ops over the C ABI (include/quadconv_b200.h).
+
+PyTorch is plumbing here: it owns device memory, the current stream and autograd bookkeeping; every
+FLOP of the path runs in libquadconv_b200.so.  Ops (namespace `quadconv_b200`):
+
+    build_pairs     neighbour search           <- QuadConv._compute_eval_indices, quadconv.py:165-199
+    pairs_to_tables tables from a given list   <- cached eval_indices Parameter, quadconv.py:186-188
+    qc_forward      fused layer forward        <- QuadConv.forward/_integrate, quadconv.py:238-265,:213-227
+    qc_backward     fused layer backward       <- autograd of the above (the reference has none)
+    segmax / gather_pool (+ backward)          <- Mesh_MaxPool.forward, mesh_pool.py:88-93
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi as C
+
+Tensor = torch.Tensor
+
+
+def _hp(h: int) -> int:
+    for v in (4, 8, 16, 32):
+        if h <= v:
+            return v
+    raise RuntimeError(f"filter MLP last hidden width {h} > 32 is not implemented by the sm_100a kernels")
+
+
+def _bp(B: int) -> int:
+    bp = 1
+    while bp < B and bp < 32:
+        bp <<= 1
+    return bp
+
+
+def _nblk(B: int) -> int:
+    return (B + 31) // 32
+
+
+def _f32c(t: Tensor, name: str) -> Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32 (got {t.dtype}); the fp32 path is the only one built")
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# pair tables
+# ---------------------------------------------------------------------------------------------
+
+def _scan(counts: Tensor) -> Tensor:
+    n = counts.numel()
+    out = torch.empty(n + 1, dtype=torch.int32, device=counts.device)
+    C.check(C.lib().qc_exclusive_scan_i32(C.ptr(counts), n, C.ptr(out), C.stream()), "qc_exclusive_scan_i32")
+    return out
+
+
+def _csc(pair_row: Tensor, pair_col: Tensor, Ni: int) -> Tuple[Tensor, Tensor, Tensor]:
+    P = pair_row.numel()
+    dev = pair_row.device
+    counts = torch.empty(Ni, dtype=torch.int32, device=dev)
+    C.check(C.lib().qc_csc_count(C.ptr(pair_col), P, Ni, C.ptr(counts), C.stream()), "qc_csc_count")
+    csc_ptr = _scan(counts)
+    cursor = torch.empty(Ni, dtype=torch.int32, device=dev)
+    csc_pair = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    csc_row = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    C.check(C.lib().qc_csc_fill(C.ptr(pair_row), C.ptr(pair_col), P, Ni, C.ptr(csc_ptr), C.ptr(cursor),
+                                C.ptr(csc_pair), C.ptr(csc_row), C.stream()), "qc_csc_fill")
+    return csc_ptr, csc_pair, csc_row
+
+
+@torch.library.custom_op("quadconv_b200::build_pairs", mutates_args=())
+def build_pairs(out_pts: Tensor, in_pts: Tensor, radius: float, same: bool) -> List[Tensor]:
+    """Grid-binned neighbour search.  Returns
+    [eval_indices int64 [P,2], pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in]."""
+    out_pts = _f32c(out_pts, "output points")
+    in_pts = _f32c(in_pts, "input points")
+    if same:
+        out_pts = in_pts
+    No, d = out_pts.shape
+    Ni = in_pts.shape[0]
+    dev = in_pts.device
+    L = C.lib()
+    r32 = float(np.float32(radius))  # quadconv.py:182: python scalar demoted to fp32
+    ws_bytes = L.qc_search_workspace_bytes(No, Ni, d)
+    if ws_bytes == 0:
+        raise RuntimeError(f"neighbour search supports spatial_dim 1..3 (got {d})")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    counts = torch.empty(No, dtype=torch.int32, device=dev)
+    order_out = torch.empty(No, dtype=torch.int32, device=dev)
+    order_in = torch.empty(Ni, dtype=torch.int32, device=dev)
+    C.check(L.qc_search_count(C.ptr(out_pts), C.ptr(in_pts), No, Ni, d, r32, C.ptr(ws), ws_bytes,
+                              C.ptr(counts), C.ptr(order_out), C.ptr(order_in), C.stream()), "qc_search_count")
+    row_ptr = _scan(counts)
+    P = int(row_ptr[-1].item())  # data-dependent size, like torch.nonzero in the reference
+    ev = torch.empty((P, 2), dtype=torch.int64, device=dev)
+    pair_row = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    pair_col = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    if P > 0:
+        C.check(L.qc_search_fill(C.ptr(out_pts), C.ptr(in_pts), No, Ni, d, r32, C.ptr(ws), ws_bytes,
+                                 C.ptr(row_ptr), C.ptr(ev), C.ptr(pair_row), C.ptr(pair_col), C.stream()),
+                "qc_search_fill")
+    pair_row, pair_col = pair_row[:P], pair_col[:P]
+    csc_ptr, csc_pair, csc_row = _csc(pair_row, pair_col, Ni)
+    return [ev, pair_row, pair_col, row_ptr, csc_ptr, csc_pair[:P], csc_row[:P], order_out, order_in]
+
+
+@build_pairs.register_fake
+def _(out_pts, in_pts, radius, same):
+    ctx = torch.library.get_ctx()
+    P = ctx.new_dynamic_size()
+    No, Ni = out_pts.shape[0], in_pts.shape[0]
+    i32 = dict(dtype=torch.int32, device=in_pts.device)
+    return [in_pts.new_empty((P, 2), dtype=torch.int64), in_pts.new_empty(P, **i32), in_pts.new_empty(P, **i32),
+            in_pts.new_empty(No + 1, **i32), in_pts.new_empty(Ni + 1, **i32), in_pts.new_empty(P, **i32),
+            in_pts.new_empty(P, **i32), in_pts.new_empty(No, **i32), in_pts.new_empty(Ni, **i32)]
+
+
+@torch.library.custom_op("quadconv_b200::pairs_to_tables", mutates_args=())
+def pairs_to_tables(eval_indices: Tensor, n_out: int, n_in: int) -> List[Tensor]:
+    """Tables for a pair list supplied by the caller (e.g. a loaded `eval_indices` Parameter).
+    Returns [pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row]."""
+    if eval_indices.dtype != torch.int64 or eval_indices.dim() != 2 or eval_indices.shape[1] != 2:
+        raise RuntimeError("eval_indices must be int64 [P,2]")
+    ev = eval_indices.contiguous()
+    P = ev.shape[0]
+    dev = ev.device
+    counts = torch.empty(n_out, dtype=torch.int32, device=dev)
+    pair_row = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    pair_col = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    C.check(C.lib().qc_pairs_to_csr(C.ptr(ev), P, n_out, n_in, C.ptr(counts), C.ptr(pair_row), C.ptr(pair_col),
+                                    C.ptr(err), C.stream()), "qc_pairs_to_csr")
+    if int(err.item()) != 0:
+        raise RuntimeError("eval_indices must be sorted by output index and within range")
+    row_ptr = _scan(counts)
+    pair_row, pair_col = pair_row[:P], pair_col[:P]
+    csc_ptr, csc_pair, csc_row = _csc(pair_row, pair_col, n_in)
+    return [pair_row, pair_col, row_ptr, csc_ptr, csc_pair[:P], csc_row[:P]]
+
+
+@pairs_to_tables.register_fake
+def _(eval_indices, n_out, n_in):
+    P = eval_indices.shape[0]
+    i32 = dict(dtype=torch.int32, device=eval_indices.device)
+    e = eval_indices.new_empty
+    return [e(P, **i32), e(P, **i32), e(n_out + 1, **i32), e(n_in + 1, **i32), e(P, **i32), e(P, **i32)]
+
+
+# ---------------------------------------------------------------------------------------------
+# fused QuadConv layer
+# ---------------------------------------------------------------------------------------------
+
+def _pack(x: Tensor) -> Tensor:
+    B, Cc, N = x.shape
+    xp = torch.empty((_nblk(B), N, Cc, _bp(B)), dtype=torch.float32, device=x.device)
+    C.check(C.lib().qc_pack_features(C.ptr(x), B, Cc, N, C.ptr(xp), C.stream()), "qc_pack_features")
+    return xp
+
+
+def _unpack(xp: Tensor, B: int, Cc: int, N: int, bias: Optional[Tensor]) -> Tensor:
+    x = torch.empty((B, Cc, N), dtype=torch.float32, device=xp.device)
+    C.check(C.lib().qc_unpack_features(C.ptr(xp), B, Cc, N, C.ptr(bias), C.ptr(x), C.stream()), "qc_unpack_features")
+    return x
+
+
+@torch.library.custom_op("quadconv_b200::qc_forward", mutates_args=())
+def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor,
+               hidden_ws: Sequence[Tensor], w_last: Tensor, bias: Optional[Tensor],
+               pair_row: Tensor, pair_col: Tensor, row_ptr: Tensor, order_out: Optional[Tensor],
+               in_channels: int, out_channels: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Returns (out [B,Co,No], phi [P,HP], packed features) -- the last two are saved for backward."""
+    features = _f32c(features, "features")
+    out_pts, in_pts, quad_w = _f32c(out_pts, "points"), _f32c(in_pts, "points"), _f32c(quad_w, "weights")
+    hidden_ws = [_f32c(w, "filter weight") for w in hidden_ws]
+    w_last = _f32c(w_last, "filter weight")
+    B, Ci, Ni = features.shape
+    No, d = out_pts.shape
+    Co = out_channels
+    if Ci != in_channels or in_pts.shape[0] != Ni:
+        raise RuntimeError(f"features {tuple(features.shape)} do not match in_channels={in_channels}, in_points={in_pts.shape[0]}")
+    H = w_last.shape[1]
+    if w_last.shape[0] != Ci * Co:
+        raise RuntimeError("last filter layer must have in_channels*out_channels outputs")
+    HP = _hp(H)
+    P = pair_row.numel()
+    dev = features.device
+    L = C.lib()
+    st = C.stream()
+    mlp = C.make_mlp(d, hidden_ws)
+    phi = torch.empty((max(P, 1), HP), dtype=torch.float32, device=dev)
+    C.check(L.qc_pair_phi_fwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row), C.ptr(pair_col),
+                              P, d, mlp, HP, C.ptr(phi), st), "qc_pair_phi_fwd")
+    xp = _pack(features)
+    CoP = (Co + 3) & ~3
+    W2 = torch.empty((Ci * H, CoP), dtype=torch.float32, device=dev)
+    C.check(L.qc_repack_wlast(C.ptr(w_last), Ci, Co, H, HP, 0, C.ptr(W2), st), "qc_repack_wlast")
+    yp = torch.empty((_nblk(B), No, Co, _bp(B)), dtype=torch.float32, device=dev)
+    C.check(L.qc_contract(C.ptr(xp), Ni, Ci, C.ptr(row_ptr), C.ptr(pair_col), None, C.ptr(phi), H, HP,
+                          C.ptr(W2), Co, C.ptr(order_out), No, B, C.ptr(yp), None, None, st), "qc_contract")
+    b2 = None
+    if bias is not None:
+        b2 = _f32c(bias, "bias").reshape(Co, No)
+    out = _unpack(yp, B, Co, No, b2)
+    return out, phi, xp
+
+
+@qc_forward.register_fake
+def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair_col, row_ptr, order_out,
+      in_channels, out_channels):
+    B, Ci, Ni = features.shape
+    No = out_pts.shape[0]
+    HP = _hp(w_last.shape[1])
+    return (features.new_empty((B, out_channels, No)), features.new_empty((pair_row.shape[0], HP)),
+            features.new_empty((_nblk(B), Ni, Ci, _bp(B))))
+
+
+@torch.library.custom_op("quadconv_b200::qc_backward", mutates_args=())
+def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor,
+                hidden_ws: Sequence[Tensor], w_last: Tensor, pair_row: Tensor, pair_col: Tensor,
+                row_ptr: Tensor, csc_ptr: Tensor, csc_pair: Tensor, csc_row: Tensor,
+                order_out: Optional[Tensor], order_in: Optional[Tensor], batch: int, in_channels: int,
+                out_channels: int, has_bias: bool) -> List[Tensor]:
+    """Returns [d_features, d_quad_w, d_w_last, d_bias (or empty), *d_hidden_ws]."""
+    grad_out = _f32c(grad_out, "grad_out")
+    hidden_ws = [_f32c(w, "filter weight") for w in hidden_ws]
+    w_last = _f32c(w_last, "filter weight")
+    B, Ci, Co = batch, in_channels, out_channels
+    Ni, No, d = in_pts.shape[0], out_pts.shape[0], out_pts.shape[1]
+    H = w_last.shape[1]
+    HP = _hp(H)
+    P = pair_row.numel()
+    dev = grad_out.device
+    L = C.lib()
+    st = C.stream()
+    f32 = dict(dtype=torch.float32, device=dev)
+
+    gp = _pack(grad_out)
+    d_bias = torch.empty(0, **f32)
+    if has_bias:
+        d_bias = torch.empty((1, Co, No), **f32)
+        C.check(L.qc_batch_sum(C.ptr(grad_out), B, Co, No, C.ptr(d_bias), st), "qc_batch_sum")
+
+    # d phi (grouped by out point), then back through the hidden layers per pair
+    W3 = torch.empty((Co, Ci, HP), **f32)
+    C.check(L.qc_repack_wlast(C.ptr(w_last), Ci, Co, H, HP, 2, C.ptr(W3), st), "qc_repack_wlast")
+    dphi = torch.zeros((max(P, 1), HP), **f32)
+    C.check(L.qc_dphi(C.ptr(xp), Ni, Ci, C.ptr(gp), Co, C.ptr(row_ptr), C.ptr(pair_col), C.ptr(W3), H, HP,
+                      C.ptr(order_out), No, B, C.ptr(dphi), st), "qc_dphi")
+    d_hidden = [torch.zeros_like(w) for w in hidden_ws]
+    d_quad_w = torch.zeros(Ni, **f32)
+    mlp = C.make_mlp(d, hidden_ws)
+    import ctypes
+    dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
+    C.check(L.qc_pair_phi_bwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row), C.ptr(pair_col),
+                              P, d, mlp, HP, C.ptr(dphi), dptrs, C.ptr(d_quad_w), st), "qc_pair_phi_bwd")
+
+    # d features (grouped by in point through the CSC tables) + d W_last in the same pass
+    CiP = (Ci + 3) & ~3
+    W2t = torch.empty((Co * H, CiP), **f32)
+    C.check(L.qc_repack_wlast(C.ptr(w_last), Ci, Co, H, HP, 1, C.ptr(W2t), st), "qc_repack_wlast")
+    dW2 = torch.zeros((Co * H, CiP), **f32)
+    dxp = torch.empty((_nblk(B), Ni, Ci, _bp(B)), **f32)
+    C.check(L.qc_contract(C.ptr(gp), No, Co, C.ptr(csc_ptr), C.ptr(csc_row), C.ptr(csc_pair), C.ptr(phi), H, HP,
+                          C.ptr(W2t), Ci, C.ptr(order_in), Ni, B, C.ptr(dxp), C.ptr(xp), C.ptr(dW2), st),
+            "qc_contract (backward)")
+    d_w_last = torch.zeros((Ci * Co, H), **f32)
+    C.check(L.qc_unpack_dwlast(C.ptr(dW2), Ci, Co, H, C.ptr(d_w_last), st), "qc_unpack_dwlast")
+    d_features = _unpack(dxp, B, Ci, Ni, None)
+    return [d_features, d_quad_w, d_w_last, d_bias] + d_hidden
+
+
+@qc_backward.register_fake
+def _(grad_out, xp, phi, out_pts, in_pts, quad_w, hidden_ws, w_last, pair_row, pair_col, row_ptr, csc_ptr,
+      csc_pair, csc_row, order_out, order_in, batch, in_channels, out_channels, has_bias):
+    Ni, No = in_pts.shape[0], out_pts.shape[0]
+    e = grad_out.new_empty
+    return [e((batch, in_channels, Ni)), e(Ni), e(w_last.shape),
+            e((1, out_channels, No)) if has_bias else e(0)] + [e(w.shape) for w in hidden_ws]
+
+
+class _QuadConvFn(torch.autograd.Function):
+    """Autograd glue: forward/backward are the two custom ops above."""
+
+    @staticmethod
+    def forward(ctx, features, quad_w, w_last, bias, tables, dims, *hidden_ws):
+        out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = tables
+        Ci, Co = dims
+        out, phi, xp = qc_forward(features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
+                                  pair_col, row_ptr, order_out, Ci, Co)
+        ctx.save_for_backward(xp, phi, quad_w, w_last, *hidden_ws)
+        ctx.tables = tables
+        ctx.dims = (features.shape[0], Ci, Co, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xp, phi, quad_w, w_last, *hidden_ws = ctx.saved_tensors
+        out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = ctx.tables
+        B, Ci, Co, has_bias = ctx.dims
+        res = qc_backward(grad_out, xp, phi, out_pts, in_pts, quad_w, list(hidden_ws), w_last, pair_row, pair_col,
+                          row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in, B, Ci, Co, has_bias)
+        d_features, d_quad_w, d_w_last, d_bias = res[:4]
+        d_hidden = res[4:]
+        return (d_features, d_quad_w, d_w_last, d_bias if has_bias else None, None, None, *d_hidden)
+
+
+def quadconv_apply(features, quad_w, hidden_ws, w_last, bias, tables, in_channels, out_channels):
+    return _QuadConvFn.apply(features, quad_w, w_last, bias, tables, (in_channels, out_channels), *hidden_ws)
+
+
+# ---------------------------------------------------------------------------------------------
+# Mesh_MaxPool
+# ---------------------------------------------------------------------------------------------
+
+@torch.library.custom_op("quadconv_b200::segmax", mutates_args=())
+def segmax(x: Tensor, group: Tensor, grp_ptr: Tensor, grp_mem: Tensor, n_out: int) -> Tensor:
+    x = _f32c(x, "pool input")
+    B, Cc, Nin = x.shape
+    out = torch.empty((B, Cc, n_out), dtype=torch.float32, device=x.device)
+    C.check(C.lib().qc_segmax_fwd(C.ptr(x), C.ptr(grp_ptr), C.ptr(grp_mem), B * Cc, Nin, n_out, C.ptr(out),
+                                  C.stream()), "qc_segmax_fwd")
+    return out
+
+
+@segmax.register_fake
+def _(x, group, grp_ptr, grp_mem, n_out):
+    return x.new_empty((x.shape[0], x.shape[1], n_out))
+
+
+@torch.library.custom_op("quadconv_b200::segmax_bwd", mutates_args=())
+def segmax_bwd(x: Tensor, out: Tensor, grad_out: Tensor, group: Tensor, grp_ptr: Tensor, grp_mem: Tensor) -> Tensor:
+    x, out, grad_out = _f32c(x, "x"), _f32c(out, "out"), _f32c(grad_out, "grad")
+    B, Cc, Nin = x.shape
+    gx = torch.empty_like(x)
+    C.check(C.lib().qc_segmax_bwd(C.ptr(x), C.ptr(out), C.ptr(grad_out), C.ptr(group), C.ptr(grp_ptr),
+                                  C.ptr(grp_mem), B * Cc, Nin, out.shape[2], C.ptr(gx), C.stream()), "qc_segmax_bwd")
+    return gx
+
+
+@segmax_bwd.register_fake
+def _(x, out, grad_out, group, grp_ptr, grp_mem):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("quadconv_b200::gather_pool", mutates_args=())
+def gather_pool(x: Tensor, index: Tensor) -> Tensor:
+    x = _f32c(x, "pool input")
+    B, Cc, Nin = x.shape
+    n_out = index.numel()
+    out = torch.empty((B, Cc, n_out), dtype=torch.float32, device=x.device)
+    C.check(C.lib().qc_gather_fwd(C.ptr(x), C.ptr(index), B * Cc, Nin, n_out, C.ptr(out), C.stream()), "qc_gather_fwd")
+    return out
+
+
+@gather_pool.register_fake
+def _(x, index):
+    return x.new_empty((x.shape[0], x.shape[1], index.numel()))
+
+
+@torch.library.custom_op("quadconv_b200::gather_pool_bwd", mutates_args=())
+def gather_pool_bwd(grad_out: Tensor, grp_ptr: Tensor, grp_mem: Tensor, n_coarse: int) -> Tensor:
+    grad_out = _f32c(grad_out, "grad")
+    B, Cc, Nf = grad_out.shape
+    gx = torch.empty((B, Cc, n_coarse), dtype=torch.float32, device=grad_out.device)
+    C.check(C.lib().qc_gather_bwd(C.ptr(grad_out), C.ptr(grp_ptr), C.ptr(grp_mem), B * Cc, Nf, n_coarse,
+                                  C.ptr(gx), C.stream()), "qc_gather_bwd")
+    return gx
+
+
+@gather_pool_bwd.register_fake
+def _(grad_out, grp_ptr, grp_mem, n_coarse):
+    return grad_out.new_empty((grad_out.shape[0], grad_out.shape[1], n_coarse))
+
+
+def _segmax_setup(ctx, inputs, output):
+    x, group, grp_ptr, grp_mem, n_out = inputs
+    ctx.save_for_backward(x, output, group, grp_ptr, grp_mem)
+
+
+def _segmax_backward(ctx, grad):
+    x, out, group, grp_ptr, grp_mem = ctx.saved_tensors
+    return segmax_bwd(x, out, grad, group, grp_ptr, grp_mem), None, None, None, None
+
+
+segmax.register_autograd(_segmax_backward, setup_context=_segmax_setup)
+
+
+class _GatherPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, index, grp_ptr, grp_mem):
+        ctx.save_for_backward(grp_ptr, grp_mem)
+        ctx.n_coarse = x.shape[2]
+        return gather_pool(x, index)
+
+    @staticmethod
+    def backward(ctx, grad):
+        grp_ptr, grp_mem = ctx.saved_tensors
+        return gather_pool_bwd(grad, grp_ptr, grp_mem, ctx.n_coarse), None, None, None
+
+
+def gather_pool_apply(x, index, grp_ptr, grp_mem):
+    return _GatherPoolFn.apply(x, index, grp_ptr, grp_mem)

@@ -1,0 +1,170 @@
+"""
+QuadConv -- drop-in for torch_quadconv.QuadConv (reference torch_quadconv/quadconv.py:25-265).
+
+Same keyword-only constructor, `forward(mesh, features)` signature, public attributes and parameter
+layout (`filter.{0,2,...}.weight`, `bias` [1,Co,No], `eval_indices` int64 [P,2] registered on first
+forward).  The work is done by hand-written sm_100a kernels behind a C ABI (include/quadconv_b200.h):
+
+    reference (ATen composition)                               here
+    ---------------------------------------------------------  --------------------------------
+    dense [No,Ni,d] subtract + vector_norm + nonzero (:178-183) grid-binned search, bit-exact
+    weights gather, eval_locs, filter MLP (:247-257)            per-pair hidden layers -> phi
+    [P,Ci,Co] filters, gather, einsum, scatter_add_ (:213-227)  fused contraction, nothing P-sized
+    autograd                                                    fused analytic backward
+
+Deliberate deviations (documented in DESIGN.md): `filter_mode` other than 'single' raises
+(`share_in` raises AttributeError upstream too, `nested` computes a scrambled layout there);
+tensors must live on a CUDA device -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .utils.misc import Sin
+
+
+class QuadConv(nn.Module):
+
+    def __init__(self, *,
+                 spatial_dim,
+                 in_points,
+                 out_points,
+                 in_channels,
+                 out_channels,
+                 filter_seq,
+                 filter_mode='single',
+                 decay_param=None,
+                 bias=False,
+                 output_same=False,
+                 cache=True,
+                 verbose=False):
+        super().__init__()
+
+        assert spatial_dim > 0                                   # quadconv.py:44
+
+        self.spatial_dim = spatial_dim
+        self.in_points = in_points
+        self.out_points = out_points
+        self.out_channels = out_channels
+        self.in_channels = in_channels
+        self.output_same = output_same
+
+        self.cache = cache
+        self.cached = False
+        self.verbose = verbose
+
+        if decay_param is None:                                  # quadconv.py:59-62
+            self.decay_param = 4 / np.sqrt(self.in_points)
+        else:
+            self.decay_param = decay_param
+
+        self._init_filter(filter_seq, filter_mode)
+
+        if bias:                                                 # quadconv.py:68-72
+            b = torch.empty(1, self.out_channels, self.out_points)
+            self.bias = nn.Parameter(nn.init.xavier_uniform_(b, gain=2), requires_grad=True)
+        else:
+            self.bias = None
+
+        self._tables = None
+        self._tables_key = None
+
+    # -- filter -------------------------------------------------------------------------------
+    def _init_filter(self, filter_seq, filter_mode):
+        if filter_mode == 'single':                              # quadconv.py:86-91
+            mlp_spec = (self.spatial_dim, *filter_seq, self.in_channels * self.out_channels)
+            self.filter = self._create_mlp(mlp_spec)
+            # H/G evaluate the filter densely with plain torch ops; they exist for API parity and
+            # for inspection -- forward() never materialises this [P,Ci,Co] tensor.
+            self.H = lambda z: self.filter(z).reshape(-1, self.in_channels, self.out_channels)
+        elif filter_mode in ('share_in', 'nested'):
+            raise NotImplementedError(
+                f"filter_mode='{filter_mode}' is outside the B200 hot path (SURVEY.md 8f-4): upstream "
+                "'share_in' raises AttributeError and 'nested' interleaves pair and channel indices")
+        else:                                                    # quadconv.py:116-117
+            raise ValueError(f'core::modules::quadconv: Filter mode {filter_mode} is not supported.')
+        self.G = self.H                                          # quadconv.py:120
+
+    def _create_mlp(self, mlp_channels):                         # quadconv.py:130-145
+        activation = Sin()
+        mlp = nn.Sequential()
+        for i in range(len(mlp_channels) - 2):
+            mlp.append(nn.Linear(mlp_channels[i], mlp_channels[i + 1], bias=False))
+            mlp.append(activation)
+        mlp.append(nn.Linear(mlp_channels[-2], mlp_channels[-1], bias=False))
+        return mlp
+
+    def _bump_arg(self, z):                                      # quadconv.py:153-154 (API parity)
+        return torch.linalg.vector_norm(z, dim=(2), keepdims=True)
+
+    # -- neighbour search -----------------------------------------------------------------------
+    def _points(self, mesh):
+        input_points = mesh.input_points()
+        output_points = input_points if self.output_same else mesh.output_points()
+        assert input_points.shape[0] == self.in_points, f'{input_points.shape[0]} != {self.in_points}'
+        assert output_points.shape[0] == self.out_points, f'{output_points.shape[0]} != {self.out_points}'
+        return output_points, input_points
+
+    def _compute_eval_indices(self, mesh):
+        """quadconv.py:165-199, on the GPU.  Returns the [P,2] int64 pair list (reference order)."""
+        output_points, input_points = self._points(mesh)
+        if not input_points.is_cuda:
+            raise RuntimeError("pytorch_quadconv_b200 has no CPU path: move the MeshHandler to a CUDA device")
+        res = ops.build_pairs(output_points.detach(), input_points.detach(), float(self.decay_param),
+                              bool(self.output_same))
+        idx = res[0]
+        self._tables = tuple(res[1:])
+        self._tables_key = (output_points.data_ptr(), input_points.data_ptr(), idx.data_ptr())
+
+        if self.cache:                                           # quadconv.py:186-188
+            self.eval_indices = nn.Parameter(idx, requires_grad=False)
+            self._tables_key = (output_points.data_ptr(), input_points.data_ptr(), self.eval_indices.data_ptr())
+            self.cached = True
+
+        if self.verbose:                                         # quadconv.py:190-197 (same statistics)
+            print(f"\nQuadConv eval_indices: {idx.numel()}")
+            hist = torch.histc(idx[:, 1].to(torch.float32), bins=self.out_points, min=0, max=self.out_points - 1)
+            print(f"Max support points: {torch.max(hist)}")
+            print(f"Min support points: {torch.min(hist)}")
+            print(f"Avg support points: {torch.sum(hist)/hist.numel()}")
+
+        return idx
+
+    def _tables_for_cached(self, output_points, input_points):
+        """Tables for an `eval_indices` that did not come from this module's own search (a loaded
+        state_dict, or the two lines of quadconv.py:187-188 run by the caller)."""
+        key = (output_points.data_ptr(), input_points.data_ptr(), self.eval_indices.data_ptr())
+        if self._tables is None or self._tables_key != key:
+            t = ops.pairs_to_tables(self.eval_indices.data, self.out_points, self.in_points)
+            self._tables = tuple(t) + (None, None)
+            self._tables_key = key
+        return self._tables
+
+    # -- forward --------------------------------------------------------------------------------
+    def forward(self, mesh, features):
+        """features: (batch, in_channels, in_points) fp32 CUDA -> (batch, out_channels, out_points)."""
+        output_points, input_points = self._points(mesh)
+
+        if self.cached:                                          # quadconv.py:241-244
+            tables = self._tables_for_cached(output_points, input_points)
+        else:
+            self._compute_eval_indices(mesh)
+            tables = self._tables
+
+        weights = mesh.weights()                                 # quadconv.py:247 (gather fused)
+
+        if not self.output_same:                                 # quadconv.py:253-254
+            mesh.step()
+
+        pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = tables
+        linears = [m for m in self.filter if isinstance(m, nn.Linear)]
+        hidden_ws = [m.weight for m in linears[:-1]]
+        w_last = linears[-1].weight
+
+        full = (output_points.detach(), input_points.detach(), pair_row, pair_col, row_ptr, csc_ptr, csc_pair,
+                csc_row, order_out, order_in)
+        return ops.quadconv_apply(features, weights, hidden_ws, w_last, self.bias, full,
+                                  self.in_channels, self.out_channels)

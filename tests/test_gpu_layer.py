@@ -1,0 +1,201 @@
+"""GPU: fused QuadConv forward/backward through the public nn.Module API (which calls the C ABI)
+against the golden vectors of the live reference and against the oracle on fresh shapes.
+Tolerance (north_star): 1e-5 normwise relative error in fp32 mode, written here as TOL."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _build_from_golden(L, d, fs, bias):
+    import pytorch_quadconv_b200 as q
+    pts = torch.from_numpy(L["pts"])
+    n, ci, co = pts.shape[0], int(L["ci"]), int(L["co"])
+    wa = {"const": False}
+    if d == 3:
+        wa = {"element_size": 4, "dimension": 3, "const": False}
+    mesh = q.MeshHandler(pts).construct([n], quad_args={"point_args": {}, "weight_args": wa})
+    mesh.load_state_dict({k[5:]: torch.from_numpy(L[k]) for k in L.files if k.startswith("mesh/")})
+    layer = q.QuadConv(spatial_dim=d, in_points=n, out_points=n, in_channels=ci, out_channels=co,
+                       filter_seq=fs, bias=bias, output_same=True, decay_param=float(L["r"]))
+    sd = {f"filter.{2 * l}.weight": torch.from_numpy(L[f"W{l}"]) for l in range(len(fs) + 1)}
+    if bias:
+        sd["bias"] = torch.from_numpy(L["bias"])
+    layer.load_state_dict(sd)
+    return mesh.cuda(), layer.cuda()
+
+
+@pytest.mark.parametrize("name,d,fs,bias", [("layer_2d", 2, [4, 4], True), ("layer_2d_wide", 2, [8, 8], False),
+                                            ("layer_3d", 3, [8], False), ("layer_1to2", 2, [5, 6, 7], True)])
+def test_layer_matches_reference_golden(cuda_lib, name, d, fs, bias):
+    L = load_golden(name)
+    mesh, layer = _build_from_golden(L, d, fs, bias)
+    x = torch.from_numpy(L["x"]).cuda().requires_grad_()
+    y = layer(mesh, x)
+    assert y.shape == tuple(L["y"].shape) and y.dtype == torch.float32
+    assert layer.cached and layer.eval_indices.dtype == torch.int64
+    assert np.array_equal(layer.eval_indices.cpu().numpy(), L["pairs"])
+    assert "eval_indices" in layer.state_dict()                            # appears after the first forward, like the reference
+    assert relerr(y.detach().cpu().numpy(), L["y"]) < TOL
+    (y * torch.from_numpy(L["grad_out"]).cuda()).sum().backward()
+    assert relerr(x.grad.cpu().numpy(), L["dx"]) < TOL
+    for l in range(len(fs) + 1):
+        got = layer.filter[2 * l].weight.grad.cpu().numpy()
+        assert relerr(got, L[f"dW{l}"]) < TOL, f"dW{l}"
+    if bias:
+        assert relerr(layer.bias.grad.cpu().numpy(), L["dbias"]) < TOL
+    # d/d quadrature weights flows on into MeshHandler._weight_network through torch autograd
+    for k, p in mesh.named_parameters():
+        if p.requires_grad:
+            assert relerr(p.grad.cpu().numpy(), L["meshgrad/" + k]) < 5e-5, k
+
+
+def test_dquadw_direct(cuda_lib):
+    L = load_golden("layer_2d")
+    mesh, layer = _build_from_golden(L, 2, [4, 4], True)
+    w = torch.from_numpy(L["quad_w"]).cuda().requires_grad_()
+    mesh.weight_map = lambda points: w
+    x = torch.from_numpy(L["x"]).cuda()
+    y = layer(mesh, x)
+    (y * torch.from_numpy(L["grad_out"]).cuda()).sum().backward()
+    assert relerr(w.grad.cpu().numpy(), L["dquad_w"]) < TOL
+
+
+def _oracle_case(d, n, ci, co, B, fs, r, bias, seed, n_out=None):
+    """Fresh seeded problem; reference values from the oracle (torch fp32 restatement)."""
+    from oracle import quadconv_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.rand(n, d, generator=g)
+    out_pts = pts if n_out is None else pts[torch.randperm(n, generator=g)[:n_out]].contiguous()
+    x = torch.randn(B, ci, n, generator=g).requires_grad_()
+    qw = (torch.rand(n, generator=g) + 0.5).requires_grad_()
+    dims = [d] + list(fs) + [ci * co]
+    ws = [(torch.randn(dims[l + 1], dims[l], generator=g) / np.sqrt(dims[l])).requires_grad_()
+          for l in range(len(dims) - 1)]
+    b = torch.randn(1, co, out_pts.shape[0], generator=g).requires_grad_() if bias else None
+    pairs = torch.from_numpy(O.eval_indices_c(out_pts.numpy(), pts.numpy(), r))
+    y = O.quadconv_forward(out_pts, pts, qw, ws, x, pairs, ci, co, b)
+    go = torch.randn(y.shape, generator=g)
+    (y * go).sum().backward()
+    return dict(pts=pts, out_pts=out_pts, x=x, qw=qw, ws=ws, b=b, pairs=pairs, y=y.detach(), go=go)
+
+
+class _StubMesh:
+    """Minimal handler exposing the accessors QuadConv reads (mesh_handler.py:68-78)."""
+
+    def __init__(self, in_pts, out_pts, w):
+        self._in, self._out, self._w, self.steps = in_pts, out_pts, w, 0
+
+    def input_points(self):
+        return self._in
+
+    def output_points(self):
+        return self._out
+
+    def weights(self):
+        return self._w
+
+    def step(self):
+        self.steps += 1
+
+
+@pytest.mark.parametrize("d,n,ci,co,B,fs,r,bias,n_out", [
+    (2, 900, 16, 16, 8, [4, 4], 0.1, False, None),     # C1-like
+    (3, 1500, 32, 32, 32, [8, 8], 0.16, True, None),   # C3-like channels/batch
+    (2, 600, 5, 7, 3, [6], 0.12, True, None),          # odd channels, B not a power of two
+    (2, 500, 4, 40, 40, [8, 8], 0.1, False, None),     # B > 32 (two batch blocks), Co > 32
+    (2, 400, 64, 16, 2, [32, 32], 0.15, False, None),  # wide hidden layers (C4-like), Ci = 64
+    (1, 300, 2, 3, 4, [4, 4], 0.02, False, None),      # 1-D
+    (2, 700, 6, 4, 5, [], 0.08, False, None),          # no hidden layer: the filter is one Linear
+    (2, 800, 8, 12, 6, [8, 8], 0.09, True, 300),       # cross-level, No != Ni
+    (3, 400, 3, 2, 1, [16, 4], 0.3, False, None),      # B = 1
+])
+def test_layer_matches_oracle(cuda_lib, d, n, ci, co, B, fs, r, bias, n_out):
+    import pytorch_quadconv_b200 as q
+    c = _oracle_case(d, n, ci, co, B, fs, r, bias, seed=1000 + n + ci, n_out=n_out)
+    same = n_out is None
+    No = c["out_pts"].shape[0]
+    layer = q.QuadConv(spatial_dim=d, in_points=n, out_points=No, in_channels=ci, out_channels=co,
+                       filter_seq=fs, bias=bias, output_same=same, decay_param=r).cuda()
+    with torch.no_grad():
+        lin = [m for m in layer.filter if isinstance(m, torch.nn.Linear)]
+        for m, w in zip(lin, c["ws"]):
+            m.weight.copy_(w.detach())
+        if bias:
+            layer.bias.copy_(c["b"].detach())
+    w_dev = c["qw"].detach().cuda().requires_grad_()
+    mesh = _StubMesh(c["pts"].cuda(), c["out_pts"].cuda(), w_dev)
+    x = c["x"].detach().cuda().requires_grad_()
+    y = layer(mesh, x)
+    assert mesh.steps == (0 if same else 1)           # quadconv.py:253-254
+    assert torch.equal(layer.eval_indices.cpu(), c["pairs"])
+    assert relerr(y.detach().cpu().numpy(), c["y"].numpy()) < TOL
+    (y * c["go"].cuda()).sum().backward()
+    assert relerr(x.grad.cpu().numpy(), c["x"].grad.numpy()) < TOL
+    assert relerr(w_dev.grad.cpu().numpy(), c["qw"].grad.numpy()) < TOL
+    for m, w in zip(lin, c["ws"]):
+        assert relerr(m.weight.grad.cpu().numpy(), w.grad.numpy()) < TOL
+    if bias:
+        assert relerr(layer.bias.grad.cpu().numpy(), c["b"].grad.numpy()) < TOL
+
+
+def test_cache_false_and_injected_pairs(cuda_lib):
+    """cache=False recomputes the search every call (the profile script's mode,
+    py_scripts/quadconv_layer_profile.py:46); a caller-supplied eval_indices (quadconv.py:187-188)
+    gives the same output."""
+    import pytorch_quadconv_b200 as q
+    L = load_golden("layer_2d_wide")
+    mesh, layer = _build_from_golden(L, 2, [8, 8], False)
+    x = torch.from_numpy(L["x"]).cuda()
+    layer.cache = False
+    y1 = layer(mesh, x)
+    assert not layer.cached and not hasattr(layer, "eval_indices")
+    y2 = layer(mesh, x)
+    assert torch.equal(y1, y2)                         # deterministic forward
+    layer.eval_indices = torch.nn.Parameter(torch.from_numpy(L["pairs"]).cuda(), requires_grad=False)
+    layer.cached = True
+    layer._tables = None
+    y3 = layer(mesh, x)
+    assert relerr(y3.cpu().numpy(), L["y"]) < TOL
+    assert relerr(y1.cpu().numpy(), L["y"]) < TOL
+
+
+def test_linearity_and_batch_independence_full_size(cuda_lib):
+    """Size-independent properties at the C3 shape (100k 3-D points, 32->32, B=32), where the
+    reference cannot run: the layer is linear in the features, each batch entry is independent,
+    and the pair count equals the survey's probe (P = 4 812 390 for this seed and radius)."""
+    import pytorch_quadconv_b200 as q
+    torch.manual_seed(0)
+    N = 100_000
+    pts = torch.rand(N, 3)
+    r = (150 / (4 * np.pi * N)) ** (1 / 3)
+    layer = q.QuadConv(spatial_dim=3, in_points=N, out_points=N, in_channels=32, out_channels=32,
+                       filter_seq=[8, 8], output_same=True, decay_param=r).cuda()
+    w = torch.rand(N).cuda() + 0.5
+    mesh = _StubMesh(pts.cuda(), pts.cuda(), w)
+    x1 = torch.randn(32, 32, N, device="cuda")
+    x2 = torch.randn(32, 32, N, device="cuda")
+    with torch.no_grad():
+        y1, y2 = layer(mesh, x1), layer(mesh, x2)
+        y12 = layer(mesh, 2.0 * x1 - 3.0 * x2)
+        assert layer.eval_indices.shape[0] == 4_812_390
+        lin = (2.0 * y1 - 3.0 * y2)
+        assert float((y12 - lin).norm() / lin.norm()) < 1e-5
+        xs = x1[:1].repeat(32, 1, 1)
+        ys = layer(mesh, xs)
+        assert float((ys - ys[:1]).abs().max()) == 0.0
+        assert float((ys[0] - y1[0]).abs().max()) == 0.0
+    # oracle spot check on a few out points (the oracle finishes these in seconds)
+    from oracle import quadconv_oracle as O
+    ev = layer.eval_indices
+    sel = torch.tensor([0, 1, 77_777, N - 1], device="cuda")
+    mask = torch.isin(ev[:, 0], sel)
+    sub = ev[mask].cpu()
+    lin_w = [m.weight.detach().cpu() for m in layer.filter if isinstance(m, torch.nn.Linear)]
+    yo = O.quadconv_forward(pts, pts, w.cpu(), lin_w, x1[:4].cpu(), sub, 32, 32)
+    got = y1[:4][:, :, sel].cpu()
+    assert relerr(got.numpy(), yo[:, :, sel.cpu()].numpy()) < TOL

@@ -1,0 +1,95 @@
+"""GPU: K1 neighbour search through the C ABI -- bit-exact pair set AND order against (a) the golden
+vectors of the live reference and (b) the C oracle on fresh seeded inputs, plus CSR/CSC invariants."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _search(out_pts, in_pts, r, same):
+    from pytorch_quadconv_b200 import ops
+    o = torch.from_numpy(np.ascontiguousarray(out_pts, dtype=np.float32)).cuda()
+    i = o if same else torch.from_numpy(np.ascontiguousarray(in_pts, dtype=np.float32)).cuda()
+    res = ops.build_pairs(o, i, float(r), same)
+    torch.cuda.synchronize()
+    return [t.cpu().numpy() for t in res]
+
+
+def _check_tables(res, No, Ni):
+    ev, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = res
+    P = ev.shape[0]
+    assert row_ptr[0] == 0 and row_ptr[-1] == P and csc_ptr[0] == 0 and csc_ptr[-1] == P
+    assert np.array_equal(pair_row, ev[:, 0].astype(np.int32))
+    assert np.array_equal(pair_col, ev[:, 1].astype(np.int32))
+    assert np.array_equal(np.diff(row_ptr), np.bincount(ev[:, 0], minlength=No))
+    assert np.array_equal(np.diff(csc_ptr), np.bincount(ev[:, 1], minlength=Ni))
+    # CSC: stable sort of the pairs by in index
+    perm = np.argsort(ev[:, 1], kind="stable")
+    assert np.array_equal(csc_pair, perm.astype(np.int32))
+    assert np.array_equal(csc_row, ev[perm, 0].astype(np.int32))
+    assert np.array_equal(np.sort(order_out), np.arange(No))
+    assert np.array_equal(np.sort(order_in), np.arange(Ni))
+
+
+def test_pairs_match_reference_golden(cuda_lib):
+    g = load_golden("pairs")
+    for name in golden_cases(g):
+        o, i = g[name + "/out_pts"], g[name + "/in_pts"]
+        same = o.shape == i.shape and np.array_equal(o, i)
+        res = _search(o, i, float(g[name + "/r"]), same)
+        assert res[0].dtype == np.int64
+        assert np.array_equal(res[0], g[name + "/pairs"]), name
+        _check_tables(res, o.shape[0], i.shape[0])
+
+
+@pytest.mark.parametrize("d,n,r", [(1, 4000, 0.003), (2, 5000, None), (2, 20000, 0.013), (3, 8000, 0.09),
+                                   (3, 30000, 0.05), (2, 3, 0.5), (3, 1, 0.1)])
+def test_pairs_match_c_oracle(cuda_lib, d, n, r):
+    from oracle import quadconv_oracle as O
+    rng = np.random.default_rng(100 + d * 7 + n)
+    pts = rng.random((n, d), dtype=np.float32)
+    if r is None:
+        r = 4 / np.sqrt(n)          # reference default (quadconv.py:59-62), a numpy float64
+    res = _search(pts, pts, r, True)
+    ref = O.eval_indices_c(pts, pts, r)
+    assert np.array_equal(res[0], ref)
+    _check_tables(res, n, n)
+
+
+def test_pairs_cross_level_and_outside_bbox(cuda_lib):
+    from oracle import quadconv_oracle as O
+    rng = np.random.default_rng(5)
+    inp = rng.random((3000, 3), dtype=np.float32)
+    out = (rng.random((1200, 3), dtype=np.float32) * 1.4 - 0.2).astype(np.float32)   # partly outside the in-point box
+    res = _search(out, inp, 0.11, False)
+    assert np.array_equal(res[0], O.eval_indices_c(out, inp, 0.11))
+    _check_tables(res, 1200, 3000)
+
+
+def test_pairs_lattice_ties_large(cuda_lib):
+    """Lattice distances tie exactly with r: the <= predicate and its fp32 rounding must agree."""
+    from oracle import quadconv_oracle as O
+    xs = np.linspace(0, 1, 64, dtype=np.float32)
+    lat = np.stack(np.meshgrid(xs, xs, indexing="ij"), -1).reshape(-1, 2)
+    for r in (float(xs[3]), float(xs[1] * np.float32(2) ** 0.5), 1 / 63 * 5):
+        res = _search(lat, lat, r, True)
+        assert np.array_equal(res[0], O.eval_indices_c(lat, lat, r))
+
+
+def test_pairs_to_tables_roundtrip(cuda_lib):
+    from pytorch_quadconv_b200 import ops
+    g = load_golden("pairs")
+    ev = torch.from_numpy(g["cross_down/pairs"]).cuda()
+    No, Ni = g["cross_down/out_pts"].shape[0], g["cross_down/in_pts"].shape[0]
+    t = [x.cpu().numpy() for x in ops.pairs_to_tables(ev, No, Ni)]
+    evn = g["cross_down/pairs"]
+    assert np.array_equal(t[0], evn[:, 0]) and np.array_equal(t[1], evn[:, 1])
+    assert np.array_equal(np.diff(t[2]), np.bincount(evn[:, 0], minlength=No))
+    perm = np.argsort(evn[:, 1], kind="stable")
+    assert np.array_equal(t[4], perm) and np.array_equal(t[5], evn[perm, 0])
+    bad = ev.flip(0).contiguous()
+    with pytest.raises(RuntimeError):
+        ops.pairs_to_tables(bad, No, Ni)

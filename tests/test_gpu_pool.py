@@ -1,0 +1,105 @@
+"""GPU: Mesh_MaxPool (segmented max + adjoint gather, with backward) and the pooled autoencoder
+slice against golden vectors from the live reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import elim_map_from, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _mesh_from_golden(g, levels):
+    """MeshHandler with the reference's own levels/elimination maps (no re-run of MFNUS needed)."""
+    import pytorch_quadconv_b200 as q
+    mesh = q.MeshHandler(torch.from_numpy(g["pts"])).construct([g["pts"].shape[0]] + [0] * (levels - 1),
+                                                               mirror=True, quad_map="mfnus")
+    return mesh
+
+
+def test_pool_chain_matches_reference(cuda_lib):
+    import pytorch_quadconv_b200 as q
+    g = load_golden("pool")
+    mesh = _mesh_from_golden(g, 3).cuda()
+    for l in range(2):       # the host MFNUS restatement reproduces the reference maps
+        dm = mesh._downsample_map[l]
+        assert list(dm.keys()) == list(elim_map_from(g, f"elim{l}").keys())
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_()
+    pool0, pool1 = q.Mesh_MaxPool(), q.Mesh_MaxPool()
+    up1, up0 = q.Mesh_MaxPool(adjoint=True), q.Mesh_MaxPool(adjoint=True)
+    mesh.reset()
+    cur = [mesh._current_index]
+    y0 = pool0(mesh, x); cur.append(mesh._current_index)
+    y1 = pool1(mesh, y0); cur.append(mesh._current_index)
+    z1 = up1(mesh, y1); cur.append(mesh._current_index)
+    z0 = up0(mesh, z1); cur.append(mesh._current_index)
+    assert cur == [int(v) for v in g["cursor"]]
+    assert y0.dtype == torch.float32
+    for got, name in ((y0, "y0"), (y1, "y1"), (z1, "z1"), (z0, "z0")):
+        assert np.array_equal(got.detach().cpu().numpy(), g[name]), name      # max/gather are exact
+    assert np.array_equal(pool0.index.cpu().numpy(), g["index_pool0"])
+    assert np.array_equal(up0.index.cpu().numpy(), g["index_up0"])
+    loss = (z0 * torch.from_numpy(g["g"]).cuda()).sum() + (y0 * torch.from_numpy(g["gy0"]).cuda()).sum()
+    loss.backward()
+    # ties split the gradient evenly (x was quantised when the golden data was made)
+    assert relerr(x.grad.cpu().numpy(), g["dx"]) < 1e-6
+
+
+def test_pool_negative_groups_and_batch_change(cuda_lib):
+    import pytorch_quadconv_b200 as q
+    g = load_golden("pool")
+    mesh = _mesh_from_golden(g, 3).cuda()
+    pool = q.Mesh_MaxPool()
+    mesh.reset()
+    x = -torch.rand(2, 3, 600, device="cuda") - 1.0          # all negative: include_self=False -> true max, not 0
+    y = pool(mesh, x)
+    assert float(y.max()) < 0
+    grp = torch.from_numpy(g["index_pool0"]).cuda()
+    ref = torch.full((2, 3, y.shape[2]), -float("inf"), device="cuda").scatter_reduce(
+        2, grp.view(1, 1, -1).expand_as(x), x, "amax", include_self=False)
+    assert torch.equal(y, ref)
+    mesh.reset()
+    y5 = pool(mesh, -torch.rand(5, 3, 600, device="cuda"))    # batch-size change (mesh_pool.py:32-34)
+    assert y5.shape == (5, 3, y.shape[2])
+
+
+def test_autoencoder_slice_matches_reference(cuda_lib):
+    import pytorch_quadconv_b200 as q
+    A = load_golden("autoencoder")
+    mesh = q.MeshHandler(torch.from_numpy(A["pts"])).construct([400, 0], mirror=True, quad_map="mfnus")
+    assert mesh.point_seq == [int(v) for v in A["point_seq"]]
+    mesh.load_state_dict({k[5:]: torch.from_numpy(A[k]) for k in A.files if k.startswith("mesh/")})
+    n0, n1 = mesh.point_seq
+    mk = lambda n, ci, co: q.QuadConv(spatial_dim=2, in_points=n, out_points=n, in_channels=ci,
+                                      out_channels=co, filter_seq=[8, 8], output_same=True, bias=True)
+    layers = {"e0": mk(n0, 2, 4), "e1": mk(n1, 4, 4), "d0": mk(n0, 4, 2)}
+    for nm, m in layers.items():
+        sd = {k.split("/", 1)[1]: torch.from_numpy(A[k]) for k in A.files
+              if k.startswith(nm + "/") and not k.endswith("eval_indices")}
+        m.load_state_dict(sd)
+        m.cuda()
+    mesh = mesh.cuda()
+    pool, up = q.Mesh_MaxPool(), q.Mesh_MaxPool(adjoint=True)
+    x = torch.from_numpy(A["x"]).cuda().requires_grad_()
+    mesh.reset()
+    cur = [mesh._current_index]
+    h = torch.sin(layers["e0"](mesh, x)); cur.append(mesh._current_index)
+    h = pool(mesh, h); cur.append(mesh._current_index)
+    h = torch.sin(layers["e1"](mesh, h)); cur.append(mesh._current_index)
+    h = up(mesh, h); cur.append(mesh._current_index)
+    y = layers["d0"](mesh, h); cur.append(mesh._current_index)
+    assert cur == [int(v) for v in A["cursor"]]
+    for nm, m in layers.items():
+        assert np.array_equal(m.eval_indices.cpu().numpy(), A[f"{nm}/eval_indices"])
+    assert relerr(y.detach().cpu().numpy(), A["y"]) < 1e-5
+    loss = torch.nn.functional.mse_loss(y, x.detach())
+    assert abs(float(loss) - float(A["loss"])) < 1e-5 * abs(float(A["loss"]))
+    loss.backward()
+    assert relerr(x.grad.cpu().numpy(), A["dx"]) < 2e-5
+    for nm, m in layers.items():
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                assert relerr(p.grad.cpu().numpy(), A[f"{nm}grad/{k}"]) < 2e-5, (nm, k)
+    for k, p in mesh.named_parameters():
+        if p.requires_grad:
+            assert relerr(p.grad.cpu().numpy(), A["meshgrad/" + k]) < 1e-4, k

@@ -1,0 +1,97 @@
+"""CPU: host-side mirror of the reference API -- construction parity, state_dict layout, cursor
+walk, MFNUS coarsening and the pool index, all against golden data from the live reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import elim_map_from, load_golden
+
+import pytorch_quadconv_b200 as q
+from pytorch_quadconv_b200.mesh_pool import _group_of_fine_points
+from pytorch_quadconv_b200.utils.mfnus import mfnus_eliminate
+
+
+def test_mfnus_matches_reference():
+    g = load_golden("mfnus")
+    for nm in ("u2d", "u3d"):
+        kept, dm = mfnus_eliminate(g[nm + "/pts"], fc=1.65, K=10)
+        assert np.array_equal(kept, g[nm + "/kept"])
+        assert np.array_equal(np.array(list(dm.keys())), g[nm + "/keys"])
+        assert np.array_equal(np.array([len(v) for v in dm.values()]), g[nm + "/lens"])
+        assert np.array_equal(np.array([int(k) for v in dm.values() for k in v]), g[nm + "/flat"])
+
+
+def test_pool_group_index_matches_reference():
+    g = load_golden("pool")
+    n0, n1, n2 = [int(v) for v in g["point_seq"]]
+    assert np.array_equal(_group_of_fine_points(elim_map_from(g, "elim0"), n0), g["index_pool0"])
+    assert np.array_equal(_group_of_fine_points(elim_map_from(g, "elim1"), n1), g["index_pool1"])
+    # adjoint uses the same last-keeper-wins table (mesh_pool.py:55-78)
+    assert np.array_equal(_group_of_fine_points(elim_map_from(g, "elim1"), n1), g["index_up1"])
+    assert np.array_equal(_group_of_fine_points(elim_map_from(g, "elim0"), n0), g["index_up0"])
+
+
+def test_mesh_construct_and_cursor_match_reference():
+    g = load_golden("pool")
+    mesh = q.MeshHandler(torch.from_numpy(g["pts"])).construct([600, 0, 0], mirror=True, quad_map="mfnus")
+    assert mesh.point_seq == [int(v) for v in g["point_seq"]]
+    for l in range(3):
+        assert np.array_equal(mesh._points[l].numpy(), g[f"level{l}"])
+    # mirrored walk of the cursor, as recorded from the reference after each pool layer
+    mesh.reset()
+    walk = [mesh._current_index]
+    for _ in range(4):
+        mesh.step()
+        walk.append(mesh._current_index)
+    assert walk == [int(v) for v in g["cursor"]]
+    mesh.reset()
+    seen = []
+    for _ in range(4):
+        seen.append((mesh.input_points().shape[0], mesh.output_points().shape[0]))
+        mesh.step()
+    n0, n1, n2 = mesh.point_seq
+    assert seen == [(n0, n1), (n1, n2), (n2, n1), (n1, n0)]
+
+
+def test_single_level_step_raises_like_reference():
+    mesh = q.MeshHandler(torch.rand(30, 2)).construct([30])
+    with pytest.raises(ZeroDivisionError):     # mesh_handler.py:60-63 with one level
+        mesh.step()
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("layer_2d", dict(d=2, n=300, ci=3, co=5, fs=[4, 4], bias=True, seed=3)),
+    ("layer_1to2", dict(d=2, n=100, ci=1, co=2, fs=[5, 6, 7], bias=True, seed=6)),
+])
+def test_same_seed_gives_reference_parameters(name, kw):
+    """Same RNG stream as the reference: rand points, randn features, MeshHandler, then QuadConv."""
+    L = load_golden(name)
+    torch.manual_seed(kw["seed"])
+    pts = torch.rand(kw["n"], kw["d"])
+    _x = torch.randn(int(L["x"].shape[0]), kw["ci"], kw["n"])
+    mesh = q.MeshHandler(pts).construct([kw["n"]])
+    layer = q.QuadConv(spatial_dim=kw["d"], in_points=kw["n"], out_points=kw["n"], in_channels=kw["ci"],
+                       out_channels=kw["co"], filter_seq=kw["fs"], bias=kw["bias"], output_same=True)
+    assert np.array_equal(pts.numpy(), L["pts"])
+    sd = layer.state_dict()
+    assert list(sd.keys()) == ["bias"] + [f"filter.{2 * l}.weight" for l in range(len(kw["fs"]) + 1)]
+    for l in range(len(kw["fs"]) + 1):
+        assert np.array_equal(sd[f"filter.{2 * l}.weight"].numpy(), L[f"W{l}"])
+    assert np.array_equal(sd["bias"].numpy(), L["bias"])
+    msd = mesh.state_dict()
+    for k in msd:
+        assert np.array_equal(msd[k].numpy(), L["mesh/" + k]), k
+    assert float(layer.decay_param) == float(L["r"])
+    # quadrature weights from the learned map (mesh_handler.py:101-112) equal the reference's
+    assert np.allclose(mesh.weights().detach().numpy(), L["quad_w"], rtol=0, atol=1e-6)
+
+
+def test_ctor_validation():
+    with pytest.raises(AssertionError):
+        q.QuadConv(spatial_dim=0, in_points=4, out_points=4, in_channels=1, out_channels=1, filter_seq=[2])
+    with pytest.raises(ValueError):
+        q.QuadConv(spatial_dim=2, in_points=4, out_points=4, in_channels=1, out_channels=1, filter_seq=[2],
+                   filter_mode="bogus")
+    layer = q.QuadConv(spatial_dim=2, in_points=16, out_points=16, in_channels=1, out_channels=1, filter_seq=[2])
+    assert float(layer.decay_param) == 1.0 and layer.bias is None and layer.cached is False
+    assert q.MeshMaxPool is q.Mesh_MaxPool

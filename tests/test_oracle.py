@@ -1,0 +1,62 @@
+"""CPU: pin the oracle (oracle/) against the golden vectors produced by the live reference
+(tests/golden/make_golden.py).  Pairs must be bit-exact; floats within 1e-6 normwise."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import elim_map_from, golden_cases, load_golden, relerr
+from oracle import quadconv_oracle as O
+
+
+def test_search_c_matches_reference_pairs():
+    g = load_golden("pairs")
+    for name in golden_cases(g):
+        p = O.eval_indices_c(g[name + "/out_pts"], g[name + "/in_pts"], float(g[name + "/r"]))
+        assert p.dtype == np.int64
+        assert np.array_equal(p, g[name + "/pairs"]), name
+
+
+def test_search_torch_blocked_matches_reference_pairs():
+    g = load_golden("pairs")
+    for name in golden_cases(g):
+        p = O.eval_indices_torch(torch.from_numpy(g[name + "/out_pts"]), torch.from_numpy(g[name + "/in_pts"]),
+                                 float(g[name + "/r"]), block=97)
+        assert torch.equal(p, torch.from_numpy(g[name + "/pairs"])), name
+
+
+@pytest.mark.parametrize("name", ["layer_2d", "layer_2d_wide", "layer_3d", "layer_1to2"])
+def test_forward_backward_matches_reference(name):
+    L = load_golden(name)
+    t = lambda k: torch.from_numpy(L[k])
+    ws = [t(f"W{l}").requires_grad_() for l in range(10) if f"W{l}" in L.files]
+    x, qw = t("x").requires_grad_(), t("quad_w").requires_grad_()
+    bias = t("bias").requires_grad_() if "bias" in L.files else None
+    y = O.quadconv_forward(t("pts"), t("pts"), qw, ws, x, t("pairs"), int(L["ci"]), int(L["co"]), bias,
+                           block_pairs=1500)
+    (y * t("grad_out")).sum().backward()
+    tol = 1e-6
+    assert relerr(y.detach().numpy(), L["y"]) < tol
+    assert relerr(x.grad.numpy(), L["dx"]) < tol
+    assert relerr(qw.grad.numpy(), L["dquad_w"]) < tol
+    for l, w in enumerate(ws):
+        assert relerr(w.grad.numpy(), L[f"dW{l}"]) < 2e-6
+    if bias is not None:
+        assert relerr(bias.grad.numpy(), L["dbias"]) < tol
+
+
+def test_pool_index_and_values_match_reference():
+    g = load_golden("pool")
+    em0, em1 = elim_map_from(g, "elim0"), elim_map_from(g, "elim1")
+    n0, n1, n2 = [int(v) for v in g["point_seq"]]
+    assert np.array_equal(O.pool_group_index(em0, n0), g["index_pool0"])
+    assert np.array_equal(O.pool_group_index(em1, n1), g["index_pool1"])
+    assert np.array_equal(O.pool_adjoint_index(em1, n1), g["index_up1"])
+    assert np.array_equal(O.pool_adjoint_index(em0, n0), g["index_up0"])
+    x = torch.from_numpy(g["x"])
+    y0 = O.maxpool_forward(x, torch.from_numpy(g["index_pool0"]), n1)
+    assert torch.equal(y0, torch.from_numpy(g["y0"]))
+    assert np.array_equal(O.segmax_c(g["x"], g["index_pool0"], n1), g["y0"])
+    y1 = O.maxpool_forward(y0, torch.from_numpy(g["index_pool1"]), n2)
+    assert torch.equal(y1, torch.from_numpy(g["y1"]))
+    z1 = O.maxpool_adjoint(y1, torch.from_numpy(g["index_up1"]))
+    assert torch.equal(z1, torch.from_numpy(g["z1"]))
