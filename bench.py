@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""
+bench.py -- QuadConv layer fwd+bwd throughput (BASELINE.json metric: "QuadConv layer fwd+bwd Mpairs/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c4] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward + backward of one QuadConv layer over one batch of synthetic features:
+`y = layer(mesh, x); y.sum().backward()`, parameter-gradient all-reduce included
+when N > 1.  One "pair" is one row of eval_indices (reference quadconv.py:183).
+
+Default workload (N=1) is C3, the largest single-GPU layer configuration in BASELINE.json's configs:
+100 000 uniform points in the unit cube, 32->32 channels, batch 32, filter_seq [8,8],
+decay_param (150/(4 pi N))^(1/3) -> P = 4 812 390 pairs.  With N GPUs every rank runs the same
+per-GPU batch on its own replica of the mesh (batch sharding, weak scaling) and one flat NCCL
+all-reduce combines the parameter gradients.
+
+Printed keys follow the driver contract; `roofline` and `cpu_baseline` are described in DESIGN.md.
+`--impl reference` times the oracle's CPU restatement of the reference path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "QuadConv layer fwd+bwd Mpairs/s"
+UNIT = "Mpairs/s"
+
+
+def workload(name: str):
+    if name == "c1":
+        return dict(name="C1: 2-D 2500->2500 pts, 16->16 ch, batch 8, filter_seq [4,4], r=4/sqrt(N)",
+                    N=2500, d=2, ci=16, co=16, B=8, fs=[4, 4], r=None)
+    if name == "c3":
+        N = 100_000
+        return dict(name="C3: 3-D 100k pts, 32->32 ch, batch 32, filter_seq [8,8], r=(150/(4 pi N))^(1/3)",
+                    N=N, d=3, ci=32, co=32, B=32, fs=[8, 8], r=(150 / (4 * np.pi * N)) ** (1 / 3))
+    if name == "c4":
+        N = 10_000
+        return dict(name="C4: 2-D 10k pts, 64->128 ch, batch 8, filter_seq [32,32], r=sqrt(200/(pi N)) (fp32 path)",
+                    N=N, d=2, ci=64, co=128, B=8, fs=[32, 32], r=float(np.sqrt(200 / (np.pi * N))))
+    raise SystemExit(f"unknown workload {name}")
+
+
+def weight_args(d):
+    return {"const": False} if d == 2 else {"element_size": d + 1, "dimension": d, "const": False}
+
+
+# --------------------------------------------------------------------------------------------
+# algorithmic work
+# --------------------------------------------------------------------------------------------
+
+def flops_per_pair(w, k_avg):
+    d, ci, co, B, fs = w["d"], w["ci"], w["co"], w["B"], w["fs"]
+    dims = [d] + list(fs)
+    S = sum(dims[l] * dims[l + 1] for l in range(len(dims) - 1))
+    hL = dims[-1]
+    direct_fwd = 2 * (S + hL * ci * co) + 2 * B * ci * co
+    direct_bwd = 4 * B * ci * co + 4 * hL * ci * co + 2 * ci * co + 2 * S + 2 * (S - d * dims[1] if fs else 0)
+    fact_fwd = 2 * S + 2 * hL * B * ci + 2 * B * ci * co * hL / k_avg
+    # backward of the factorised form: d phi (dense dT + dots), d features (stage B + C) and d W_last
+    fact_bwd = (2 * hL * B * ci + 2 * B * ci * co * hL / k_avg) + (2 * hL * B * co + 2 * B * ci * co * hL / k_avg) \
+        + 2 * B * ci * co * hL / k_avg + 4 * S
+    return dict(direct=direct_fwd + direct_bwd, factorised=fact_fwd + fact_bwd, fact_fwd=fact_fwd)
+
+
+def bytes_per_step(w, P):
+    N, d, ci, co, B = w["N"], w["d"], w["ci"], w["co"], w["B"]
+    fwd = 4 * (B * ci * N + B * co * N + 2 * N * d + N) + 4 * P
+    bwd = 4 * (B * co * N + 2 * B * ci * N + 2 * N + 2 * N * d) + 4 * P
+    return fwd + bwd
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's restatement of the reference on host cores
+# --------------------------------------------------------------------------------------------
+
+def cpu_sample_config(w):
+    """Bounded sample of the workload: same channels / batch / filter / neighbours-per-point,
+    fewer points (the reference's materialised [P,Ci,Co] tensors do not fit at full size)."""
+    s = dict(w)
+    if w["N"] > 5000:
+        s["N"] = 5000 if w["d"] == 3 else 2500
+        if w["r"] is not None:   # keep the expected neighbour count: r ~ N^(-1/d)
+            s["r"] = w["r"] * (w["N"] / s["N"]) ** (1.0 / w["d"])
+    return s
+
+
+def run_cpu_reference(w, steps, warmup):
+    """`y = layer(mesh, x); y.sum().backward()` with the oracle's torch-CPU restatement of
+    quadconv.py:238-265 (same ATen ops and association order as the reference), all host threads."""
+    from oracle import quadconv_oracle as O
+    s = cpu_sample_config(w)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    pts = torch.rand(s["N"], s["d"])
+    x = torch.randn(s["B"], s["ci"], s["N"], requires_grad=True)
+    r = s["r"] if s["r"] is not None else 4 / np.sqrt(s["N"])
+    dims = [s["d"]] + list(s["fs"]) + [s["ci"] * s["co"]]
+    ws = [torch.nn.Linear(dims[l], dims[l + 1], bias=False).weight.detach().requires_grad_()
+          for l in range(len(dims) - 1)]
+    qw = torch.rand(s["N"], requires_grad=True)
+    pairs = torch.from_numpy(O.eval_indices_c(pts.numpy(), pts.numpy(), r))
+    P = pairs.shape[0]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        y = O.quadconv_forward(pts, pts, qw, ws, x, pairs, s["ci"], s["co"], None, block_pairs=1 << 16)
+        y.sum().backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        x.grad = None
+    t = sum(times) / len(times)
+    sample = (f"oracle port of quadconv.py:238-265 (+autograd) on N={s['N']} pts (same channels/batch/filter, "
+              f"radius rescaled to keep ~{P / s['N']:.0f} neighbours/pt), P={P} pairs, {t:.2f} s/step")
+    return dict(value=P / t / 1e6, unit=UNIT, cores=cores, kind="port", sample=sample), t, P
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        mx = self.samples[0][1]
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": float(mx) if mx.replace(".", "").isdigit() else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+
+def build_problem(w, dev):
+    import pytorch_quadconv_b200 as q
+    torch.manual_seed(0)
+    pts = torch.rand(w["N"], w["d"])
+    x_host = torch.randn(w["B"], w["ci"], w["N"]).pin_memory()
+    mesh = q.MeshHandler(pts).construct([w["N"]], quad_args={"point_args": {}, "weight_args": weight_args(w["d"])})
+    layer = q.QuadConv(spatial_dim=w["d"], in_points=w["N"], out_points=w["N"], in_channels=w["ci"],
+                       out_channels=w["co"], filter_seq=w["fs"], output_same=True, decay_param=w["r"])
+    return mesh.to(dev), layer.to(dev), x_host
+
+
+def time_kernels(w, mesh, layer, x, reps=5):
+    """Per-kernel device time of one fwd+bwd, CUDA events on the launching (current) stream around
+    each C-ABI call.  Returns {name: ms}."""
+    from pytorch_quadconv_b200 import _cabi as C, ops
+    L = C.lib()
+    names = ["qc_pair_phi_fwd", "qc_pack_features", "qc_repack_wlast", "qc_contract", "qc_unpack_features",
+             "qc_batch_sum", "qc_dphi", "qc_pair_phi_bwd", "qc_unpack_dwlast"]
+    acc = {}
+    orig = {n: getattr(L, n) for n in names}
+    phase = {"bwd": False}
+
+    def wrap(n):
+        f = orig[n]
+
+        def g(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = f(*a)
+            e1.record()
+            key = n + (".bwd" if phase["bwd"] else ".fwd")
+            acc.setdefault(key, []).append((e0, e1))
+            return rc
+        return g
+    for n in names:
+        setattr(L, n, wrap(n))
+    try:
+        for _ in range(reps):
+            phase["bwd"] = False
+            x.grad = None
+            y = layer(mesh, x)
+            loss = y.sum()
+            phase["bwd"] = True
+            loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        for n in names:
+            setattr(L, n, orig[n])
+    out = {}
+    for k, evs in acc.items():
+        per_step = len(evs) // reps
+        ts = [a.elapsed_time(b) for a, b in evs[per_step:]]      # drop the first repetition
+        out[k] = sum(ts) / max(reps - 1, 1)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", default=None, help="write the per-kernel timing table (json) here")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    w = workload(args.workload)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        cb, t, P = run_cpu_reference(w, steps, 1)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "note": "CPU host cores; bounded sample, see cpu_baseline.sample"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from pytorch_quadconv_b200 import _cabi  # fails loudly if the .so is missing
+    _cabi.lib()
+    from pytorch_quadconv_b200.distributed import FlatGradAllReduce, trainable_parameters
+
+    mesh, layer, x_host = build_problem(w, dev)
+    x = x_host.to(dev).requires_grad_()
+    params = trainable_parameters([layer, mesh])
+    reducer = FlatGradAllReduce(params) if world > 1 else None
+
+    def step(xin):
+        for p in params:
+            p.grad = None
+        xin.grad = None
+        y = layer(mesh, xin)
+        loss = y.sum()
+        loss.backward()
+        if reducer is not None:
+            reducer()
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x)
+    P = int(layer.eval_indices.shape[0])
+
+    # ---- device-resident timing --------------------------------------------------------------
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            step(x)
+        e1.record()
+        sync()
+    ms = e0.elapsed_time(e1) / args.steps
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    value = P * world / (ms * 1e-3) / 1e6
+
+    # ---- end to end: host (pinned) features -> device -> fwd+bwd -> loss + filter grads to host ----
+    grads_host = [torch.empty(p.shape, dtype=p.dtype).pin_memory() for p in layer.parameters() if p.requires_grad]
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        xin = x_host.to(dev, non_blocking=True).requires_grad_()
+        loss = step(xin)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        for h, p in zip(grads_host, [p for p in layer.parameters() if p.requires_grad]):
+            h.copy_(p.grad, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    sync()
+    n_e2e = max(3, args.steps // 2)
+    e0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    e1.record()
+    sync()
+    ems = torch.tensor([e0.elapsed_time(e1) / n_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ems.item())
+    h2d = x_host.numel() * 4
+    d2h = 4 + sum(g.numel() * 4 for g in grads_host)
+
+    # ---- per-kernel table + roofline of the dominant kernel (rank 0) ----------------------------
+    roof, cb, table = None, None, None
+    if rank == 0:
+        table = time_kernels(w, mesh, layer, x)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16 = peaks.get("bf16_tflops", 1590.0)
+        src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        k_avg = P / w["N"]
+        fl = flops_per_pair(w, k_avg)
+        dom = max(table, key=table.get)
+        dom_ms = table[dom]
+        # algorithmic flops of the dominant launch, factorised formulation (DESIGN.md "Kernels")
+        B, ci, co, hL = w["B"], w["ci"], w["co"], (w["fs"][-1] if w["fs"] else w["d"])
+        stageB = 2.0 * P * B * hL
+        dense = 2.0 * w["N"] * B * ci * co * hL
+        alg = {"qc_contract.fwd": stageB * ci + dense, "qc_contract.bwd": stageB * co + 2 * dense,
+               "qc_dphi.bwd": stageB * ci + dense}.get(dom, 0.0)
+        peak = bf16 / 6.0     # fp32 mode on tensor cores = 3xTF32 ~ bf16/6
+        ach = alg / (dom_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None,
+                "note": f"fp32-mode tensor peak = bf16/6 of {src}; numerator = factorised-formulation FLOPs of this "
+                        f"launch ({alg / 1e9:.1f} GFLOP) / CUDA-event time {dom_ms:.3f} ms; this round the kernel runs "
+                        f"on the FP32 CUDA-core pipe (FFMA peak ~ 148 SM x 128 lanes x 2 x clock)",
+                "step_direct_formulation_tflops": fl["direct"] * P / (ms * 1e-3) / 1e12,
+                "step_factorised_tflops": fl["factorised"] * P / (ms * 1e-3) / 1e12,
+                "step_hbm_alg_gbs": bytes_per_step(w, P) / (ms * 1e-3) / 1e9,
+                "hbm_peak_gbs": peaks.get("hbm_gbs", 6650.0)}
+        if args.kernel_table:
+            json.dump({"workload": w["name"], "P": P, "ms_per_step": ms, "kernels_ms": table},
+                      open(args.kernel_table, "w"), indent=1)
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _, _ = run_cpu_reference(w, 1, 1)
+
+    if rank == 0:
+        launches = 0
+        if table:
+            # kernels launched per C-ABI call (see csrc/*.cu): contract 1 (+memset), dphi 1, pair 1, pack 1 ...
+            launches = len(table)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "pairs_per_gpu": P, "batch_per_gpu": w["B"],
+                       "parallelism": f"batch-sharded dp{world}, flat NCCL all-reduce of parameter grads",
+                       "l2": "inputs larger than L2 (features+grads 1.6 GB/step > 126 MB)" if w["N"] >= 50000
+                       else "working set fits in L2 (reference's own CPU-runnable case)",
+                       "includes": "MeshHandler.weights() (PyTorch autograd, mesh_handler.py:101-112) every step"},
+            "clocks": clk.summary(),
+            "e2e": {"value": P * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches * args.steps,
+            "roofline": roof, "cpu_baseline": cb, "kernels_ms": table,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

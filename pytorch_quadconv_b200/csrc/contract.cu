@@ -142,23 +142,25 @@ __global__ void __launch_bounds__(256, DW ? 1 : 2) k_contract(const ContractArgs
                     }
                 }
             }
-            // combine the WK partial sums of each row through shared memory
+            // combine the WK partial sums of each row through shared memory: every warp owns a
+            // [32][OUT_STRIDE] slot, the store phase adds the WK slots of a row in fixed order
+            // (deterministic, no atomics)
             __syncthreads();
-            for (int i = threadIdx.x; i < rows * OUT_STRIDE; i += 256) out_s[i] = 0.f;
-            if (wk == 0) row_dst[wp * 32 + lane] = dstp;
-            __syncthreads();
-            if (kvalid && pvalid) {
-                float* orow = out_s + (wp * 32 + lane) * OUT_STRIDE;
+            {
+                float* orow = out_s + (size_t)(warp * 32 + lane) * OUT_STRIDE;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(orow + j, acc[j]);
+                for (int j = 0; j < 32; ++j) orow[j] = acc[j];
             }
+            if (wk == 0) row_dst[wp * 32 + lane] = dstp;
             __syncthreads();
             for (int idx = threadIdx.x; idx < rows * 32; idx += 256) {
                 const int row = idx & (rows - 1), jj = idx / rows;
                 const int j = jt + jj;
                 const int dp = row_dst[row];
                 if (dp >= 0 && j < a.Cy) {
-                    const float v = out_s[row * OUT_STRIDE + jj];
+                    const float* src = out_s + (size_t)(((row >> 5) * WK) * 32 + (row & 31)) * OUT_STRIDE + jj;
+                    float v = 0.f;
+                    for (int k = 0; k < WK; ++k) v += src[(size_t)k * 32 * OUT_STRIDE];
                     float* y = a.Y + (((size_t)blk * a.Ndst + dp) * a.Cy + j) * Bp + (row & (Bp - 1));
                     if (a.KSPLIT > 1) atomicAdd(y, v);
                     else *y = v;

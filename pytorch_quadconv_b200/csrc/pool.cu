@@ -39,7 +39,11 @@ __global__ void k_segmax_bwd(const float* __restrict__ x, const float* __restric
         const float m = out[r * Nout + g];
         float gx = 0.f;
         if (x[t] == m) {
-            int ties = 0;
+            // torch's amax backward counts `self == result` as one more tie even with
+            // include_self=False, and self is the reference's zeros() tensor (mesh_pool.py:88):
+            // a group whose maximum is exactly 0 spreads its gradient over ties+1.  Reproduced
+            // for parity with the reference's autograd.
+            int ties = (m == 0.f) ? 1 : 0;
             for (int e = grp_ptr[g]; e < grp_ptr[g + 1]; ++e) ties += (__ldg(x + r * Nin + grp_mem[e]) == m);
             gx = grad_out[r * Nout + g] / (float)ties;
         }

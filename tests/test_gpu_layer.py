@@ -155,13 +155,14 @@ def test_cache_false_and_injected_pairs(cuda_lib):
     y1 = layer(mesh, x)
     assert not layer.cached and not hasattr(layer, "eval_indices")
     y2 = layer(mesh, x)
-    assert torch.equal(y1, y2)                         # deterministic forward
+    # (MeshHandler.weights() uses torch's atomic scatter_add on CUDA, so y is reproducible to rounding only)
+    assert relerr(y2.detach().cpu().numpy(), y1.detach().cpu().numpy()) < 1e-6
     layer.eval_indices = torch.nn.Parameter(torch.from_numpy(L["pairs"]).cuda(), requires_grad=False)
     layer.cached = True
     layer._tables = None
     y3 = layer(mesh, x)
-    assert relerr(y3.cpu().numpy(), L["y"]) < TOL
-    assert relerr(y1.cpu().numpy(), L["y"]) < TOL
+    assert relerr(y3.detach().cpu().numpy(), L["y"]) < TOL
+    assert relerr(y1.detach().cpu().numpy(), L["y"]) < TOL
 
 
 def test_linearity_and_batch_independence_full_size(cuda_lib):
