@@ -18,22 +18,11 @@
 //   indices are sub-group-uniform broadcast loads.  Segments are contiguous in the CSR, so the
 //   per-point reduction needs no atomics and is bit-reproducible.
 #include "common.cuh"
+#include "contract_args.cuh"
 
 namespace {
 
-struct ContractArgs {
-    const float* X;
-    float* Y;
-    const float* Z;
-    float* dW2;
-    const int* seg_ptr;
-    const int* src_idx;
-    const int* phi_idx;
-    const float* phi;
-    const float* W2;
-    const int* order;
-    int Nsrc, Ndst, Cx, Cy, CyP, CyS, H, LB, LWK, KSPLIT;
-};
+
 
 constexpr int OUT_STRIDE = 33;  // conflict-free row stride of the output staging tile
 constexpr int Z_STRIDE = 36;    // float4-aligned row stride of the Z tile (aliases the output tile)
@@ -233,16 +222,7 @@ __global__ void __launch_bounds__(256, DW ? 1 : 2) k_contract(const ContractArgs
 }
 
 // ---------------------------------------------------------------------------------------------
-struct DphiArgs {
-    const float* X;
-    const float* G;
-    const float* W3;
-    const int* seg_ptr;
-    const int* src_idx;
-    const int* order;
-    float* dphi;
-    int Nsrc, Ndst, Cx, Cg, H, LWK;
-};
+
 
 __host__ __device__ constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
 
@@ -445,6 +425,10 @@ int qc_contract(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, const int
     a.LWK = ilog2(WK);
     a.KSPLIT = qc_ceil_div(NKC, WK);
     if (a.KSPLIT > 65535 || nblk > 65535) return QC_EUNSUP;
+    {
+        const int rc = qc_contract_fast(a, HP, B, dw, st);
+        if (rc != 0) return rc == 1 ? 0 : rc;
+    }
     const int WP = 8 / WK;
     size_t smem = (256 + 256 * Z_STRIDE) * 4;
     if (dw) smem += ((size_t)WP * 32 * (WK * 64 + 4) + (size_t)WK * 64 * a.CyS) * 4;
@@ -483,6 +467,10 @@ int qc_dphi(const float* Xp, int Nsrc, int Cx, const float* Gp, int Cg, const in
     const int nksplit = qc_ceil_div(NKC, WK);
     if (nksplit > 65535 || nblk > 65535) return QC_EUNSUP;
     const int LB = ilog2(Bp);
+    {
+        const int rc = qc_dphi_fast(a, HP, B, st);
+        if (rc != 0) return rc == 1 ? 0 : rc;
+    }
     switch (HP) {
         case 4: return dispatch_dphi<4>(a, LB, nksplit, nblk, st);
         case 8: return dispatch_dphi<8>(a, LB, nksplit, nblk, st);

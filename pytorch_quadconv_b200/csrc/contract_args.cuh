@@ -1,0 +1,34 @@
+// contract_args.cuh -- argument blocks shared by the generic (contract.cu) and the fast
+// (contract_fast.cu) gather-contract kernels.
+#pragma once
+#include "common.cuh"
+
+struct ContractArgs {
+    const float* X;
+    float* Y;
+    const float* Z;
+    float* dW2;
+    const int* seg_ptr;
+    const int* src_idx;
+    const int* phi_idx;
+    const float* phi;
+    const float* W2;
+    const int* order;
+    int Nsrc, Ndst, Cx, Cy, CyP, CyS, H, LB, LWK, KSPLIT;
+};
+
+struct DphiArgs {
+    const float* X;
+    const float* G;
+    const float* W3;
+    const int* seg_ptr;
+    const int* src_idx;
+    const int* order;
+    float* dphi;
+    int Nsrc, Ndst, Cx, Cg, H, LWK;
+};
+
+// Fast paths (contract_fast.cu).  Return 1 when the shape is handled, 0 when the caller must
+// fall back to the generic kernel, <0 / cudaError on failure.
+int qc_contract_fast(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t st);
+int qc_dphi_fast(const DphiArgs& a, int HP, int B, cudaStream_t st);

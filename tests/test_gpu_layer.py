@@ -113,6 +113,9 @@ class _StubMesh:
     (2, 700, 6, 4, 5, [], 0.08, False, None),          # no hidden layer: the filter is one Linear
     (2, 800, 8, 12, 6, [8, 8], 0.09, True, 300),       # cross-level, No != Ni
     (3, 400, 3, 2, 1, [16, 4], 0.3, False, None),      # B = 1
+    (2, 1000, 4, 8, 8, [8, 8], 0.08, True, None),      # fast path, partial channel chunk (Ci < 8)
+    (2, 700, 20, 24, 32, [8, 8], 0.1, False, None),    # fast path, 3 channel chunks, last one partial
+    (3, 900, 32, 16, 64, [4, 4], 0.2, True, None),     # fast path, two batch blocks (B = 64), H = 4
 ])
 def test_layer_matches_oracle(cuda_lib, d, n, ci, co, B, fs, r, bias, n_out):
     import pytorch_quadconv_b200 as q
@@ -133,7 +136,19 @@ def test_layer_matches_oracle(cuda_lib, d, n, ci, co, B, fs, r, bias, n_out):
     y = layer(mesh, x)
     assert mesh.steps == (0 if same else 1)           # quadconv.py:253-254
     assert torch.equal(layer.eval_indices.cpu(), c["pairs"])
-    assert relerr(y.detach().cpu().numpy(), c["y"].numpy()) < TOL
+    if relerr(y.detach().cpu().numpy(), c["y"].numpy()) >= TOL:      # diagnostics for the failure message
+        from oracle import quadconv_oracle as O
+        y64 = O.quadconv_forward(c["out_pts"].double(), c["pts"].double(), c["qw"].detach().double(),
+                                 [w.detach().double() for w in c["ws"]], c["x"].detach().double(), c["pairs"],
+                                 ci, co, None if not bias else c["b"].detach().double())
+        yd = y.detach().cpu().double()
+        ea = (yd - c["y"].double()).abs()
+        top = ea.flatten().topk(12)
+        msg = [(tuple(int(v) for v in np.unravel_index(int(i), ea.shape)), float(v)) for v, i in zip(top.values, top.indices)]
+        y2 = layer(mesh, x).detach().cpu().double()
+        raise AssertionError(f"ours-vs-oracle32 {relerr(yd.numpy(), c['y'].numpy()):.3e} ours-vs-f64 "
+                             f"{relerr(yd.numpy(), y64.numpy()):.3e} oracle32-vs-f64 {relerr(c['y'].numpy(), y64.numpy()):.3e} "
+                             f"rerun-vs-f64 {relerr(y2.numpy(), y64.numpy()):.3e} top {msg}")
     (y * c["go"].cuda()).sum().backward()
     assert relerr(x.grad.cpu().numpy(), c["x"].grad.numpy()) < TOL
     assert relerr(w_dev.grad.cpu().numpy(), c["qw"].grad.numpy()) < TOL
