@@ -16,7 +16,7 @@
  *   - re-entrant, no global state apart from one-time cudaFuncSetAttribute calls.
  *
  * Internal data layouts (DESIGN.md "Data layout in HBM")
- *   packed features  Xp[nblk][N][C][Bp]   fp32; batch innermost. Bp = min(32, pow2ceil(B)) lanes,
+ *   packed features  Xp[nblk][N][CP4/4][Bp][4] fp32; CP4 = C rounded up to 4, Bp = min(32, pow2ceil(B)) lanes,
  *                    nblk = ceil(B/32) batch blocks, padded batch lanes are zero.
  *   CSR              seg_ptr[Ndst+1] int32, src_idx[P] int32 (pairs grouped by destination point)
  *   phi              [P][HP] fp32: last hidden activation of the filter MLP per pair, times the
@@ -84,7 +84,7 @@ int qc_csc_fill(const int* pair_row, const int* pair_col, int64_t P, int Ni, con
 
 /* ------------------------------------------------------------------------------------------
  * Layout conversion between the reference's [B,C,N] tensors (quadconv.py:238 docstring) and the
- * packed [nblk][N][C][Bp] layout.  qc_unpack_features optionally adds bias[C][N]
+ * packed [nblk][N][CP4/4][Bp][4] layout.  qc_unpack_features optionally adds bias[C][N]
  * (quadconv.py:262-263) and/or accumulates the per-(c,n) batch sum of the source (d bias).
  * ------------------------------------------------------------------------------------------ */
 int qc_pack_features(const float* x, int B, int C, int N, float* xp, void* stream);
@@ -111,11 +111,12 @@ int qc_pair_phi_fwd(const float* out_pts, const float* in_pts, const float* quad
                     const int* pair_row, const int* pair_col, int64_t P, int d,
                     const qc_mlp_t* mlp /*host*/, int HP, float* phi, void* stream);
 
-/* Backward of the above.  dphi[P][HP] is d loss / d phi.  Accumulates (+=) into
- *   d_mlp_w[l] (same shapes as mlp_w[l]) and d_quad_w[Ni] (may be NULL). */
+/* Backward of the above.  dphi[nslices][P][HP] holds partial d loss / d phi (summed over the
+ * slices here, in fixed order).  Accumulates (+=) into d_mlp_w[l] (same shapes as mlp_w[l]) and
+ * d_quad_w[Ni] (may be NULL). */
 int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad_w,
                     const int* pair_row, const int* pair_col, int64_t P, int d,
-                    const qc_mlp_t* mlp /*host*/, int HP, const float* dphi,
+                    const qc_mlp_t* mlp /*host*/, int HP, const float* dphi, int nslices,
                     float* const* d_mlp_w /*host array of device ptrs*/, float* d_quad_w,
                     void* stream);
 
@@ -143,10 +144,13 @@ int qc_contract(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, const int
 /* d loss / d phi (grouped by out point):
  *     dT[t; b, c, h] = sum_j Gp[t][j][b] * W3[j][c][h]          W3[j][c][h] = W_last[c*Co+j][h]
  *     dphi[q][h]    += sum_{b,c} Xp[src_idx[q]][c][b] * dT[t; b, c, h]       (q in S(t))
- * W3 is [Cg][Cx][HP] (h padded with zeros).  dphi must be zeroed by the caller. */
+ * W3 is [Cg][Cx][HP] (h padded with zeros).  dphi is [qc_dphi_num_slices(...)][P][HP]: the fast
+ * kernels write one slice per (batch block, channel chunk) with plain stores; the slices are
+ * summed by qc_pair_phi_bwd.  No initialisation needed by the caller. */
+int qc_dphi_num_slices(int Nsrc, int Cx, int Cg, int HP, int B);
 int qc_dphi(const float* Xp, int Nsrc, int Cx, const float* Gp, int Cg, const int* seg_ptr,
             const int* src_idx, const float* W3, int H, int HP, const int* order, int Ndst, int B,
-            float* dphi, void* stream);
+            int64_t P, float* dphi, void* stream);
 
 /* Repack the last Linear weight W_last [Ci*Co][H] (filter.{2L}.weight, quadconv.py:143):
  *   mode 0: W2[(i*H+h)*CoP + j]  (forward)        mode 1: W2[(j*H+h)*CiP + i]  (d features)

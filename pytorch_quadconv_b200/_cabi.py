@@ -43,13 +43,14 @@ _SIGNATURES = {
     "qc_pair_phi_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                 ctypes.POINTER(QcMlp), c_int, c_void_p, c_void_p]),
     "qc_pair_phi_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-                                ctypes.POINTER(QcMlp), c_int, c_void_p, ctypes.POINTER(c_void_p),
+                                ctypes.POINTER(QcMlp), c_int, c_void_p, c_int, ctypes.POINTER(c_void_p),
                                 c_void_p, c_void_p]),
     "qc_contract": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                             c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                             c_void_p]),
+    "qc_dphi_num_slices": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "qc_dphi": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
-                        c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+                        c_int, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),
     "qc_repack_wlast": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qc_unpack_dwlast": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qc_segmax_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

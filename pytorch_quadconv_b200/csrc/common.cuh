@@ -27,6 +27,13 @@ static inline int qc_bp(int B)
 }
 static inline int qc_nblk(int B) { return (B + 31) / 32; }
 
+// Packed feature layout  Xp[nblk][N][CP4/4][Bp][4]  (fp32): per point, channels in groups of four,
+// batch lane next, the four channels of a group innermost -- so the thread that owns batch lane b
+// reads four channels with one 128-bit load and a warp's load is one contiguous 512 B segment.
+// CP4 = C rounded up to 4; padded channels and padded batch lanes hold zeros.
+__host__ __device__ inline int qc_cp4(int C) { return (C + 3) & ~3; }
+__host__ __device__ inline int qc_off(int c, int b, int Bp) { return ((((c >> 2) * Bp) + b) << 2) + (c & 3); }
+
 static inline int qc_num_sms()
 {
     static int sms = 0;

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(256, DW ? 1 : 2) k_contract(const ContractArgs
 
     const int ppt = WP * PPW;
     const int ntiles = (a.Ndst + ppt - 1) / ppt;
-    const float* xb = a.X + ((size_t)blk * a.Nsrc * a.Cx + cx0) * Bp + b;
+    const size_t xrow = (size_t)qc_cp4(a.Cx) * Bp, yrow = (size_t)qc_cp4(a.Cy) * Bp;  // floats per point
+    const float* xb = a.X + (size_t)blk * a.Nsrc * xrow;
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * ppt + wp * PPW + s;
@@ -90,10 +91,10 @@ __global__ void __launch_bounds__(256, DW ? 1 : 2) k_contract(const ContractArgs
                     ph[4 * hq + 2] = v.z;
                     ph[4 * hq + 3] = v.w;
                 }
-                const float* xr = xb + (size_t)u * a.Cx * Bp;
+                const float* xr = xb + (size_t)u * xrow;
                 float f[CXC];
 #pragma unroll
-                for (int i = 0; i < CXC; ++i) f[i] = (cx0 + i < a.Cx) ? __ldg(xr + (size_t)i * Bp) : 0.f;
+                for (int i = 0; i < CXC; ++i) f[i] = (cx0 + i < a.Cx) ? __ldg(xr + qc_off(cx0 + i, b, Bp)) : 0.f;
 #pragma unroll
                 for (int i = 0; i < CXC; ++i)
 #pragma unroll
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(256, DW ? 1 : 2) k_contract(const ContractArgs
                     const float* src = out_s + (size_t)(((row >> 5) * WK) * 32 + (row & 31)) * OUT_STRIDE + jj;
                     float v = 0.f;
                     for (int k = 0; k < WK; ++k) v += src[(size_t)k * 32 * OUT_STRIDE];
-                    float* y = a.Y + (((size_t)blk * a.Ndst + dp) * a.Cy + j) * Bp + (row & (Bp - 1));
+                    float* y = a.Y + ((size_t)blk * a.Ndst + dp) * yrow + qc_off(j, row & (Bp - 1), Bp);
                     if (a.KSPLIT > 1) atomicAdd(y, v);
                     else *y = v;
                 }
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(256, DW ? 1 : 2) k_contract(const ContractArgs
                     const int dp = row_dst[row];
                     float v = 0.f;
                     if (dp >= 0 && j < a.Cy)
-                        v = __ldg(a.Z + (((size_t)blk * a.Ndst + dp) * a.Cy + j) * Bp + (row & (Bp - 1)));
+                        v = __ldg(a.Z + ((size_t)blk * a.Ndst + dp) * yrow + qc_off(j, row & (Bp - 1), Bp));
                     Z_s[row * Z_STRIDE + jj] = v;
                 }
                 __syncthreads();
@@ -271,7 +272,8 @@ __global__ void __launch_bounds__(256, 2) k_dphi(const DphiArgs a)
     const bool kvalid = cx0 < a.Cx;
     const int ppt = WP * PPW;
     const int ntiles = (a.Ndst + ppt - 1) / ppt;
-    const float* xb = a.X + ((size_t)blk * a.Nsrc * a.Cx + cx0) * Bp + b;
+    const size_t xrow = (size_t)qc_cp4(a.Cx) * Bp, grow = (size_t)qc_cp4(a.Cg) * Bp;
+    const float* xb = a.X + (size_t)blk * a.Nsrc * xrow;
     const bool writer = (lane & ((1 << (LB - NH)) - 1)) == 0;
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -292,9 +294,9 @@ __global__ void __launch_bounds__(256, 2) k_dphi(const DphiArgs a)
 #pragma unroll
             for (int h = 0; h < HP; ++h) dT[i][h] = 0.f;
         if (pvalid && kvalid) {
-            const float* gp = a.G + ((size_t)blk * a.Ndst + dstp) * a.Cg * Bp + b;
+            const float* gp = a.G + ((size_t)blk * a.Ndst + dstp) * grow;
             for (int j = 0; j < a.Cg; ++j) {
-                const float g = __ldg(gp + (size_t)j * Bp);
+                const float g = __ldg(gp + qc_off(j, b, Bp));
                 const float4* w3 = reinterpret_cast<const float4*>(a.W3 + ((size_t)j * a.Cx + cx0) * HP);
 #pragma unroll
                 for (int i = 0; i < CXC; ++i) {
@@ -321,10 +323,10 @@ __global__ void __launch_bounds__(256, 2) k_dphi(const DphiArgs a)
             if (act) {
                 q = beg + it;
                 const int u = a.src_idx[q];
-                const float* xr = xb + (size_t)u * a.Cx * Bp;
+                const float* xr = xb + (size_t)u * xrow;
                 float f[CXC];
 #pragma unroll
-                for (int i = 0; i < CXC; ++i) f[i] = (cx0 + i < a.Cx) ? __ldg(xr + (size_t)i * Bp) : 0.f;
+                for (int i = 0; i < CXC; ++i) f[i] = (cx0 + i < a.Cx) ? __ldg(xr + qc_off(cx0 + i, b, Bp)) : 0.f;
 #pragma unroll
                 for (int i = 0; i < CXC; ++i)
 #pragma unroll
@@ -433,7 +435,7 @@ int qc_contract(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, const int
     size_t smem = (256 + 256 * Z_STRIDE) * 4;
     if (dw) smem += ((size_t)WP * 32 * (WK * 64 + 4) + (size_t)WK * 64 * a.CyS) * 4;
     if (a.KSPLIT > 1)
-        QC_CUDA(cudaMemsetAsync(Yp, 0, (size_t)nblk * Ndst * Cy * Bp * 4, st));
+        QC_CUDA(cudaMemsetAsync(Yp, 0, (size_t)nblk * Ndst * qc_cp4(Cy) * Bp * 4, st));
 #define QC_LC(HPV)                                                            \
     case HPV:                                                                 \
         return dw ? launch_contract<HPV, true>(a, nblk, smem, st)             \
@@ -448,9 +450,16 @@ int qc_contract(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, const int
     return QC_EUNSUP;
 }
 
+int qc_dphi_num_slices(int Nsrc, int Cx, int Cg, int HP, int B)
+{
+    if (HP <= 0 || B <= 0) return 1;
+    if (qc_dphi_fast_ok(Nsrc, Cx, Cg, HP, B)) return qc_ceil_div(Cx, 64 / HP) * qc_nblk(B);
+    return 1;
+}
+
 int qc_dphi(const float* Xp, int Nsrc, int Cx, const float* Gp, int Cg, const int* seg_ptr,
             const int* src_idx, const float* W3, int H, int HP, const int* order, int Ndst, int B,
-            float* dphi, void* stream)
+            int64_t P, float* dphi, void* stream)
 {
     if (Nsrc <= 0 || Ndst <= 0 || Cx <= 0 || Cg <= 0 || B <= 0 || H <= 0 || H > HP) return QC_EINVAL;
     if (!(HP == 4 || HP == 8 || HP == 16 || HP == 32)) return QC_EUNSUP;
@@ -460,7 +469,7 @@ int qc_dphi(const float* Xp, int Nsrc, int Cx, const float* Gp, int Cg, const in
     const int NKC = qc_ceil_div(Cx, CXC);
     DphiArgs a;
     a.X = Xp; a.G = Gp; a.W3 = W3; a.seg_ptr = seg_ptr; a.src_idx = src_idx; a.order = order; a.dphi = dphi;
-    a.Nsrc = Nsrc; a.Ndst = Ndst; a.Cx = Cx; a.Cg = Cg; a.H = H;
+    a.Nsrc = Nsrc; a.Ndst = Ndst; a.Cx = Cx; a.Cg = Cg; a.H = H; a.P = P;
     int WK = 1;
     while (WK * 2 <= 8 && WK * 2 <= NKC) WK *= 2;
     a.LWK = ilog2(WK);
@@ -471,6 +480,7 @@ int qc_dphi(const float* Xp, int Nsrc, int Cx, const float* Gp, int Cg, const in
         const int rc = qc_dphi_fast(a, HP, B, st);
         if (rc != 0) return rc == 1 ? 0 : rc;
     }
+    QC_CUDA(cudaMemsetAsync(dphi, 0, (size_t)P * HP * 4, st));   // the generic kernel accumulates with atomics
     switch (HP) {
         case 4: return dispatch_dphi<4>(a, LB, nksplit, nblk, st);
         case 8: return dispatch_dphi<8>(a, LB, nksplit, nblk, st);

@@ -19,22 +19,30 @@ namespace {
 constexpr int TS = 68;  // row stride of the T tile in shared memory (floats, 16-byte aligned rows)
 constexpr int ZS = 36;  // row stride of the Z tile
 
+constexpr int PCH = 64;  // pairs staged per chunk (indices + phi rows in shared memory)
+
 template <int HP, int LB, bool DW>
-__global__ void __launch_bounds__(256, DW ? 1 : 2)
+__global__ void __launch_bounds__(256, 1)
 k_contract_fast(const ContractArgs a, const int nkc, const int dw_in_smem)
 {
     constexpr int CXC = 64 / HP, Bp = 1 << LB, PPW = 32 >> LB;
+    constexpr int NG = CXC / 4, HQ = HP / 4;
+    constexpr int D = 8;  // gathered pairs in flight per thread
+    constexpr int PHS = PCH * HP + 4;  // per-point phi slab stride (padded: distinct banks per sub-group)
     extern __shared__ __align__(16) float smem[];
-    float* W2s = smem;             // [64][32]
-    float* T_s = W2s + 64 * 32;    // DW: [256][TS]
-    float* Z_s = T_s + 256 * TS;   // DW: [256][ZS]
-    float* dW_s = Z_s + 256 * ZS;  // DW && dw_in_smem: [nkc*64][32]
+    float* W2s = smem;                                   // [64][32]
+    float* phi_s = W2s + 64 * 32;                        // [8*PPW][PHS]
+    int* idx_s = reinterpret_cast<int*>(phi_s + 8 * PPW * PHS);  // [8*PPW][PCH]
+    float* T_s = reinterpret_cast<float*>(idx_s + 8 * PPW * PCH);  // DW: [256][TS]
+    float* Z_s = T_s + 256 * TS;                         // DW: [256][ZS]
+    float* dW_s = Z_s + 256 * ZS;                        // DW && dw_in_smem: [nkc*64][32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = lane >> LB, b = lane & (Bp - 1);
     const int blk = blockIdx.y;
-    const size_t rowstride = (size_t)a.Cx * Bp;
-    const float* Xb = a.X + (size_t)blk * a.Nsrc * rowstride + b;
+    const unsigned xrow = (unsigned)qc_cp4(a.Cx) * Bp;   // floats per source point
+    const size_t yrow = (size_t)qc_cp4(a.Cy) * Bp;
+    const float* Xb = a.X + (size_t)blk * a.Nsrc * xrow + b * 4;
     constexpr int ppt = 8 * PPW;
     const int ntiles = (a.Ndst + ppt - 1) / ppt;
 
@@ -50,7 +58,7 @@ k_contract_fast(const ContractArgs a, const int nkc, const int dw_in_smem)
             beg = a.seg_ptr[dstp];
             len = a.seg_ptr[dstp + 1] - beg;
         }
-        const int maxlen = qc_warp_max_i(len);
+        const int maxlen = PPW == 1 ? len : qc_warp_max_i(len);
         const int* sidx = a.src_idx + beg;
         const int* pidx = a.phi_idx ? a.phi_idx + beg : nullptr;
 
@@ -61,14 +69,19 @@ k_contract_fast(const ContractArgs a, const int nkc, const int dw_in_smem)
         if (DW) {
             __syncthreads();  // the previous tile's last mini-GEMM is done with Z_s
             float* zr = Z_s + (warp * 32 + lane) * ZS;
-            const float* zg = a.Z + ((size_t)blk * a.Ndst + (pvalid ? dstp : 0)) * a.Cy * Bp + b;
+            const float* zg = a.Z + ((size_t)blk * a.Ndst + (pvalid ? dstp : 0)) * yrow + b * 4;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) zr[j] = (pvalid && j < a.Cy) ? __ldg(zg + (size_t)j * Bp) : 0.f;
+            for (int g = 0; g < 8; ++g) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pvalid && 4 * g < a.Cy) v = __ldg(reinterpret_cast<const float4*>(zg + (size_t)g * Bp * 4));
+                *reinterpret_cast<float4*>(zr + 4 * g) = v;
+            }
         }
 
         for (int kc = 0; kc < nkc; ++kc) {
             const int cx0 = kc * CXC;
             const int nval = min(CXC, a.Cx - cx0);
+            const int ngv = (nval + 3) >> 2;  // channel groups of this chunk that exist
             __syncthreads();  // W2s / T_s of the previous chunk are no longer read
             for (int idx = tid; idx < 64 * 32; idx += 256) {
                 const int k = idx >> 5, j = idx & 31;
@@ -78,69 +91,71 @@ k_contract_fast(const ContractArgs a, const int nkc, const int dw_in_smem)
                 W2s[idx] = v;
             }
 
-            // ---- stage B: segmented gather-accumulate over the pair list, software pipelined ----
+            // ---- stage B: segmented gather-accumulate, D pairs in flight ------------------------
             float T[CXC][HP];
 #pragma unroll
             for (int i = 0; i < CXC; ++i)
 #pragma unroll
                 for (int h = 0; h < HP; ++h) T[i][h] = 0.f;
 
-            const float* Xc = Xb + (size_t)cx0 * Bp;
-            float f_c[CXC], ph_c[HP], f_n[CXC], ph_n[HP];
+            const float* Xc = Xb + (size_t)(cx0 >> 2) * (Bp * 4);
+            float* my_phi = phi_s + (warp * PPW + s) * PHS;
+            int* my_idx = idx_s + (warp * PPW + s) * PCH;
+            float4 buf[D][NG];
 #pragma unroll
-            for (int i = 0; i < CXC; ++i) f_c[i] = 0.f;
+            for (int d = 0; d < D; ++d)
 #pragma unroll
-            for (int h = 0; h < HP; ++h) ph_c[h] = 0.f, ph_n[h] = 0.f;
-            int u_n = 0, p_n = 0;
-            if (0 < len) {
-                const int u = sidx[0];
-                const int pp = pidx ? pidx[0] : beg;
-                const float4* php = reinterpret_cast<const float4*>(a.phi + (size_t)pp * HP);
+                for (int g = 0; g < NG; ++g) buf[d][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto issue = [&](float4 (&xb)[NG], int e) {
+                const unsigned u = (unsigned)my_idx[e];
+                const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)(u * xrow));
 #pragma unroll
-                for (int hq = 0; hq < HP / 4; ++hq) {
-                    const float4 v = __ldg(php + hq);
-                    ph_c[4 * hq] = v.x, ph_c[4 * hq + 1] = v.y, ph_c[4 * hq + 2] = v.z, ph_c[4 * hq + 3] = v.w;
+                for (int g = 0; g < NG; ++g)
+                    if (g < ngv) xb[g] = __ldg(xr + g * Bp);
+            };
+            auto consume = [&](const float4 (&xb)[NG], int e) {
+                float ph[HP];
+                const float4* pr = reinterpret_cast<const float4*>(my_phi + e * HP);
+#pragma unroll
+                for (int q = 0; q < HQ; ++q) {
+                    const float4 v = pr[q];
+                    ph[4 * q] = v.x, ph[4 * q + 1] = v.y, ph[4 * q + 2] = v.z, ph[4 * q + 3] = v.w;
                 }
-                const float* xr = Xc + (size_t)u * rowstride;
 #pragma unroll
-                for (int i = 0; i < CXC; ++i)
-                    if (i < nval) f_c[i] = __ldg(xr + i * Bp);
-            }
-            if (1 < len) {
-                u_n = sidx[1];
-                p_n = pidx ? pidx[1] : beg + 1;
-            }
-#pragma unroll 2
-            for (int it = 0; it < maxlen; ++it) {
-                // data of pair it+1
+                for (int g = 0; g < NG; ++g) {
+                    const float f[4] = {xb[g].x, xb[g].y, xb[g].z, xb[g].w};
 #pragma unroll
-                for (int i = 0; i < CXC; ++i) f_n[i] = 0.f;
-                if (it + 1 < len) {
-                    const float4* php = reinterpret_cast<const float4*>(a.phi + (size_t)p_n * HP);
+                    for (int e2 = 0; e2 < 4; ++e2)
 #pragma unroll
-                    for (int hq = 0; hq < HP / 4; ++hq) {
-                        const float4 v = __ldg(php + hq);
-                        ph_n[4 * hq] = v.x, ph_n[4 * hq + 1] = v.y, ph_n[4 * hq + 2] = v.z, ph_n[4 * hq + 3] = v.w;
+                        for (int h = 0; h < HP; ++h) T[4 * g + e2][h] = fmaf(f[e2], ph[h], T[4 * g + e2][h]);
+                }
+            };
+            for (int c0 = 0; c0 < maxlen; c0 += PCH) {
+                const int clen = min(PCH, len - c0);        // this lane's point (may be <= 0)
+                const int cmax = min(PCH, maxlen - c0);     // warp-uniform
+                __syncwarp();
+                // stage the pair indices and phi rows of this chunk (coalesced, once per chunk)
+                for (int e = b; e < clen; e += Bp) {
+                    const int p = c0 + e;
+                    my_idx[e] = sidx[p];
+                    const int pp = pidx ? pidx[p] : beg + p;
+                    const float4* php = reinterpret_cast<const float4*>(a.phi + (size_t)pp * HP);
+#pragma unroll
+                    for (int q = 0; q < HQ; ++q) reinterpret_cast<float4*>(my_phi + e * HP)[q] = __ldg(php + q);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                    if (d < clen) issue(buf[d], d);
+                for (int it = 0; it < cmax; it += D) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        if (it + d < clen) {
+                            consume(buf[d], it + d);
+                            if (it + d + D < clen) issue(buf[d], it + d + D);
+                        }
                     }
-                    const float* xr = Xc + (size_t)u_n * rowstride;
-#pragma unroll
-                    for (int i = 0; i < CXC; ++i)
-                        if (i < nval) f_n[i] = __ldg(xr + i * Bp);
                 }
-                // indices of pair it+2
-                if (it + 2 < len) {
-                    u_n = sidx[it + 2];
-                    p_n = pidx ? pidx[it + 2] : beg + it + 2;
-                }
-                // accumulate pair it (f_c is zero for lanes past their segment)
-#pragma unroll
-                for (int i = 0; i < CXC; ++i)
-#pragma unroll
-                    for (int h = 0; h < HP; ++h) T[i][h] = fmaf(f_c[i], ph_c[h], T[i][h]);
-#pragma unroll
-                for (int i = 0; i < CXC; ++i) f_c[i] = f_n[i];
-#pragma unroll
-                for (int h = 0; h < HP; ++h) ph_c[h] = ph_n[h];
             }
 
             __syncthreads();  // W2s staged
@@ -223,10 +238,12 @@ k_contract_fast(const ContractArgs a, const int nkc, const int dw_in_smem)
         }
 
         if (pvalid) {
-            float* y = a.Y + ((size_t)blk * a.Ndst + dstp) * a.Cy * Bp + b;
+            float* y = a.Y + ((size_t)blk * a.Ndst + dstp) * yrow + b * 4;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j < a.Cy) y[(size_t)j * Bp] = acc[j];
+            for (int g = 0; g < 8; ++g)
+                if (4 * g < a.Cy)
+                    *reinterpret_cast<float4*>(y + (size_t)g * Bp * 4) =
+                        make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
         }
     }
 
@@ -270,21 +287,25 @@ __device__ __forceinline__ int subgroup_reduce_f(float (&v)[HP], int lane)
 }
 
 template <int HP, int LB>
-__global__ void __launch_bounds__(256, 2)
-k_dphi_fast(const DphiArgs a, const int nkc, const int use_atomic)
+__global__ void __launch_bounds__(256, 1)
+k_dphi_fast(const DphiArgs a, const int nkc, const size_t slice_stride)
 {
     constexpr int CXC = 64 / HP, Bp = 1 << LB, PPW = 32 >> LB;
+    constexpr int NG = CXC / 4;
+    constexpr int D = 8;
     constexpr int LH = ilog2f(HP);
     constexpr int NH = LB < LH ? LB : LH;
     constexpr int NF = HP >> NH;
     extern __shared__ __align__(16) float smem[];
     float* W3s = smem;  // [32 j][64 k]
+    int* idx_s = reinterpret_cast<int*>(W3s + 32 * 64);  // [8*PPW][PCH]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = lane >> LB, b = lane & (Bp - 1);
     const int blk = blockIdx.y;
-    const size_t rowstride = (size_t)a.Cx * Bp;
-    const float* Xb = a.X + (size_t)blk * a.Nsrc * rowstride + b;
+    const unsigned xrow = (unsigned)qc_cp4(a.Cx) * Bp;
+    const size_t grow = (size_t)qc_cp4(a.Cg) * Bp;
+    const float* Xb = a.X + (size_t)blk * a.Nsrc * xrow + b * 4;
     constexpr int ppt = 8 * PPW;
     const int ntiles = (a.Ndst + ppt - 1) / ppt;
     const bool writer = (lane & ((1 << (LB - NH)) - 1)) == 0;
@@ -303,14 +324,19 @@ k_dphi_fast(const DphiArgs a, const int nkc, const int use_atomic)
 
         float g[32];
         {
-            const float* gp = a.G + ((size_t)blk * a.Ndst + (pvalid ? dstp : 0)) * a.Cg * Bp + b;
+            const float* gp = a.G + ((size_t)blk * a.Ndst + (pvalid ? dstp : 0)) * grow + b * 4;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) g[j] = (pvalid && j < a.Cg) ? __ldg(gp + (size_t)j * Bp) : 0.f;
+            for (int q = 0; q < 8; ++q) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pvalid && 4 * q < a.Cg) v = __ldg(reinterpret_cast<const float4*>(gp + (size_t)q * Bp * 4));
+                g[4 * q] = v.x, g[4 * q + 1] = v.y, g[4 * q + 2] = v.z, g[4 * q + 3] = v.w;
+            }
         }
 
         for (int kc = 0; kc < nkc; ++kc) {
             const int cx0 = kc * CXC;
             const int nval = min(CXC, a.Cx - cx0);
+            const int ngv = (nval + 3) >> 2;
             __syncthreads();
             for (int idx = tid; idx < 32 * 64; idx += 256) {
                 const int j = idx >> 6, k = idx & 63;
@@ -342,49 +368,62 @@ k_dphi_fast(const DphiArgs a, const int nkc, const int use_atomic)
                     }
             }
 
-            const float* Xc = Xb + (size_t)cx0 * Bp;
-            float f_c[CXC], f_n[CXC];
+            const float* Xc = Xb + (size_t)(cx0 >> 2) * (Bp * 4);
+            int* my_idx = idx_s + (warp * PPW + s) * PCH;
+            float4 xbuf[D][NG];
 #pragma unroll
-            for (int i = 0; i < CXC; ++i) f_c[i] = 0.f;
-            int u_n = 0;
-            if (0 < len) {
-                const float* xr = Xc + (size_t)sidx[0] * rowstride;
+            for (int d = 0; d < D; ++d)
 #pragma unroll
-                for (int i = 0; i < CXC; ++i)
-                    if (i < nval) f_c[i] = __ldg(xr + i * Bp);
-            }
-            if (1 < len) u_n = sidx[1];
-#pragma unroll 2
-            for (int it = 0; it < maxlen; ++it) {
+                for (int q = 0; q < NG; ++q) xbuf[d][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto issue = [&](float4 (&xb)[NG], int e) {
+                const unsigned u = (unsigned)my_idx[e];
+                const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)(u * xrow));
 #pragma unroll
-                for (int i = 0; i < CXC; ++i) f_n[i] = 0.f;
-                if (it + 1 < len) {
-                    const float* xr = Xc + (size_t)u_n * rowstride;
+                for (int q = 0; q < NG; ++q)
+                    if (q < ngv) xb[q] = __ldg(xr + q * Bp);
+            };
+            for (int c0 = 0; c0 < maxlen; c0 += PCH) {
+                const int clen = min(PCH, len - c0);
+                const int cmax = min(PCH, maxlen - c0);
+                __syncwarp();
+                for (int e = b; e < clen; e += Bp) my_idx[e] = sidx[c0 + e];
+                __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < CXC; ++i)
-                        if (i < nval) f_n[i] = __ldg(xr + i * Bp);
-                }
-                if (it + 2 < len) u_n = sidx[it + 2];
-                float part[HP];
+                for (int d = 0; d < D; ++d)
+                    if (d < clen) issue(xbuf[d], d);
+                for (int it = 0; it < cmax; it += D) {
 #pragma unroll
-                for (int h = 0; h < HP; ++h) part[h] = 0.f;
+                    for (int d = 0; d < D; ++d) {
+                        if (it + d < cmax) {   // warp-uniform: the shuffles below need every lane
+                            const bool act = it + d < clen;
+                            float part[HP];
 #pragma unroll
-                for (int i = 0; i < CXC; ++i)
+                            for (int h = 0; h < HP; ++h) part[h] = 0.f;
 #pragma unroll
-                    for (int h = 0; h < HP; ++h) part[h] = fmaf(f_c[i], dT[i][h], part[h]);
-                const int hsel = subgroup_reduce_f<HP, LB>(part, lane);
-                if (it < len && writer) {
-                    float* dst = a.dphi + (size_t)(beg + it) * HP + hsel * NF;
+                            for (int q = 0; q < NG; ++q) {
+                                const float f[4] = {xbuf[d][q].x, xbuf[d][q].y, xbuf[d][q].z, xbuf[d][q].w};
 #pragma unroll
-                    for (int k = 0; k < NF; ++k) {
-                        if (hsel * NF + k < a.H) {
-                            if (use_atomic) atomicAdd(dst + k, part[k]);
-                            else dst[k] += part[k];
+                                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                                    for (int h = 0; h < HP; ++h) part[h] = fmaf(f[e], dT[4 * q + e][h], part[h]);
+                            }
+                            if (!act) {
+#pragma unroll
+                                for (int h = 0; h < HP; ++h) part[h] = 0.f;
+                            }
+                            const int hsel = subgroup_reduce_f<HP, LB>(part, lane);
+                            if (act && writer) {
+                                // one slice per (batch block, channel chunk): plain stores, summed by
+                                // qc_pair_phi_bwd in fixed order (deterministic, no read-modify-write)
+                                float* dst = a.dphi + (size_t)(blk * nkc + kc) * slice_stride +
+                                             (size_t)(beg + c0 + it + d) * HP + hsel * NF;
+#pragma unroll
+                                for (int k = 0; k < NF; ++k) dst[k] = part[k];
+                            }
+                            if (it + d + D < clen) issue(xbuf[d], it + d + D);
                         }
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < CXC; ++i) f_c[i] = f_n[i];
             }
         }
     }
@@ -396,7 +435,7 @@ int launch_cf(const ContractArgs& a, int B, cudaStream_t st)
     constexpr int CXC = 64 / HP, PPW = 32 >> LB;
     const int nkc = qc_ceil_div(a.Cx, CXC);
     const int nblk = qc_nblk(B);
-    size_t smem = 64 * 32 * 4;
+    size_t smem = (64 * 32 + 8 * PPW * (PCH * HP + 4) + 8 * PPW * PCH) * 4;
     int dw_in_smem = 0;
     if (DW) {
         smem += (256 * TS + 256 * ZS) * 4;
@@ -407,7 +446,7 @@ int launch_cf(const ContractArgs& a, int B, cudaStream_t st)
     }
     QC_CUDA(cudaFuncSetAttribute(k_contract_fast<HP, LB, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = qc_ceil_div(a.Ndst, 8 * PPW);
-    int gx = qc_num_sms() * (DW ? 1 : 2);
+    int gx = qc_num_sms();
     gx = (gx + nblk - 1) / nblk;
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
@@ -423,14 +462,15 @@ int launch_df(const DphiArgs& a, int B, cudaStream_t st)
     constexpr int CXC = 64 / HP, PPW = 32 >> LB;
     const int nkc = qc_ceil_div(a.Cx, CXC);
     const int nblk = qc_nblk(B);
-    const size_t smem = 32 * 64 * 4;
+    const size_t smem = (32 * 64 + 8 * PPW * PCH) * 4;
     const int ntiles = qc_ceil_div(a.Ndst, 8 * PPW);
-    int gx = qc_num_sms() * 2;
+    int gx = qc_num_sms();
     gx = (gx + nblk - 1) / nblk;
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     dim3 grid(gx, nblk);
-    k_dphi_fast<HP, LB><<<grid, 256, smem, st>>>(a, nkc, nblk > 1 ? 1 : 0);
+    QC_CUDA(cudaFuncSetAttribute(k_dphi_fast<HP, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dphi_fast<HP, LB><<<grid, 256, smem, st>>>(a, nkc, (size_t)a.P * HP);
     QC_CHECK_LAUNCH();
     return 1;
 }
@@ -441,6 +481,7 @@ int qc_contract_fast(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t
 {
     const int Bp = qc_bp(B);
     if (a.Cy > 32 || !(HP == 4 || HP == 8) || !(Bp == 8 || Bp == 32)) return 0;
+    if ((size_t)a.Nsrc * qc_cp4(a.Cx) * Bp >= ((size_t)1 << 32)) return 0;   // 32-bit row offsets
     if (nullptr != getenv("QC_NO_FAST")) return 0;
 #define QC_F(HPV, LBV) (dw ? launch_cf<HPV, LBV, true>(a, B, st) : launch_cf<HPV, LBV, false>(a, B, st))
     if (HP == 4) return Bp == 8 ? QC_F(4, 3) : QC_F(4, 5);
@@ -448,10 +489,20 @@ int qc_contract_fast(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t
 #undef QC_F
 }
 
+bool qc_dphi_fast_ok(int Nsrc, int Cx, int Cg, int HP, int B)
+{
+    const int Bp = qc_bp(B);
+    if (Cg > 32 || !(HP == 4 || HP == 8) || !(Bp == 8 || Bp == 32)) return false;
+    if ((size_t)Nsrc * qc_cp4(Cx) * Bp >= ((size_t)1 << 32)) return false;
+    if (nullptr != getenv("QC_NO_FAST")) return false;
+    return true;
+}
+
 int qc_dphi_fast(const DphiArgs& a, int HP, int B, cudaStream_t st)
 {
     const int Bp = qc_bp(B);
     if (a.Cg > 32 || !(HP == 4 || HP == 8) || !(Bp == 8 || Bp == 32)) return 0;
+    if ((size_t)a.Nsrc * qc_cp4(a.Cx) * Bp >= ((size_t)1 << 32)) return 0;
     if (nullptr != getenv("QC_NO_FAST")) return 0;
     if (HP == 4) return Bp == 8 ? launch_df<4, 3>(a, B, st) : launch_df<4, 5>(a, B, st);
     return Bp == 8 ? launch_df<8, 3>(a, B, st) : launch_df<8, 5>(a, B, st);

@@ -8,26 +8,27 @@
 
 namespace {
 
-// grid: (ceil(N/32), C, nblk); block 256 = 8 warps.  Tile: 32 points x 32 batch lanes.
+// grid: (ceil(N/32), CP4/4, nblk); block 256 = 8 warps.  Tile: 32 points x 4 channels x Bp lanes.
 __global__ void __launch_bounds__(256)
 k_pack(const float* __restrict__ x, int B, int C, int N, int Bp, float* __restrict__ xp)
 {
-    __shared__ float tile[32][33];
-    const int n0 = blockIdx.x * 32, c = blockIdx.y, blk = blockIdx.z;
+    __shared__ float tile[4][32][33];  // [channel in group][batch lane][point]
+    const int n0 = blockIdx.x * 32, cg = blockIdx.y, blk = blockIdx.z;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    // read: rows = batch lane, contiguous along n
-    for (int bl = w; bl < Bp; bl += 8) {
-        int b = blk * 32 + bl, n = n0 + lane;
+    const int CG = gridDim.y;
+    for (int r = w; r < 4 * Bp; r += 8) {
+        const int e = r / Bp, bl = r % Bp;
+        const int c = cg * 4 + e, b = blk * 32 + bl, n = n0 + lane;
         float v = 0.f;
-        if (b < B && n < N) v = x[((size_t)b * C + c) * N + n];
-        tile[bl][lane] = v;
+        if (c < C && b < B && n < N) v = x[((size_t)b * C + c) * N + n];
+        tile[e][bl][lane] = v;
     }
     __syncthreads();
-    // write: for each point, Bp contiguous floats
-    for (int idx = threadIdx.x; idx < 32 * Bp; idx += 256) {
-        int nl = idx / Bp, bl = idx % Bp;
-        int n = n0 + nl;
-        if (n < N) xp[(((size_t)blk * N + n) * C + c) * Bp + bl] = tile[bl][nl];
+    // write: per point Bp*4 contiguous floats, (lane, channel-in-group) innermost
+    for (int idx = threadIdx.x; idx < 32 * Bp * 4; idx += 256) {
+        const int e = idx & 3, bl = (idx >> 2) % Bp, nl = (idx >> 2) / Bp;
+        const int n = n0 + nl;
+        if (n < N) xp[((((size_t)blk * N + n) * CG + cg) * Bp + bl) * 4 + e] = tile[e][bl][nl];
     }
 }
 
@@ -35,20 +36,24 @@ __global__ void __launch_bounds__(256)
 k_unpack(const float* __restrict__ xp, int B, int C, int N, int Bp, const float* __restrict__ bias,
          float* __restrict__ x)
 {
-    __shared__ float tile[32][33];
-    const int n0 = blockIdx.x * 32, c = blockIdx.y, blk = blockIdx.z;
+    __shared__ float tile[4][32][33];
+    const int n0 = blockIdx.x * 32, cg = blockIdx.y, blk = blockIdx.z;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int idx = threadIdx.x; idx < 32 * Bp; idx += 256) {
-        int nl = idx / Bp, bl = idx % Bp;
-        int n = n0 + nl;
-        tile[bl][nl] = n < N ? xp[(((size_t)blk * N + n) * C + c) * Bp + bl] : 0.f;
+    const int CG = gridDim.y;
+    for (int idx = threadIdx.x; idx < 32 * Bp * 4; idx += 256) {
+        const int e = idx & 3, bl = (idx >> 2) % Bp, nl = (idx >> 2) / Bp;
+        const int n = n0 + nl;
+        tile[e][bl][nl] = n < N ? xp[((((size_t)blk * N + n) * CG + cg) * Bp + bl) * 4 + e] : 0.f;
     }
     __syncthreads();
     const int n = n0 + lane;
-    const float bv = (bias != nullptr && n < N) ? bias[(size_t)c * N + n] : 0.f;
-    for (int bl = w; bl < Bp; bl += 8) {
-        int b = blk * 32 + bl;
-        if (b < B && n < N) x[((size_t)b * C + c) * N + n] = tile[bl][lane] + bv;
+    for (int r = w; r < 4 * Bp; r += 8) {
+        const int e = r / Bp, bl = r % Bp;
+        const int c = cg * 4 + e, b = blk * 32 + bl;
+        if (c < C && b < B && n < N) {
+            const float bv = bias != nullptr ? bias[(size_t)c * N + n] : 0.f;
+            x[((size_t)b * C + c) * N + n] = tile[e][bl][lane] + bv;
+        }
     }
 }
 
@@ -99,8 +104,8 @@ extern "C" {
 
 int qc_pack_features(const float* x, int B, int C, int N, float* xp, void* stream)
 {
-    if (B <= 0 || C <= 0 || N <= 0 || C > 65535) return QC_EINVAL;
-    dim3 grid(qc_ceil_div(N, 32), C, qc_nblk(B));
+    if (B <= 0 || C <= 0 || N <= 0 || C > 4 * 65535) return QC_EINVAL;
+    dim3 grid(qc_ceil_div(N, 32), qc_cp4(C) / 4, qc_nblk(B));
     k_pack<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, C, N, qc_bp(B), xp);
     QC_CHECK_LAUNCH();
     return 0;
@@ -108,8 +113,8 @@ int qc_pack_features(const float* x, int B, int C, int N, float* xp, void* strea
 
 int qc_unpack_features(const float* xp, int B, int C, int N, const float* bias, float* x, void* stream)
 {
-    if (B <= 0 || C <= 0 || N <= 0 || C > 65535) return QC_EINVAL;
-    dim3 grid(qc_ceil_div(N, 32), C, qc_nblk(B));
+    if (B <= 0 || C <= 0 || N <= 0 || C > 4 * 65535) return QC_EINVAL;
+    dim3 grid(qc_ceil_div(N, 32), qc_cp4(C) / 4, qc_nblk(B));
     k_unpack<<<grid, 256, 0, (cudaStream_t)stream>>>(xp, B, C, N, qc_bp(B), bias, x);
     QC_CHECK_LAUNCH();
     return 0;

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128)
 k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_pts,
                const float* __restrict__ quad_w, const int* __restrict__ pair_row,
                const int* __restrict__ pair_col, int64_t P, int d, MlpDev m, int HP,
-               const float* __restrict__ dphi, float* __restrict__ d_quad_w)
+               const float* __restrict__ dphi, int nslices, float* __restrict__ d_quad_w)
 {
     constexpr int NT = 128;
     extern __shared__ float smem[];
@@ -133,7 +133,9 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
         float dwq = 0.f;
 #pragma unroll
         for (int h = 0; h < WMAX; ++h) {
-            float g = (valid && h < H && h < HP) ? dphi[(size_t)p * HP + h] : 0.f;
+            float g = 0.f;
+            if (valid && h < H && h < HP)
+                for (int sl = 0; sl < nslices; ++sl) g += dphi[((size_t)sl * P + p) * HP + h];
             dwq = fmaf(g, xs[L][h], dwq);
             dx[h] = wq * g;
         }
@@ -218,12 +220,12 @@ int launch_fwd(const float* out_pts, const float* in_pts, const float* quad_w, c
 template <int WMAX>
 int launch_bwd(const float* out_pts, const float* in_pts, const float* quad_w, const int* pair_row,
                const int* pair_col, int64_t P, int d, const MlpDev& m, int HP, const float* dphi,
-               float* d_quad_w, cudaStream_t st)
+               int nslices, float* d_quad_w, cudaStream_t st)
 {
     size_t smem = ((size_t)2 * m.n_hidden * WMAX * WMAX + 2 * 128 * WMAX) * 4;
     QC_CUDA(cudaFuncSetAttribute(k_pair_phi_bwd<WMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 4);
-    k_pair_phi_bwd<WMAX><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, d_quad_w);
+    k_pair_phi_bwd<WMAX><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w);
     QC_CHECK_LAUNCH();
     return 0;
 }
@@ -257,11 +259,11 @@ int qc_pair_phi_fwd(const float* out_pts, const float* in_pts, const float* quad
 
 int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad_w,
                     const int* pair_row, const int* pair_col, int64_t P, int d,
-                    const qc_mlp_t* mlp, int HP, const float* dphi, float* const* d_mlp_w,
-                    float* d_quad_w, void* stream)
+                    const qc_mlp_t* mlp, int HP, const float* dphi, int nslices,
+                    float* const* d_mlp_w, float* d_quad_w, void* stream)
 {
     if (P <= 0) return 0;
-    if (d < 1 || d > 3) return QC_EUNSUP;
+    if (d < 1 || d > 3 || nslices < 1) return QC_EUNSUP;
     MlpDev m;
     int rc = fill_dev(mlp, d, m);
     if (rc) return rc;
@@ -272,10 +274,10 @@ int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad
     cudaStream_t st = (cudaStream_t)stream;
     const int wsel = wmax > HP ? wmax : HP;
     switch (wsel) {
-        case 4: return launch_bwd<4>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, d_quad_w, st);
-        case 8: return launch_bwd<8>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, d_quad_w, st);
-        case 16: return launch_bwd<16>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, d_quad_w, st);
-        case 32: return launch_bwd<32>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, d_quad_w, st);
+        case 4: return launch_bwd<4>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
+        case 8: return launch_bwd<8>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
+        case 16: return launch_bwd<16>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
+        case 32: return launch_bwd<32>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
     }
     return QC_EUNSUP;
 }

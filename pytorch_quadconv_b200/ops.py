@@ -40,6 +40,11 @@ def _nblk(B: int) -> int:
     return (B + 31) // 32
 
 
+def _packed_shape(B: int, Cc: int, N: int):
+    """Packed feature layout [nblk][N][CP4/4][Bp][4] (csrc/common.cuh)."""
+    return (_nblk(B), N, ((Cc + 3) // 4), _bp(B), 4)
+
+
 def _f32c(t: Tensor, name: str) -> Tensor:
     if t.dtype != torch.float32:
         raise RuntimeError(f"{name} must be float32 (got {t.dtype}); the fp32 path is the only one built")
@@ -155,7 +160,7 @@ def _(eval_indices, n_out, n_in):
 
 def _pack(x: Tensor) -> Tensor:
     B, Cc, N = x.shape
-    xp = torch.empty((_nblk(B), N, Cc, _bp(B)), dtype=torch.float32, device=x.device)
+    xp = torch.empty(_packed_shape(B, Cc, N), dtype=torch.float32, device=x.device)
     C.check(C.lib().qc_pack_features(C.ptr(x), B, Cc, N, C.ptr(xp), C.stream()), "qc_pack_features")
     return xp
 
@@ -197,7 +202,7 @@ def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor
     CoP = (Co + 3) & ~3
     W2 = torch.empty((Ci * H, CoP), dtype=torch.float32, device=dev)
     C.check(L.qc_repack_wlast(C.ptr(w_last), Ci, Co, H, HP, 0, C.ptr(W2), st), "qc_repack_wlast")
-    yp = torch.empty((_nblk(B), No, Co, _bp(B)), dtype=torch.float32, device=dev)
+    yp = torch.empty(_packed_shape(B, Co, No), dtype=torch.float32, device=dev)
     C.check(L.qc_contract(C.ptr(xp), Ni, Ci, C.ptr(row_ptr), C.ptr(pair_col), None, C.ptr(phi), H, HP,
                           C.ptr(W2), Co, C.ptr(order_out), No, B, C.ptr(yp), None, None, st), "qc_contract")
     b2 = None
@@ -214,7 +219,7 @@ def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair
     No = out_pts.shape[0]
     HP = _hp(w_last.shape[1])
     return (features.new_empty((B, out_channels, No)), features.new_empty((pair_row.shape[0], HP)),
-            features.new_empty((_nblk(B), Ni, Ci, _bp(B))))
+            features.new_empty(_packed_shape(B, Ci, Ni)))
 
 
 @torch.library.custom_op("quadconv_b200::qc_backward", mutates_args=())
@@ -246,23 +251,24 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
     # d phi (grouped by out point), then back through the hidden layers per pair
     W3 = torch.empty((Co, Ci, HP), **f32)
     C.check(L.qc_repack_wlast(C.ptr(w_last), Ci, Co, H, HP, 2, C.ptr(W3), st), "qc_repack_wlast")
-    dphi = torch.zeros((max(P, 1), HP), **f32)
+    nsl = L.qc_dphi_num_slices(Ni, Ci, Co, HP, B)
+    dphi = torch.empty((nsl, max(P, 1), HP), **f32)
     C.check(L.qc_dphi(C.ptr(xp), Ni, Ci, C.ptr(gp), Co, C.ptr(row_ptr), C.ptr(pair_col), C.ptr(W3), H, HP,
-                      C.ptr(order_out), No, B, C.ptr(dphi), st), "qc_dphi")
+                      C.ptr(order_out), No, B, P, C.ptr(dphi), st), "qc_dphi")
     d_hidden = [torch.zeros_like(w) for w in hidden_ws]
     d_quad_w = torch.zeros(Ni, **f32)
     mlp = C.make_mlp(d, hidden_ws)
     import ctypes
     dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
     C.check(L.qc_pair_phi_bwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row), C.ptr(pair_col),
-                              P, d, mlp, HP, C.ptr(dphi), dptrs, C.ptr(d_quad_w), st), "qc_pair_phi_bwd")
+                              P, d, mlp, HP, C.ptr(dphi), nsl, dptrs, C.ptr(d_quad_w), st), "qc_pair_phi_bwd")
 
     # d features (grouped by in point through the CSC tables) + d W_last in the same pass
     CiP = (Ci + 3) & ~3
     W2t = torch.empty((Co * H, CiP), **f32)
     C.check(L.qc_repack_wlast(C.ptr(w_last), Ci, Co, H, HP, 1, C.ptr(W2t), st), "qc_repack_wlast")
     dW2 = torch.zeros((Co * H, CiP), **f32)
-    dxp = torch.empty((_nblk(B), Ni, Ci, _bp(B)), **f32)
+    dxp = torch.empty(_packed_shape(B, Ci, Ni), **f32)
     C.check(L.qc_contract(C.ptr(gp), No, Co, C.ptr(csc_ptr), C.ptr(csc_row), C.ptr(csc_pair), C.ptr(phi), H, HP,
                           C.ptr(W2t), Ci, C.ptr(order_in), Ni, B, C.ptr(dxp), C.ptr(xp), C.ptr(dW2), st),
             "qc_contract (backward)")

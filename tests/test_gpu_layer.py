@@ -116,6 +116,8 @@ class _StubMesh:
     (2, 1000, 4, 8, 8, [8, 8], 0.08, True, None),      # fast path, partial channel chunk (Ci < 8)
     (2, 700, 20, 24, 32, [8, 8], 0.1, False, None),    # fast path, 3 channel chunks, last one partial
     (3, 900, 32, 16, 64, [4, 4], 0.2, True, None),     # fast path, two batch blocks (B = 64), H = 4
+    (2, 600, 8, 8, 8, [8, 8], 0.25, False, None),      # fast path, ~118 pairs/point: several staged chunks
+    (2, 500, 16, 16, 32, [4, 4], 0.3, True, 200),      # fast path, ~140 pairs/point, cross-level, B = 32
 ])
 def test_layer_matches_oracle(cuda_lib, d, n, ci, co, B, fs, r, bias, n_out):
     import pytorch_quadconv_b200 as q
