@@ -178,6 +178,11 @@ int qc_gather_fwd(const float* x, const int* index /*[Nout]*/, int BC, int Nin, 
 int qc_gather_bwd(const float* grad_out, const int* grp_ptr, const int* grp_mem, int BC, int Nfine,
                   int Ncoarse, float* grad_x, void* stream);
 
+/* Known-answer self test of the tcgen05 building blocks (TMEM alloc, tcgen05.st/ld, kind::tf32 MMA with
+ * A in TMEM and B through a K-major shared-memory descriptor, 3xTF32 split):
+ * D[128][32] = A[128][64] * B[32][64]^T.  Used by tests only. */
+int qc_tc_selftest(const float* A, const float* B, float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,98 @@
+// tc_selftest.cu -- known-answer test of the tcgen05 building blocks used by the fused kernels:
+// D[128 x 32] = A[128 x 64] * B^T (B given as [32 x 64], K-major) in 3xTF32 (hi/lo split), with A
+// written to TMEM by the threads (tcgen05.st), B staged in shared memory in the canonical K-major
+// layout, the accumulator read back with tcgen05.ld.  tests/test_gpu_tc.py compares against fp32.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ D)
+{
+    __shared__ __align__(128) float Bhi[32 * 64];
+    __shared__ __align__(128) float Blo[32 * 64];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_fence_init();
+    }
+    // stage B (hi / lo) in the canonical K-major layout
+    for (int idx = tid; idx < 32 * 64; idx += 128) {
+        const int n = idx / 64, k = idx % 64;
+        const float v = Bm[idx];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const uint32_t off = tc::kmajor_off_bytes(n, k, 64) / 4;
+        Bhi[off] = hi;
+        Blo[off] = v - hi;
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t a_hi = tmem + 0, a_lo = tmem + 64, d_acc = tmem + 128;
+
+    // A row of this thread -> TMEM (hi in columns [0,64), lo in [64,128))
+    const float* arow = A + (size_t)tid * 64;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float v = arow[c * 16 + j];
+            const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            hi[j] = __float_as_uint(h);
+            lo[j] = __float_as_uint(v - h);
+        }
+        tc::tmem_st16(lane_base + a_hi + c * 16, hi);
+        tc::tmem_st16(lane_base + a_lo + c * 16, lo);
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc = tc::make_idesc_tf32(128, 32);
+        const uint32_t bhi = tc::smem_u32(Bhi), blo = tc::smem_u32(Blo);
+        const uint32_t sbo = (64 / 4) * 128;
+        bool acc = false;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // K = 64 in steps of 8 (two core matrices)
+            const uint64_t dhi = tc::make_smem_desc(bhi + ks * 256, 128, sbo);
+            const uint64_t dlo = tc::make_smem_desc(blo + ks * 256, 128, sbo);
+            tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dhi, idesc, acc);
+            acc = true;
+            tc::mma_tf32_ts(d_acc, a_lo + ks * 8, dhi, idesc, true);
+            tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dlo, idesc, true);
+        }
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    uint32_t r0[16], r1[16];
+    tc::tmem_ld16(lane_base + d_acc, r0);
+    tc::tmem_ld16(lane_base + d_acc + 16, r1);
+    tc::wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        D[(size_t)tid * 32 + j] = __uint_as_float(r0[j]);
+        D[(size_t)tid * 32 + 16 + j] = __uint_as_float(r1[j]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+
+extern "C" int qc_tc_selftest(const float* A, const float* B, float* D, void* stream)
+{
+    k_tc_selftest<<<1, 128, 0, (cudaStream_t)stream>>>(A, B, D);
+    QC_CHECK_LAUNCH();
+    return 0;
+}

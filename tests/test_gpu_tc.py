@@ -1,0 +1,25 @@
+"""GPU: known-answer test of the tcgen05 (tensor-core) building blocks: TMEM-resident A operand,
+K-major shared-memory B descriptor, 3xTF32 error-compensated product, TMEM read-back."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_tcgen05_3xtf32_gemm(cuda_lib):
+    from pytorch_quadconv_b200 import _cabi as C
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(128, 64, generator=g).cuda()
+    B = torch.randn(32, 64, generator=g).cuda()
+    D = torch.full((128, 32), float("nan"), device="cuda")
+    C.check(cuda_lib.qc_tc_selftest(C.ptr(A), C.ptr(B), C.ptr(D), C.stream()), "qc_tc_selftest")
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().T
+    err = float((D.double() - ref).norm() / ref.norm())
+    assert err < 2e-6, err          # plain TF32 would give ~5e-4
+    # structured operands catch layout mix-ups that random data can hide
+    A2 = torch.zeros(128, 64, device="cuda"); A2[5, 7] = 1.0; A2[100, 63] = 2.0
+    B2 = torch.arange(32 * 64, dtype=torch.float32, device="cuda").reshape(32, 64)
+    C.check(cuda_lib.qc_tc_selftest(C.ptr(A2), C.ptr(B2), C.ptr(D), C.stream()), "qc_tc_selftest")
+    ref2 = A2.double() @ B2.double().T
+    assert float((D.double() - ref2).abs().max()) < 1e-3
