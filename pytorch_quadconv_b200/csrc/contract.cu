@@ -428,7 +428,9 @@ int qc_contract(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, const int
     a.KSPLIT = qc_ceil_div(NKC, WK);
     if (a.KSPLIT > 65535 || nblk > 65535) return QC_EUNSUP;
     {
-        const int rc = qc_contract_fast(a, HP, B, dw, st);
+        int rc = qc_contract_tc(a, HP, B, dw, st);       // tcgen05 dense stage (contract_tc.cu)
+        if (rc != 0) return rc == 1 ? 0 : rc;
+        rc = qc_contract_fast(a, HP, B, dw, st);         // FP32-pipe fast path (contract_fast.cu)
         if (rc != 0) return rc == 1 ? 0 : rc;
     }
     const int WP = 8 / WK;

@@ -31,6 +31,7 @@ struct DphiArgs {
 
 // Fast paths (contract_fast.cu).  Return 1 when the shape is handled, 0 when the caller must
 // fall back to the generic kernel, <0 / cudaError on failure.
+int qc_contract_tc(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t st);
 int qc_contract_fast(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t st);
 int qc_dphi_fast(const DphiArgs& a, int HP, int B, cudaStream_t st);
 bool qc_dphi_fast_ok(int Nsrc, int Cx, int Cg, int HP, int B);

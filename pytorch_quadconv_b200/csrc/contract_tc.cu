@@ -1,0 +1,363 @@
+// contract_tc.cu -- tensor-core (tcgen05) version of the fused gather-contract kernel.
+//
+// Stage B (segmented gather-accumulate over the pair list) is irregular, per-pair-unique work and
+// stays on the FP32 pipe exactly as in contract_fast.cu.  Stage C -- the last Linear of the
+// reference's filter MLP (quadconv.py:143) folded into the contraction,
+//     Y[row][j] = sum_k T[row][k] * W2[k][j],      row = (point, batch lane), k = (channel, h)
+// -- is a dense GEMM with a shared weight, and runs on the 5th-generation tensor cores:
+//   * each thread owns one row; after a channel chunk (K = 64) it splits its 64 fp32 partial sums
+//     into tf32 hi + lo parts and writes them straight from registers into TENSOR MEMORY with
+//     tcgen05.st, where they are the A operand (lane = row, column = k) -- no shared-memory A tile;
+//   * the repacked weight slices (hi and lo) sit in shared memory for the whole kernel in the
+//     canonical K-major no-swizzle layout and are the B operand through matrix descriptors;
+//   * one elected thread per 128-row block issues 3 x 8 tcgen05.mma.kind::tf32 (M=128, N=32, K=8):
+//     A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (3xTF32 error compensation: fp32-grade accuracy, needed for
+//     the 1e-5 bound); the accumulator D lives in TMEM across all channel chunks of a tile;
+//   * tcgen05.commit -> mbarrier tells the row block when A may be overwritten / D may be read;
+//     the epilogue reads D with tcgen05.ld and stores the packed output rows with 128-bit stores.
+// The MMAs are asynchronous: the FP32 pipe is already gathering the next chunk while they run.
+#include <cstdlib>
+#include "contract_args.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TS = 68;   // row stride of the T tile in shared memory (DW mini-GEMM)
+constexpr int ZS = 36;   // row stride of the Z tile
+constexpr int PCH = 64;  // pairs staged per chunk
+constexpr int BSLICE = 32 * 64;  // floats per weight slice (N = 32 rows x K = 64), hi or lo
+
+template <int HP, int LB, bool DW>
+__global__ void __launch_bounds__(256, 1)
+k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
+{
+    constexpr int CXC = 64 / HP, Bp = 1 << LB, PPW = 32 >> LB;
+    constexpr int NG = CXC / 4, HQ = HP / 4;
+    constexpr int D = 8;
+    constexpr int PHS = PCH * HP + 4;
+    extern __shared__ __align__(128) float smem[];
+    float* Bs = smem;                                              // [nkc][2][BSLICE] (hi, lo), canonical K-major
+    float* phi_s = Bs + (size_t)nkc * 2 * BSLICE;                  // [8*PPW][PHS]
+    int* idx_s = reinterpret_cast<int*>(phi_s + 8 * PPW * PHS);    // [8*PPW][PCH]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + 8 * PPW * PCH);  // [2] mbarriers + tmem base
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2);
+    float* T_s = reinterpret_cast<float*>(bars + 4);               // DW: [256][TS]
+    float* Z_s = T_s + 256 * TS;                                   // DW: [256][ZS]
+    float* dW_s = Z_s + 256 * ZS;                                  // DW && dw_in_smem: [nkc*64][32]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rb = warp >> 2;                                      // 128-row block of this warp
+    const int s = lane >> LB, b = lane & (Bp - 1);
+    const int blk = blockIdx.y;
+    const unsigned xrow = (unsigned)qc_cp4(a.Cx) * Bp;
+    const size_t yrow = (size_t)qc_cp4(a.Cy) * Bp;
+    const float* Xb = a.X + (size_t)blk * a.Nsrc * xrow + b * 4;
+    constexpr int ppt = 8 * PPW;
+    const int ntiles = (a.Ndst + ppt - 1) / ppt;
+
+    // ---- one-time setup: TMEM, mbarriers, weight slices -------------------------------------
+    if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
+    if (tid == 32) {
+        tc::mbar_init(&bars[0], 1);
+        tc::mbar_init(&bars[1], 1);
+        tc::mbar_fence_init();
+    }
+    for (int idx = tid; idx < nkc * BSLICE; idx += 256) {
+        const int kc = idx / BSLICE, r = idx % BSLICE;
+        const int n = r >> 6, k = r & 63;                          // n = output channel j, k = (i, h)
+        const int i = k / HP, h = k % HP;
+        const int cx = kc * CXC + i;
+        float v = 0.f;
+        if (cx < a.Cx && h < a.H && n < a.Cy) v = __ldg(a.W2 + ((size_t)cx * a.H + h) * a.CyP + n);
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const uint32_t off = tc::kmajor_off_bytes(n, k, 64) / 4;
+        Bs[(size_t)(kc * 2 + 0) * BSLICE + off] = hi;
+        Bs[(size_t)(kc * 2 + 1) * BSLICE + off] = v - hi;
+    }
+    if (DW && dw_in_smem)
+        for (int i = tid; i < nkc * 64 * 32; i += 256) dW_s[i] = 0.f;
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_base_s;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t a_hi = tmem + rb * 160, a_lo = a_hi + 64, d_acc = a_hi + 128;
+    const uint32_t idesc = tc::make_idesc_tf32(128, 32);
+    const uint32_t bs_addr = tc::smem_u32(Bs);
+    uint32_t g = 0;  // MMA groups committed so far on this row block (same value in all its threads)
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int t = tile * ppt + warp * PPW + s;
+        const bool pvalid = t < a.Ndst;
+        const int dstp = pvalid ? (a.order ? a.order[t] : t) : -1;
+        int beg = 0, len = 0;
+        if (pvalid) {
+            beg = a.seg_ptr[dstp];
+            len = a.seg_ptr[dstp + 1] - beg;
+        }
+        const int maxlen = PPW == 1 ? len : qc_warp_max_i(len);
+        const int* sidx = a.src_idx + beg;
+        const int* pidx = a.phi_idx ? a.phi_idx + beg : nullptr;
+
+        if (DW) {
+            __syncthreads();  // the previous tile's last mini-GEMM is done with Z_s
+            float* zr = Z_s + (warp * 32 + lane) * ZS;
+            const float* zg = a.Z + ((size_t)blk * a.Ndst + (pvalid ? dstp : 0)) * yrow + b * 4;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pvalid && 4 * q < a.Cy) v = __ldg(reinterpret_cast<const float4*>(zg + (size_t)q * Bp * 4));
+                *reinterpret_cast<float4*>(zr + 4 * q) = v;
+            }
+        }
+
+        for (int kc = 0; kc < nkc; ++kc) {
+            const int cx0 = kc * CXC;
+            const int nval = min(CXC, a.Cx - cx0);
+            const int ngv = (nval + 3) >> 2;
+            if (DW) __syncthreads();  // T_s of the previous chunk is no longer read
+
+            // ---- stage B: segmented gather-accumulate on the FP32 pipe ---------------------------
+            float T[CXC][HP];
+#pragma unroll
+            for (int i = 0; i < CXC; ++i)
+#pragma unroll
+                for (int h = 0; h < HP; ++h) T[i][h] = 0.f;
+
+            const float* Xc = Xb + (size_t)(cx0 >> 2) * (Bp * 4);
+            float* my_phi = phi_s + (warp * PPW + s) * PHS;
+            int* my_idx = idx_s + (warp * PPW + s) * PCH;
+            float4 buf[D][NG];
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+#pragma unroll
+                for (int q = 0; q < NG; ++q) buf[d][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto issue = [&](float4 (&xb)[NG], int e) {
+                const unsigned u = (unsigned)my_idx[e];
+                const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)(u * xrow));
+#pragma unroll
+                for (int q = 0; q < NG; ++q)
+                    if (q < ngv) xb[q] = __ldg(xr + q * Bp);
+            };
+            auto consume = [&](const float4 (&xb)[NG], int e) {
+                float ph[HP];
+                const float4* pr = reinterpret_cast<const float4*>(my_phi + e * HP);
+#pragma unroll
+                for (int q = 0; q < HQ; ++q) {
+                    const float4 v = pr[q];
+                    ph[4 * q] = v.x, ph[4 * q + 1] = v.y, ph[4 * q + 2] = v.z, ph[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int q = 0; q < NG; ++q) {
+                    const float f[4] = {xb[q].x, xb[q].y, xb[q].z, xb[q].w};
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2)
+#pragma unroll
+                        for (int h = 0; h < HP; ++h) T[4 * q + e2][h] = fmaf(f[e2], ph[h], T[4 * q + e2][h]);
+                }
+            };
+            for (int c0 = 0; c0 < maxlen; c0 += PCH) {
+                const int clen = min(PCH, len - c0);
+                const int cmax = min(PCH, maxlen - c0);
+                __syncwarp();
+                for (int e = b; e < clen; e += Bp) {
+                    const int p = c0 + e;
+                    my_idx[e] = sidx[p];
+                    const int pp = pidx ? pidx[p] : beg + p;
+                    const float4* php = reinterpret_cast<const float4*>(a.phi + (size_t)pp * HP);
+#pragma unroll
+                    for (int q = 0; q < HQ; ++q) reinterpret_cast<float4*>(my_phi + e * HP)[q] = __ldg(php + q);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                    if (d < clen) issue(buf[d], d);
+                for (int it = 0; it < cmax; it += D) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        if (it + d < clen) {
+                            consume(buf[d], it + d);
+                            if (it + d + D < clen) issue(buf[d], it + d + D);
+                        }
+                    }
+                }
+            }
+
+            // ---- stage C on the tensor cores: T (hi/lo) -> TMEM, 3xTF32 MMAs into D ---------------
+            if (g > 0) {
+                tc::mbar_wait(&bars[rb], (g - 1) & 1);   // previous group has finished reading A
+                tc::fence_after_sync();
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float v = T[(c * 16 + j) / HP][(c * 16 + j) % HP];
+                    const float hv = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                    hi[j] = __float_as_uint(hv);
+                    lo[j] = __float_as_uint(v - hv);
+                }
+                tc::tmem_st16(lane_base + a_hi + c * 16, hi);
+                tc::tmem_st16(lane_base + a_lo + c * 16, lo);
+            }
+            tc::wait_st();
+            tc::fence_before_sync();
+            tc::named_bar_sync(1 + rb, 128);
+            if ((warp & 3) == 0 && lane == 0) {
+                tc::fence_after_sync();
+                const uint32_t bhi = bs_addr + (uint32_t)(kc * 2) * BSLICE * 4, blo = bhi + BSLICE * 4;
+                constexpr uint32_t SBO = (64 / 4) * 128;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint64_t dhi = tc::make_smem_desc(bhi + ks * 256, 128, SBO);
+                    const uint64_t dlo = tc::make_smem_desc(blo + ks * 256, 128, SBO);
+                    tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dhi, idesc, !(kc == 0 && ks == 0));
+                    tc::mma_tf32_ts(d_acc, a_lo + ks * 8, dhi, idesc, true);
+                    tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dlo, idesc, true);
+                }
+                tc::mma_commit(&bars[rb]);
+            }
+            ++g;
+
+            if (DW) {
+                // dW2[(c,h)][j] += sum_rows T[row][(c,h)] * Z[row][j] for this chunk (FP32 pipe)
+                float* tr = T_s + (warp * 32 + lane) * TS;
+#pragma unroll
+                for (int i = 0; i < CXC; ++i)
+#pragma unroll
+                    for (int hq = 0; hq < HP / 4; ++hq)
+                        *reinterpret_cast<float4*>(tr + i * HP + 4 * hq) =
+                            make_float4(T[i][4 * hq], T[i][4 * hq + 1], T[i][4 * hq + 2], T[i][4 * hq + 3]);
+                __syncthreads();
+                const int half = tid >> 7, tq = tid & 127;
+                const int kq = tq >> 3, jq = tq & 7;
+                float c[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) c[r][cc] = 0.f;
+                const float* tp = T_s + (half * 128) * TS + kq * 4;
+                const float* zp = Z_s + (half * 128) * ZS + jq * 4;
+#pragma unroll 4
+                for (int row = 0; row < 128; ++row) {
+                    const float4 tv = *reinterpret_cast<const float4*>(tp + row * TS);
+                    const float4 zv = *reinterpret_cast<const float4*>(zp + row * ZS);
+                    const float tva[4] = {tv.x, tv.y, tv.z, tv.w};
+                    const float zva[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) c[r][cc] = fmaf(tva[r], zva[cc], c[r][cc]);
+                }
+                if (dw_in_smem) {
+                    float* dst = dW_s + ((size_t)kc * 64 + kq * 4) * 32 + jq * 4;
+                    if (half == 0) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) dst[r * 32 + cc] += c[r][cc];
+                    }
+                    __syncthreads();
+                    if (half == 1) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) dst[r * 32 + cc] += c[r][cc];
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int k = kq * 4 + r, i = k / HP, h = k % HP;
+                        if (i < nval && h < a.H) {
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                const int j = jq * 4 + cc;
+                                if (j < a.Cy) atomicAdd(a.dW2 + ((size_t)(cx0 + i) * a.H + h) * a.CyP + j, c[r][cc]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- epilogue: D (TMEM) -> registers -> packed output rows ------------------------------
+        tc::mbar_wait(&bars[rb], (g - 1) & 1);
+        tc::fence_after_sync();
+        uint32_t r0[16], r1[16];
+        tc::tmem_ld16(lane_base + d_acc, r0);
+        tc::tmem_ld16(lane_base + d_acc + 16, r1);
+        tc::wait_ld();
+        if (pvalid) {
+            float* y = a.Y + ((size_t)blk * a.Ndst + dstp) * yrow + b * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (4 * q < a.Cy)
+                    *reinterpret_cast<float4*>(y + (size_t)q * Bp * 4) =
+                        make_float4(__uint_as_float(r0[4 * q]), __uint_as_float(r0[4 * q + 1]),
+                                    __uint_as_float(r0[4 * q + 2]), __uint_as_float(r0[4 * q + 3]));
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (16 + 4 * q < a.Cy)
+                    *reinterpret_cast<float4*>(y + (size_t)(4 + q) * Bp * 4) =
+                        make_float4(__uint_as_float(r1[4 * q]), __uint_as_float(r1[4 * q + 1]),
+                                    __uint_as_float(r1[4 * q + 2]), __uint_as_float(r1[4 * q + 3]));
+        }
+    }
+
+    if (DW && dw_in_smem) {
+        __syncthreads();
+        for (int idx = tid; idx < nkc * 64 * 32; idx += 256) {
+            const int kc = idx >> 11, k = (idx >> 5) & 63, j = idx & 31;
+            const int i = k / HP, h = k % HP;
+            const int cx = kc * CXC + i;
+            if (cx < a.Cx && h < a.H && j < a.Cy) atomicAdd(a.dW2 + ((size_t)cx * a.H + h) * a.CyP + j, dW_s[idx]);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+template <int HP, int LB, bool DW>
+int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
+{
+    constexpr int CXC = 64 / HP, PPW = 32 >> LB;
+    const int nkc = qc_ceil_div(a.Cx, CXC);
+    const int nblk = qc_nblk(B);
+    size_t smem = ((size_t)nkc * 2 * BSLICE + 8 * PPW * (PCH * HP + 4) + 8 * PPW * PCH) * 4 + 32;
+    int dw_in_smem = 0;
+    if (DW) {
+        smem += (256 * TS + 256 * ZS) * 4;
+        if (smem + (size_t)nkc * 64 * 32 * 4 <= 227 * 1024) {
+            dw_in_smem = 1;
+            smem += (size_t)nkc * 64 * 32 * 4;
+        }
+    }
+    if (smem > 227 * 1024) return 0;   // weight slices do not fit: use the FP32-pipe kernel
+    QC_CUDA(cudaFuncSetAttribute(k_contract_tc<HP, LB, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = qc_ceil_div(a.Ndst, 8 * PPW);
+    int gx = qc_num_sms();
+    gx = (gx + nblk - 1) / nblk;
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, nblk);
+    k_contract_tc<HP, LB, DW><<<grid, 256, smem, st>>>(a, nkc, dw_in_smem);
+    QC_CHECK_LAUNCH();
+    return 1;
+}
+
+}  // namespace
+
+int qc_contract_tc(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t st)
+{
+    const int Bp = qc_bp(B);
+    if (a.Cy > 32 || !(HP == 4 || HP == 8) || !(Bp == 8 || Bp == 32)) return 0;
+    if ((size_t)a.Nsrc * qc_cp4(a.Cx) * Bp >= ((size_t)1 << 32)) return 0;
+    if (nullptr != getenv("QC_NO_FAST") || nullptr != getenv("QC_NO_TC")) return 0;
+#define QC_T(HPV, LBV) (dw ? launch_tc<HPV, LBV, true>(a, B, st) : launch_tc<HPV, LBV, false>(a, B, st))
+    if (HP == 4) return Bp == 8 ? QC_T(4, 3) : QC_T(4, 5);
+    return Bp == 8 ? QC_T(8, 3) : QC_T(8, 5);
+#undef QC_T
+}
