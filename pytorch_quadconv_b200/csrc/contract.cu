@@ -479,7 +479,9 @@ int qc_dphi(const float* Xp, int Nsrc, int Cx, const float* Gp, int Cg, const in
     if (nksplit > 65535 || nblk > 65535) return QC_EUNSUP;
     const int LB = ilog2(Bp);
     {
-        const int rc = qc_dphi_fast(a, HP, B, st);
+        int rc = qc_dphi_tc(a, HP, B, st);
+        if (rc != 0) return rc == 1 ? 0 : rc;
+        rc = qc_dphi_fast(a, HP, B, st);
         if (rc != 0) return rc == 1 ? 0 : rc;
     }
     QC_CUDA(cudaMemsetAsync(dphi, 0, (size_t)P * HP * 4, st));   // the generic kernel accumulates with atomics

@@ -33,5 +33,6 @@ struct DphiArgs {
 // fall back to the generic kernel, <0 / cudaError on failure.
 int qc_contract_tc(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t st);
 int qc_contract_fast(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t st);
+int qc_dphi_tc(const DphiArgs& a, int HP, int B, cudaStream_t st);
 int qc_dphi_fast(const DphiArgs& a, int HP, int B, cudaStream_t st);
 bool qc_dphi_fast_ok(int Nsrc, int Cx, int Cg, int HP, int B);

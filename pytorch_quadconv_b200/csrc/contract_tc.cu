@@ -348,6 +348,270 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
     return 1;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// d(phi) kernel with the dense stage  dT[row][(c,h)] = sum_j G[row][j] * W3[j][c][h]  on tcgen05:
+// the thread's grad_out row (hi/lo) is the A operand in TMEM (written once per tile), the W3 slices
+// of all channel chunks are the B operand in shared memory, D (64 columns) is double buffered in
+// TMEM so the MMAs of chunk kc+1 / kc+2 run while the FP32 pipe walks the pair list of chunk kc.
+constexpr int WSLICE = 64 * 32;  // floats per W3 slice: N = 64 rows (c,h) x K = 32 (j), hi or lo
+
+template <int HP, int LB>
+__global__ void __launch_bounds__(256, 1)
+k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
+{
+    constexpr int CXC = 64 / HP, Bp = 1 << LB, PPW = 32 >> LB;
+    constexpr int NG = CXC / 4;
+    constexpr int D = 8;
+    constexpr int LH = HP == 8 ? 3 : 2;
+    constexpr int NH = LB < LH ? LB : LH;
+    constexpr int NF = HP >> NH;
+    extern __shared__ __align__(128) float smem[];
+    float* Ws = smem;                                              // [nkc][2][WSLICE]
+    int* idx_s = reinterpret_cast<int*>(Ws + (size_t)nkc * 2 * WSLICE);   // [8*PPW][PCH]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + 8 * PPW * PCH);  // [2 row blocks][2 buffers]
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rb = warp >> 2;
+    const int s = lane >> LB, b = lane & (Bp - 1);
+    const int blk = blockIdx.y;
+    const unsigned xrow = (unsigned)qc_cp4(a.Cx) * Bp;
+    const size_t grow = (size_t)qc_cp4(a.Cg) * Bp;
+    const float* Xb = a.X + (size_t)blk * a.Nsrc * xrow + b * 4;
+    constexpr int ppt = 8 * PPW;
+    const int ntiles = (a.Ndst + ppt - 1) / ppt;
+    const bool writer = (lane & ((1 << (LB - NH)) - 1)) == 0;
+
+    if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
+    if (tid == 32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
+        tc::mbar_fence_init();
+    }
+    for (int idx = tid; idx < nkc * WSLICE; idx += 256) {
+        const int kc = idx / WSLICE, r = idx % WSLICE;
+        const int n = r >> 5, k = r & 31;                          // n = (i,h) of the chunk, k = j
+        const int i = n / HP, h = n % HP;
+        const int cx = kc * CXC + i;
+        float v = 0.f;
+        if (cx < a.Cx && k < a.Cg) v = __ldg(a.W3 + ((size_t)k * a.Cx + cx) * HP + h);
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const uint32_t off = tc::kmajor_off_bytes(n, k, 32) / 4;
+        Ws[(size_t)(kc * 2 + 0) * WSLICE + off] = hi;
+        Ws[(size_t)(kc * 2 + 1) * WSLICE + off] = v - hi;
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_base_s;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    // TMEM columns per row block: A_hi [0,32) A_lo [32,64) D0 [64,128) D1 [128,192)
+    const uint32_t a_hi = tmem + rb * 192, a_lo = a_hi + 32, d0 = a_hi + 64;
+    const uint32_t idesc = tc::make_idesc_tf32(128, 64);
+    const uint32_t ws_addr = tc::smem_u32(Ws);
+    uint64_t* mybars = bars + rb * 2;
+    uint32_t cnt[2] = {0u, 0u};   // completed waits per D buffer (phase bookkeeping)
+    const bool issuer = (warp & 3) == 0 && lane == 0;
+
+    auto issue_mma = [&](int kc) {
+        // dT chunk kc -> D[kc & 1]
+        const uint32_t whi = ws_addr + (uint32_t)(kc * 2) * WSLICE * 4, wlo = whi + WSLICE * 4;
+        constexpr uint32_t SBO = (32 / 4) * 128;
+        const uint32_t d = d0 + (kc & 1) * 64;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t dhi = tc::make_smem_desc(whi + ks * 256, 128, SBO);
+            const uint64_t dlo = tc::make_smem_desc(wlo + ks * 256, 128, SBO);
+            tc::mma_tf32_ts(d, a_hi + ks * 8, dhi, idesc, ks != 0);
+            tc::mma_tf32_ts(d, a_lo + ks * 8, dhi, idesc, true);
+            tc::mma_tf32_ts(d, a_hi + ks * 8, dlo, idesc, true);
+        }
+        tc::mma_commit(&mybars[kc & 1]);
+    };
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int t = tile * ppt + warp * PPW + s;
+        const bool pvalid = t < a.Ndst;
+        const int dstp = pvalid ? (a.order ? a.order[t] : t) : -1;
+        int beg = 0, len = 0;
+        if (pvalid) {
+            beg = a.seg_ptr[dstp];
+            len = a.seg_ptr[dstp + 1] - beg;
+        }
+        const int maxlen = qc_warp_max_i(len);
+        const int* sidx = a.src_idx + beg;
+
+        // A operand: this thread's grad_out row, hi / lo (all MMAs of the previous tile have been
+        // waited for, so A and both D buffers are free)
+        {
+            const float* gp = a.G + ((size_t)blk * a.Ndst + (pvalid ? dstp : 0)) * grow + b * 4;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (pvalid && 16 * c + 4 * q < a.Cg)
+                        v = __ldg(reinterpret_cast<const float4*>(gp + (size_t)(4 * c + q) * Bp * 4));
+                    const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float hv = __uint_as_float(__float_as_uint(f[e]) & 0xffffe000u);
+                        hi[4 * q + e] = __float_as_uint(hv);
+                        lo[4 * q + e] = __float_as_uint(f[e] - hv);
+                    }
+                }
+                tc::tmem_st16(lane_base + a_hi + c * 16, hi);
+                tc::tmem_st16(lane_base + a_lo + c * 16, lo);
+            }
+            tc::wait_st();
+            tc::fence_before_sync();
+            tc::named_bar_sync(1 + rb, 128);
+            if (issuer) {
+                tc::fence_after_sync();
+                issue_mma(0);
+                if (nkc > 1) issue_mma(1);
+            }
+        }
+
+        for (int kc = 0; kc < nkc; ++kc) {
+            const int cx0 = kc * CXC;
+            const int nval = min(CXC, a.Cx - cx0);
+            const int ngv = (nval + 3) >> 2;
+            const int q2 = kc & 1;
+            // dT of this chunk: TMEM -> registers
+            tc::mbar_wait(&mybars[q2], cnt[q2] & 1);
+            ++cnt[q2];
+            tc::fence_after_sync();
+            float dT[CXC][HP];
+            {
+                const uint32_t d = lane_base + d0 + q2 * 64;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(d + c * 16, r);
+                    tc::wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dT[(c * 16 + j) / HP][(c * 16 + j) % HP] = __uint_as_float(r[j]);
+                }
+            }
+            if (kc + 2 < nkc) {
+                // D[q2] is free again once every thread of the row block has read it
+                tc::fence_before_sync();
+                tc::named_bar_sync(1 + rb, 128);
+                if (issuer) {
+                    tc::fence_after_sync();
+                    issue_mma(kc + 2);
+                }
+            }
+
+            const float* Xc = Xb + (size_t)(cx0 >> 2) * (Bp * 4);
+            int* my_idx = idx_s + (warp * PPW + s) * PCH;
+            float4 xbuf[D][NG];
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+#pragma unroll
+                for (int q = 0; q < NG; ++q) xbuf[d][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto issue = [&](float4 (&xb)[NG], int e) {
+                const unsigned u = (unsigned)my_idx[e];
+                const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)(u * xrow));
+#pragma unroll
+                for (int q = 0; q < NG; ++q)
+                    if (q < ngv) xb[q] = __ldg(xr + q * Bp);
+            };
+            for (int c0 = 0; c0 < maxlen; c0 += PCH) {
+                const int clen = min(PCH, len - c0);
+                const int cmax = min(PCH, maxlen - c0);
+                __syncwarp();
+                for (int e = b; e < clen; e += Bp) my_idx[e] = sidx[c0 + e];
+                __syncwarp();
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                    if (d < clen) issue(xbuf[d], d);
+                for (int it = 0; it < cmax; it += D) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        if (it + d < cmax) {   // warp-uniform: the shuffles below need every lane
+                            const bool act = it + d < clen;
+                            float part[HP];
+#pragma unroll
+                            for (int h = 0; h < HP; ++h) part[h] = 0.f;
+#pragma unroll
+                            for (int q = 0; q < NG; ++q) {
+                                const float f[4] = {xbuf[d][q].x, xbuf[d][q].y, xbuf[d][q].z, xbuf[d][q].w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                                    for (int h = 0; h < HP; ++h) part[h] = fmaf(f[e], dT[4 * q + e][h], part[h]);
+                            }
+                            if (!act) {
+#pragma unroll
+                                for (int h = 0; h < HP; ++h) part[h] = 0.f;
+                            }
+                            // reduce over the batch lanes of the sub-group (transposed butterfly)
+                            int hsel = 0;
+#pragma unroll
+                            for (int st = 0; st < LB; ++st) {
+                                const int mask = 1 << (LB - 1 - st);
+                                if (st < NH) {
+                                    const int half = HP >> (st + 1);
+                                    const bool upper = (lane & mask) != 0;
+#pragma unroll
+                                    for (int k = 0; k < half; ++k) {
+                                        const float send = upper ? part[k] : part[k + half];
+                                        const float keep = upper ? part[k + half] : part[k];
+                                        part[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+                                    }
+                                    hsel = (hsel << 1) | (upper ? 1 : 0);
+                                } else {
+                                    part[0] += __shfl_xor_sync(0xffffffffu, part[0], mask);
+                                }
+                            }
+                            if (act && writer) {
+                                float* dst = a.dphi + (size_t)(blk * nkc + kc) * slice_stride +
+                                             (size_t)(beg + c0 + it + d) * HP + hsel * NF;
+#pragma unroll
+                                for (int k = 0; k < NF; ++k) dst[k] = part[k];
+                            }
+                            if (it + d + D < clen) issue(xbuf[d], it + d + D);
+                        }
+                    }
+                }
+            }
+        }
+        // every MMA group of this tile has been waited for; make sure all threads are past their
+        // last TMEM read before the next tile overwrites A / D
+        tc::fence_before_sync();
+        tc::named_bar_sync(1 + rb, 128);
+        tc::fence_after_sync();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+template <int HP, int LB>
+int launch_dtc(const DphiArgs& a, int B, cudaStream_t st)
+{
+    constexpr int CXC = 64 / HP, PPW = 32 >> LB;
+    const int nkc = qc_ceil_div(a.Cx, CXC);
+    const int nblk = qc_nblk(B);
+    const size_t smem = ((size_t)nkc * 2 * WSLICE + 8 * PPW * PCH) * 4 + 64;
+    if (smem > 227 * 1024) return 0;
+    QC_CUDA(cudaFuncSetAttribute(k_dphi_tc<HP, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = qc_ceil_div(a.Ndst, 8 * PPW);
+    int gx = qc_num_sms();
+    gx = (gx + nblk - 1) / nblk;
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, nblk);
+    k_dphi_tc<HP, LB><<<grid, 256, smem, st>>>(a, nkc, (size_t)a.P * HP);
+    QC_CHECK_LAUNCH();
+    return 1;
+}
+
 }  // namespace
 
 int qc_contract_tc(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t st)
@@ -360,4 +624,14 @@ int qc_contract_tc(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t s
     if (HP == 4) return Bp == 8 ? QC_T(4, 3) : QC_T(4, 5);
     return Bp == 8 ? QC_T(8, 3) : QC_T(8, 5);
 #undef QC_T
+}
+
+// Same eligibility as the FP32-pipe fast path (so qc_dphi_num_slices stays valid for both).
+int qc_dphi_tc(const DphiArgs& a, int HP, int B, cudaStream_t st)
+{
+    if (!qc_dphi_fast_ok(a.Nsrc, a.Cx, a.Cg, HP, B)) return 0;
+    if (nullptr != getenv("QC_NO_TC")) return 0;
+    const int Bp = qc_bp(B);
+    if (HP == 4) return Bp == 8 ? launch_dtc<4, 3>(a, B, st) : launch_dtc<4, 5>(a, B, st);
+    return Bp == 8 ? launch_dtc<8, 3>(a, B, st) : launch_dtc<8, 5>(a, B, st);
 }
