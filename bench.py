@@ -228,17 +228,19 @@ def time_kernels(w, mesh, layer, x, reps=5):
         for n in names:
             setattr(L, n, orig[n])
     out = {}
+    calls = 0
     for k, evs in acc.items():
         per_step = len(evs) // reps
+        calls += per_step
         ts = [a.elapsed_time(b) for a, b in evs[per_step:]]      # drop the first repetition
         out[k] = sum(ts) / max(reps - 1, 1)
-    return out
+    return out, calls
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -346,7 +348,7 @@ def main():
     # ---- per-kernel table + roofline of the dominant kernel (rank 0) ----------------------------
     roof, cb, table = None, None, None
     if rank == 0:
-        table = time_kernels(w, mesh, layer, x)
+        table, calls_per_step = time_kernels(w, mesh, layer, x)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -366,11 +368,18 @@ def main():
                "qc_dphi.bwd": stageB * ci + dense}.get(dom, 0.0)
         peak = bf16 / 6.0     # fp32 mode on tensor cores = 3xTF32 ~ bf16/6
         ach = alg / (dom_ms * 1e-3) / 1e12
+        traffic = None
+        try:   # dram__bytes_read+write of this kernel from the committed `ncu --set full` capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+            traffic = tr.get(args.workload, {}).get(dom)
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None,
+                "frac": ach / peak, "traffic": traffic,
                 "note": f"fp32-mode tensor peak = bf16/6 of {src}; numerator = factorised-formulation FLOPs of this "
-                        f"launch ({alg / 1e9:.1f} GFLOP) / CUDA-event time {dom_ms:.3f} ms; this round the kernel runs "
-                        f"on the FP32 CUDA-core pipe (FFMA peak ~ 148 SM x 128 lanes x 2 x clock)",
+                        f"launch ({alg / 1e9:.1f} GFLOP) / CUDA-event time {dom_ms:.3f} ms; the dense stage of the kernel "
+                        f"runs on tcgen05 (3xTF32), the per-pair gather-accumulate on the FP32 pipe, which bounds it "
+                        f"(FFMA peak = 148 SM x 128 lanes x 2 x clock ~ 74 TFLOP/s)",
                 "step_direct_formulation_tflops": fl["direct"] * P / (ms * 1e-3) / 1e12,
                 "step_factorised_tflops": fl["factorised"] * P / (ms * 1e-3) / 1e12,
                 "step_hbm_alg_gbs": bytes_per_step(w, P) / (ms * 1e-3) / 1e9,
@@ -384,8 +393,8 @@ def main():
     if rank == 0:
         launches = 0
         if table:
-            # kernels launched per C-ABI call (see csrc/*.cu): contract 1 (+memset), dphi 1, pair 1, pack 1 ...
-            launches = len(table)
+            # every timed C-ABI call launches exactly one of our kernels (csrc/*.cu); memsets are not counted
+            launches = calls_per_step
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
