@@ -33,7 +33,8 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
 {
     constexpr int CXC = 64 / HP, Bp = 1 << LB, PPW = 32 >> LB;
     constexpr int NG = CXC / 4, HQ = HP / 4;
-    constexpr int D = 8;
+    constexpr int D = (DW ? 8 : 32) / NG;       // gathered pairs in flight per warp (async smem ring)
+    constexpr int RING = D * NG * 512;          // bytes per warp: slot = NG groups x 32 lanes x 16 B
     constexpr int PHS = PCH * HP + 4;
     extern __shared__ __align__(128) float smem[];
     float* Bs = smem;                                              // [nkc][2][BSLICE] (hi, lo), canonical K-major
@@ -41,7 +42,8 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     int* idx_s = reinterpret_cast<int*>(phi_s + 8 * PPW * PHS);    // [8*PPW][PCH]
     uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + 8 * PPW * PCH);  // [2] mbarriers + tmem base
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2);
-    float* T_s = reinterpret_cast<float*>(bars + 4);               // DW: [256][TS]
+    float* ring_s = reinterpret_cast<float*>(bars + 4);            // [8 warps][RING bytes]
+    float* T_s = ring_s + 8 * RING / 4;                            // DW: [256][TS]
     float* Z_s = T_s + 256 * TS;                                   // DW: [256][ZS]
     float* dW_s = Z_s + 256 * ZS;                                  // DW && dw_in_smem: [nkc*64][32]
 
@@ -128,19 +130,18 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
             const float* Xc = Xb + (size_t)(cx0 >> 2) * (Bp * 4);
             float* my_phi = phi_s + (warp * PPW + s) * PHS;
             int* my_idx = idx_s + (warp * PPW + s) * PCH;
-            float4 buf[D][NG];
-#pragma unroll
-            for (int d = 0; d < D; ++d)
-#pragma unroll
-                for (int q = 0; q < NG; ++q) buf[d][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            auto issue = [&](float4 (&xb)[NG], int e) {
+            // gathers go global -> shared asynchronously (cp.async, one commit group per pair) into a
+            // per-warp ring; each lane copies and later reads back only its own 16 bytes per group
+            const uint32_t my_ring = tc::smem_u32(ring_s) + warp * RING + lane * 16;
+            const float* my_ring_p = ring_s + (warp * RING + lane * 16) / 4;
+            auto issue = [&](int slot, int e) {
                 const unsigned u = (unsigned)my_idx[e];
                 const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)(u * xrow));
 #pragma unroll
                 for (int q = 0; q < NG; ++q)
-                    if (q < ngv) xb[q] = __ldg(xr + q * Bp);
+                    if (q < ngv) tc::cp_async16(my_ring + (slot * NG + q) * 512, xr + q * Bp);
             };
-            auto consume = [&](const float4 (&xb)[NG], int e) {
+            auto consume = [&](int slot, int e) {
                 float ph[HP];
                 const float4* pr = reinterpret_cast<const float4*>(my_phi + e * HP);
 #pragma unroll
@@ -150,7 +151,9 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                 }
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
-                    const float f[4] = {xb[q].x, xb[q].y, xb[q].z, xb[q].w};
+                    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q < ngv) xv = *reinterpret_cast<const float4*>(my_ring_p + (slot * NG + q) * 128);
+                    const float f[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
                     for (int e2 = 0; e2 < 4; ++e2)
 #pragma unroll
@@ -171,15 +174,19 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                 }
                 __syncwarp();
 #pragma unroll
-                for (int d = 0; d < D; ++d)
-                    if (d < clen) issue(buf[d], d);
+                for (int d = 0; d < D; ++d) {
+                    if (d < clen) issue(d, d);
+                    tc::cp_async_commit();
+                }
                 for (int it = 0; it < cmax; it += D) {
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
+                        tc::cp_async_wait<D - 1>();       // the oldest group (slot d) has landed
                         if (it + d < clen) {
-                            consume(buf[d], it + d);
-                            if (it + d + D < clen) issue(buf[d], it + d + D);
+                            consume(d, it + d);
+                            if (it + d + D < clen) issue(d, it + d + D);
                         }
+                        tc::cp_async_commit();
                     }
                 }
             }
@@ -326,7 +333,9 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
     constexpr int CXC = 64 / HP, PPW = 32 >> LB;
     const int nkc = qc_ceil_div(a.Cx, CXC);
     const int nblk = qc_nblk(B);
-    size_t smem = ((size_t)nkc * 2 * BSLICE + 8 * PPW * (PCH * HP + 4) + 8 * PPW * PCH) * 4 + 32;
+    constexpr int NG = CXC / 4;
+    constexpr int RING = ((DW ? 8 : 32) / NG) * NG * 512;
+    size_t smem = ((size_t)nkc * 2 * BSLICE + 8 * PPW * (PCH * HP + 4) + 8 * PPW * PCH) * 4 + 32 + 8 * RING;
     int dw_in_smem = 0;
     if (DW) {
         smem += (256 * TS + 256 * ZS) * 4;
@@ -362,7 +371,8 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
 {
     constexpr int CXC = 64 / HP, Bp = 1 << LB, PPW = 32 >> LB;
     constexpr int NG = CXC / 4;
-    constexpr int D = 8;
+    constexpr int D = 32 / NG;                  // gathered pairs in flight per warp (async smem ring)
+    constexpr int RING = D * NG * 512;
     constexpr int LH = HP == 8 ? 3 : 2;
     constexpr int NH = LB < LH ? LB : LH;
     constexpr int NF = HP >> NH;
@@ -371,6 +381,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
     int* idx_s = reinterpret_cast<int*>(Ws + (size_t)nkc * 2 * WSLICE);   // [8*PPW][PCH]
     uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + 8 * PPW * PCH);  // [2 row blocks][2 buffers]
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 4);
+    float* ring_s = reinterpret_cast<float*>(bars + 8);                   // [8 warps][RING bytes]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rb = warp >> 2;
@@ -509,17 +520,14 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
 
             const float* Xc = Xb + (size_t)(cx0 >> 2) * (Bp * 4);
             int* my_idx = idx_s + (warp * PPW + s) * PCH;
-            float4 xbuf[D][NG];
-#pragma unroll
-            for (int d = 0; d < D; ++d)
-#pragma unroll
-                for (int q = 0; q < NG; ++q) xbuf[d][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            auto issue = [&](float4 (&xb)[NG], int e) {
+            const uint32_t my_ring = tc::smem_u32(ring_s) + warp * RING + lane * 16;
+            const float* my_ring_p = ring_s + (warp * RING + lane * 16) / 4;
+            auto issue = [&](int slot, int e) {
                 const unsigned u = (unsigned)my_idx[e];
                 const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)(u * xrow));
 #pragma unroll
                 for (int q = 0; q < NG; ++q)
-                    if (q < ngv) xb[q] = __ldg(xr + q * Bp);
+                    if (q < ngv) tc::cp_async16(my_ring + (slot * NG + q) * 512, xr + q * Bp);
             };
             for (int c0 = 0; c0 < maxlen; c0 += PCH) {
                 const int clen = min(PCH, len - c0);
@@ -528,27 +536,30 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                 for (int e = b; e < clen; e += Bp) my_idx[e] = sidx[c0 + e];
                 __syncwarp();
 #pragma unroll
-                for (int d = 0; d < D; ++d)
-                    if (d < clen) issue(xbuf[d], d);
+                for (int d = 0; d < D; ++d) {
+                    if (d < clen) issue(d, d);
+                    tc::cp_async_commit();
+                }
                 for (int it = 0; it < cmax; it += D) {
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
+                        tc::cp_async_wait<D - 1>();
                         if (it + d < cmax) {   // warp-uniform: the shuffles below need every lane
                             const bool act = it + d < clen;
                             float part[HP];
 #pragma unroll
                             for (int h = 0; h < HP; ++h) part[h] = 0.f;
+                            if (act) {
 #pragma unroll
-                            for (int q = 0; q < NG; ++q) {
-                                const float f[4] = {xbuf[d][q].x, xbuf[d][q].y, xbuf[d][q].z, xbuf[d][q].w};
+                                for (int q = 0; q < NG; ++q) {
+                                    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (q < ngv) xv = *reinterpret_cast<const float4*>(my_ring_p + (d * NG + q) * 128);
+                                    const float f[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-                                for (int e = 0; e < 4; ++e)
+                                    for (int e = 0; e < 4; ++e)
 #pragma unroll
-                                    for (int h = 0; h < HP; ++h) part[h] = fmaf(f[e], dT[4 * q + e][h], part[h]);
-                            }
-                            if (!act) {
-#pragma unroll
-                                for (int h = 0; h < HP; ++h) part[h] = 0.f;
+                                        for (int h = 0; h < HP; ++h) part[h] = fmaf(f[e], dT[4 * q + e][h], part[h]);
+                                }
                             }
                             // reduce over the batch lanes of the sub-group (transposed butterfly)
                             int hsel = 0;
@@ -575,8 +586,9 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
 #pragma unroll
                                 for (int k = 0; k < NF; ++k) dst[k] = part[k];
                             }
-                            if (it + d + D < clen) issue(xbuf[d], it + d + D);
+                            if (it + d + D < clen) issue(d, it + d + D);
                         }
+                        tc::cp_async_commit();
                     }
                 }
             }
@@ -598,7 +610,8 @@ int launch_dtc(const DphiArgs& a, int B, cudaStream_t st)
     constexpr int CXC = 64 / HP, PPW = 32 >> LB;
     const int nkc = qc_ceil_div(a.Cx, CXC);
     const int nblk = qc_nblk(B);
-    const size_t smem = ((size_t)nkc * 2 * WSLICE + 8 * PPW * PCH) * 4 + 64;
+    constexpr int RING = (32 / (CXC / 4)) * (CXC / 4) * 512;
+    const size_t smem = ((size_t)nkc * 2 * WSLICE + 8 * PPW * PCH) * 4 + 64 + 8 * RING;
     if (smem > 227 * 1024) return 0;
     QC_CUDA(cudaFuncSetAttribute(k_dphi_tc<HP, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = qc_ceil_div(a.Ndst, 8 * PPW);

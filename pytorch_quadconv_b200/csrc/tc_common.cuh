@@ -109,6 +109,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 
+// ---- asynchronous global->shared copies (LDGSTS): completion is tracked per commit group in FIFO
+// order, NOT through the 6 per-warp scoreboards -- ptxas puts every gather LDG of an unrolled loop on
+// one scoreboard, which collapses a register-prefetch pipeline to a depth of one (profiles/README.md).
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
