@@ -25,15 +25,22 @@ namespace {
 constexpr int TS = 68;   // row stride of the T tile in shared memory (DW mini-GEMM)
 constexpr int ZS = 36;   // row stride of the Z tile
 constexpr int PCH = 64;  // pairs staged per chunk
-constexpr int BSLICE = 32 * 64;  // floats per weight slice (N = 32 rows x K = 64), hi or lo
 
-template <int HP, int LB, bool DW>
-__global__ void __launch_bounds__(256, 1)
+// KCH = K of one channel chunk = channels per chunk x HP.  KCH = 64 runs one CTA per SM (TMEM: 2 row
+// blocks x (64 hi + 64 lo + 32 D) = 320 of 512 columns); KCH = 32 halves the register tile and the
+// TMEM footprint (2 x 96 = 192 -> a 256-column allocation) so that TWO CTAs share an SM: 16 warps
+// hide the latencies that 8 cannot.  The DW variant keeps KCH = 64 (its mini-GEMM tiles assume it).
+template <int HP, int KCH, int LB, bool DW>
+__global__ void __launch_bounds__(256, KCH == 32 ? 2 : 1)
 k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
 {
-    constexpr int CXC = 64 / HP, Bp = 1 << LB, PPW = 32 >> LB;
+    static_assert(!DW || KCH == 64, "the dW mini-GEMM assumes 64-wide chunks");
+    constexpr int CXC = KCH / HP, Bp = 1 << LB, PPW = 32 >> LB;
+    constexpr int BSLICE = 32 * KCH;            // floats per weight slice (N = 32 rows x K = KCH), hi or lo
+    constexpr int TCOLS = KCH == 32 ? 256 : 512;   // TMEM columns allocated by this CTA
+    constexpr int RBCOLS = 2 * KCH + 32;           // per row block: A_hi, A_lo, D
     constexpr int NG = CXC / 4, HQ = HP / 4;
-    constexpr int D = (DW ? 8 : 32) / NG;       // gathered pairs in flight per warp (async smem ring)
+    constexpr int D = (DW ? 8 : (KCH == 32 ? 6 : 32)) / NG;   // gathered pairs in flight per warp (async smem ring)
     constexpr int RING = D * NG * 512;          // bytes per warp: slot = NG groups x 32 lanes x 16 B
     constexpr int PHS = PCH * HP + 4;
     extern __shared__ __align__(128) float smem[];
@@ -58,7 +65,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     const int ntiles = (a.Ndst + ppt - 1) / ppt;
 
     // ---- one-time setup: TMEM, mbarriers, weight slices -------------------------------------
-    if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
+    if (warp == 0) tc::tmem_alloc(tmem_base_s, TCOLS);
     if (tid == 32) {
         tc::mbar_init(&bars[0], 1);
         tc::mbar_init(&bars[1], 1);
@@ -66,13 +73,13 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     }
     for (int idx = tid; idx < nkc * BSLICE; idx += 256) {
         const int kc = idx / BSLICE, r = idx % BSLICE;
-        const int n = r >> 6, k = r & 63;                          // n = output channel j, k = (i, h)
+        const int n = r / KCH, k = r % KCH;                        // n = output channel j, k = (i, h)
         const int i = k / HP, h = k % HP;
         const int cx = kc * CXC + i;
         float v = 0.f;
         if (cx < a.Cx && h < a.H && n < a.Cy) v = __ldg(a.W2 + ((size_t)cx * a.H + h) * a.CyP + n);
         const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-        const uint32_t off = tc::kmajor_off_bytes(n, k, 64) / 4;
+        const uint32_t off = tc::kmajor_off_bytes(n, k, KCH) / 4;
         Bs[(size_t)(kc * 2 + 0) * BSLICE + off] = hi;
         Bs[(size_t)(kc * 2 + 1) * BSLICE + off] = v - hi;
     }
@@ -84,7 +91,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_base_s;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t a_hi = tmem + rb * 160, a_lo = a_hi + 64, d_acc = a_hi + 128;
+    const uint32_t a_hi = tmem + rb * RBCOLS, a_lo = a_hi + KCH, d_acc = a_hi + 2 * KCH;
     const uint32_t idesc = tc::make_idesc_tf32(128, 32);
     const uint32_t bs_addr = tc::smem_u32(Bs);
     uint32_t g = 0;  // MMA groups committed so far on this row block (same value in all its threads)
@@ -197,7 +204,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                 tc::fence_after_sync();
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < KCH / 16; ++c) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -215,9 +222,9 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
             if ((warp & 3) == 0 && lane == 0) {
                 tc::fence_after_sync();
                 const uint32_t bhi = bs_addr + (uint32_t)(kc * 2) * BSLICE * 4, blo = bhi + BSLICE * 4;
-                constexpr uint32_t SBO = (64 / 4) * 128;
+                constexpr uint32_t SBO = (KCH / 4) * 128;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
+                for (int ks = 0; ks < KCH / 8; ++ks) {
                     const uint64_t dhi = tc::make_smem_desc(bhi + ks * 256, 128, SBO);
                     const uint64_t dlo = tc::make_smem_desc(blo + ks * 256, 128, SBO);
                     tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dhi, idesc, !(kc == 0 && ks == 0));
@@ -324,17 +331,18 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+    if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
 }
 
-template <int HP, int LB, bool DW>
+template <int HP, int KCH, int LB, bool DW>
 int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
 {
-    constexpr int CXC = 64 / HP, PPW = 32 >> LB;
+    constexpr int CXC = KCH / HP, PPW = 32 >> LB;
+    constexpr int BSLICE = 32 * KCH;
     const int nkc = qc_ceil_div(a.Cx, CXC);
     const int nblk = qc_nblk(B);
     constexpr int NG = CXC / 4;
-    constexpr int RING = ((DW ? 8 : 32) / NG) * NG * 512;
+    constexpr int RING = ((DW ? 8 : (KCH == 32 ? 6 : 32)) / NG) * NG * 512;
     size_t smem = ((size_t)nkc * 2 * BSLICE + 8 * PPW * (PCH * HP + 4) + 8 * PPW * PCH) * 4 + 32 + 8 * RING;
     int dw_in_smem = 0;
     if (DW) {
@@ -344,15 +352,22 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
             smem += (size_t)nkc * 64 * 32 * 4;
         }
     }
+    constexpr int CTAS = KCH == 32 ? 2 : 1;
+    if (CTAS == 2) {
+        // exactly two CTAs per SM: each allocates 256 of the 512 TMEM columns, a third resident CTA
+        // would spin in tcgen05.alloc forever -> keep the footprint above a third of the SM's smem
+        if (smem < 80 * 1024) smem = 80 * 1024;
+        if (smem > 113 * 1024) return 0;
+    }
     if (smem > 227 * 1024) return 0;   // weight slices do not fit: use the FP32-pipe kernel
-    QC_CUDA(cudaFuncSetAttribute(k_contract_tc<HP, LB, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA(cudaFuncSetAttribute(k_contract_tc<HP, KCH, LB, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = qc_ceil_div(a.Ndst, 8 * PPW);
-    int gx = qc_num_sms();
+    int gx = qc_num_sms() * CTAS;
     gx = (gx + nblk - 1) / nblk;
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     dim3 grid(gx, nblk);
-    k_contract_tc<HP, LB, DW><<<grid, 256, smem, st>>>(a, nkc, dw_in_smem);
+    k_contract_tc<HP, KCH, LB, DW><<<grid, 256, smem, st>>>(a, nkc, dw_in_smem);
     QC_CHECK_LAUNCH();
     return 1;
 }
@@ -633,7 +648,17 @@ int qc_contract_tc(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t s
     if (a.Cy > 32 || !(HP == 4 || HP == 8) || !(Bp == 8 || Bp == 32)) return 0;
     if ((size_t)a.Nsrc * qc_cp4(a.Cx) * Bp >= ((size_t)1 << 32)) return 0;
     if (nullptr != getenv("QC_NO_FAST") || nullptr != getenv("QC_NO_TC")) return 0;
-#define QC_T(HPV, LBV) (dw ? launch_tc<HPV, LBV, true>(a, B, st) : launch_tc<HPV, LBV, false>(a, B, st))
+    // Forward-type launches can also run with 32-wide chunks and two CTAs per SM (QC_TC_K32=1).
+    // Measured on C3 (profiles/README.md): 16 instead of 8 warps/SM lift issue utilisation from 45 % to
+    // 60 %, but the per-pair overhead is amortised over half the FMAs (+23 % instructions) and the two
+    // CTAs halve the L1 hit rate, so the time is the same (4.0 ms); the one-CTA variant is the default.
+    if (!dw && nullptr != getenv("QC_TC_K32")) {
+        int rc;
+        if (HP == 4) rc = Bp == 8 ? launch_tc<4, 32, 3, false>(a, B, st) : launch_tc<4, 32, 5, false>(a, B, st);
+        else rc = Bp == 8 ? launch_tc<8, 32, 3, false>(a, B, st) : launch_tc<8, 32, 5, false>(a, B, st);
+        if (rc != 0) return rc;
+    }
+#define QC_T(HPV, LBV) (dw ? launch_tc<HPV, 64, LBV, true>(a, B, st) : launch_tc<HPV, 64, LBV, false>(a, B, st))
     if (HP == 4) return Bp == 8 ? QC_T(4, 3) : QC_T(4, 5);
     return Bp == 8 ? QC_T(8, 3) : QC_T(8, 5);
 #undef QC_T
