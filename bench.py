@@ -2,7 +2,7 @@
 """
 bench.py -- QuadConv layer fwd+bwd throughput (BASELINE.json metric: "QuadConv layer fwd+bwd Mpairs/s").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c4|c2|c5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one forward + backward of one QuadConv layer over one batch of synthetic features:
@@ -52,6 +52,12 @@ def workload(name: str):
         N = 10_000
         return dict(name="C4: 2-D 10k pts, 64->128 ch, batch 8, filter_seq [32,32], r=sqrt(200/(pi N)) (fp32 path)",
                     N=N, d=2, ci=64, co=128, B=8, fs=[32, 32], r=float(np.sqrt(200 / (np.pi * N))))
+    if name in ("c2", "c5"):
+        # QuadConv + Mesh_MaxPool autoencoder on a 10k-point 2-D mesh, 4 pooling stages
+        return dict(name=("C2" if name == "c2" else "C5") + ": autoencoder 10k-pt 2-D mesh, levels via mfnus, "
+                    "channels [4,8,16,32,32], filter_seq [8,8], training step (MSE + Adam)",
+                    N=10_000, d=2, ci=4, co=4, B=8 if name == "c2" else 256, fs=[8, 8], r=None, model="autoencoder",
+                    strong=(name == "c5"))
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -190,6 +196,47 @@ def build_problem(w, dev):
     return mesh.to(dev), layer.to(dev), x_host
 
 
+class QuadConvAutoencoder(torch.nn.Module):
+    """C2: encoder 4 x (QuadConv(output_same) -> sin -> Mesh_MaxPool), decoder mirrored with the adjoint
+    pool; built only from the drop-in modules, as a user of the reference would."""
+
+    def __init__(self, mesh, channels, filter_seq):
+        super().__init__()
+        import pytorch_quadconv_b200 as q
+        self.mesh = mesh
+        lv = mesh.point_seq
+        nl = len(lv) - 1
+        mk = lambda n, ci, co: q.QuadConv(spatial_dim=2, in_points=n, out_points=n, in_channels=ci, out_channels=co,
+                                          filter_seq=filter_seq, output_same=True, bias=True)
+        self.enc = torch.nn.ModuleList([mk(lv[l], channels[l], channels[l + 1]) for l in range(nl)])
+        self.dec = torch.nn.ModuleList([mk(lv[l], channels[l + 1], channels[l]) for l in reversed(range(nl))])
+        self.pools = torch.nn.ModuleList([q.Mesh_MaxPool() for _ in range(nl)])
+        self.unpools = torch.nn.ModuleList([q.Mesh_MaxPool(adjoint=True) for _ in range(nl)])
+
+    def forward(self, x):
+        self.mesh.reset()
+        for conv, pool in zip(self.enc, self.pools):
+            x = pool(self.mesh, torch.sin(conv(self.mesh, x)))
+        for i, (up, conv) in enumerate(zip(self.unpools, self.dec)):
+            x = conv(self.mesh, up(self.mesh, x))
+            if i + 1 < len(self.dec):
+                x = torch.sin(x)
+        return x
+
+    def pairs(self):
+        return sum(int(m.eval_indices.shape[0]) for m in list(self.enc) + list(self.dec))
+
+
+def build_autoencoder(w, dev, B):
+    import pytorch_quadconv_b200 as q
+    torch.manual_seed(0)
+    pts = torch.rand(w["N"], 2)
+    x_host = torch.randn(B, 4, w["N"]).pin_memory()
+    mesh = q.MeshHandler(pts).construct([w["N"], 0, 0, 0, 0], mirror=True, quad_map="mfnus")
+    model = QuadConvAutoencoder(mesh, [4, 8, 16, 32, 32], w["fs"])
+    return mesh.to(dev), model.to(dev), x_host
+
+
 def time_kernels(w, mesh, layer, x, reps=5):
     """Per-kernel device time of one fwd+bwd, CUDA events on the launching (current) stream around
     each C-ABI call.  Returns {name: ms}."""
@@ -278,21 +325,40 @@ def main():
     _cabi.lib()
     from pytorch_quadconv_b200.distributed import FlatGradAllReduce, trainable_parameters
 
-    mesh, layer, x_host = build_problem(w, dev)
-    x = x_host.to(dev).requires_grad_()
-    params = trainable_parameters([layer, mesh])
-    reducer = FlatGradAllReduce(params) if world > 1 else None
+    is_ae = w.get("model") == "autoencoder"
+    if is_ae:
+        b_local = w["B"] // world if w.get("strong") else w["B"]
+        mesh, layer, x_host = build_autoencoder(w, dev, b_local)
+        x = x_host.to(dev)
+        params = trainable_parameters([layer])      # the model owns the mesh (and its weight network)
+        reducer = FlatGradAllReduce(params) if world > 1 else None
+        opt = torch.optim.Adam(params, lr=1e-3)
 
-    def step(xin):
-        for p in params:
-            p.grad = None
-        xin.grad = None
-        y = layer(mesh, xin)
-        loss = y.sum()
-        loss.backward()
-        if reducer is not None:
-            reducer()
-        return loss
+        def step(xin):
+            opt.zero_grad(set_to_none=True)
+            y = layer(xin)
+            loss = torch.nn.functional.mse_loss(y, xin.detach())
+            loss.backward()
+            if reducer is not None:
+                reducer()
+            opt.step()
+            return loss
+    else:
+        mesh, layer, x_host = build_problem(w, dev)
+        x = x_host.to(dev).requires_grad_()
+        params = trainable_parameters([layer, mesh])
+        reducer = FlatGradAllReduce(params) if world > 1 else None
+
+        def step(xin):
+            for p in params:
+                p.grad = None
+            xin.grad = None
+            y = layer(mesh, xin)
+            loss = y.sum()
+            loss.backward()
+            if reducer is not None:
+                reducer()
+            return loss
 
     def sync():
         if world > 1:
@@ -301,7 +367,7 @@ def main():
 
     for _ in range(args.warmup):
         step(x)
-    P = int(layer.eval_indices.shape[0])
+    P = layer.pairs() if is_ae else int(layer.eval_indices.shape[0])
 
     # ---- device-resident timing --------------------------------------------------------------
     sync()
@@ -324,7 +390,9 @@ def main():
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        xin = x_host.to(dev, non_blocking=True).requires_grad_()
+        xin = x_host.to(dev, non_blocking=True)
+        if not is_ae:
+            xin.requires_grad_()
         loss = step(xin)
         loss_host.copy_(loss.detach(), non_blocking=True)
         for h, p in zip(grads_host, [p for p in layer.parameters() if p.requires_grad]):
@@ -347,7 +415,11 @@ def main():
 
     # ---- per-kernel table + roofline of the dominant kernel (rank 0) ----------------------------
     roof, cb, table = None, None, None
-    if rank == 0:
+    if rank == 0 and is_ae:
+        roof = {"bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                "note": "multi-layer training step: launch-latency dominated (SURVEY 8d); per-kernel roofline is "
+                        "reported on the single-layer workloads (default c3)"}
+    if rank == 0 and not is_ae:
         table, calls_per_step = time_kernels(w, mesh, layer, x)
         peaks = {}
         try:
@@ -392,14 +464,18 @@ def main():
 
     if rank == 0:
         launches = 0
+        if is_ae:
+            launches = 8 * 13 + 8 * 2      # 8 QuadConv layers x 13 kernels (fwd+bwd) + 8 pool layers x 2
         if table:
             # every timed C-ABI call launches exactly one of our kernels (csrc/*.cu); memsets are not counted
             launches = calls_per_step
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if w.get("strong") else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "pairs_per_gpu": P, "batch_per_gpu": w["B"],
+            "config": {"workload": w["name"], "pairs_per_gpu": P,
+                       "batch_per_gpu": (w["B"] // world if w.get("strong") else w["B"]),
                        "parallelism": f"batch-sharded dp{world}, flat NCCL all-reduce of parameter grads",
                        "l2": "inputs larger than L2 (features+grads 1.6 GB/step > 126 MB)" if w["N"] >= 50000
                        else "working set fits in L2 (reference's own CPU-runnable case)",
