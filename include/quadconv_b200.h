@@ -178,6 +178,22 @@ int qc_gather_fwd(const float* x, const int* index /*[Nout]*/, int BC, int Nin, 
 int qc_gather_bwd(const float* grad_out, const int* grp_ptr, const int* grp_mem, int BC, int Nfine,
                   int Ncoarse, float* grad_x, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Learned quadrature-weight map.  Replaces MeshHandler.weight_map,
+ * torch_quadconv/mesh_handler.py:101-112 (per-simplex Linear/Sigmoid x4 + scatter_add_) and its
+ * autograd.  adj: [M][E] int32 simplices, wb: HOST array of 8 device pointers
+ * {W0,b0,W1,b1,W2,b2,W3,b3} (Linear(E*d,8), (8,8), (8,8), (8,E), Sigmoid after each).
+ *   qc_weight_map_fwd : el_w[M][E]
+ *   qc_vertex_sum     : w[v] = sum of el_w over the incidences of vertex v (CSR inc_ptr/inc_idx of
+ *                       flat (simplex*E+slot) indices, ascending) -- deterministic scatter_add_
+ *   qc_weight_map_bwd : accumulates (+=) d W/b into dwb (8 device pointers) from gw = d loss / d w[N]
+ * ------------------------------------------------------------------------------------------ */
+int qc_weight_map_fwd(const float* pts, const int* adj, int M, int E, int d, const float* const* wb,
+                      float* el_w, void* stream);
+int qc_vertex_sum(const float* el_w, const int* inc_ptr, const int* inc_idx, int N, float* w, void* stream);
+int qc_weight_map_bwd(const float* pts, const int* adj, int M, int E, int d, const float* const* wb,
+                      const float* gw, float* const* dwb, void* stream);
+
 /* Known-answer self test of the tcgen05 building blocks (TMEM alloc, tcgen05.st/ld, kind::tf32 MMA with
  * A in TMEM and B through a K-major shared-memory descriptor, 3xTF32 split):
  * D[128][32] = A[128][64] * B[32][64]^T.  Used by tests only. */

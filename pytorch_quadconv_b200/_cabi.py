@@ -59,6 +59,10 @@ _SIGNATURES = {
     "qc_gather_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qc_gather_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qc_tc_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "qc_weight_map_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
+    "qc_vertex_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "qc_weight_map_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p,
+                                  ctypes.POINTER(c_void_p), c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

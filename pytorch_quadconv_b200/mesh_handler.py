@@ -89,8 +89,19 @@ class MeshHandler(nn.Module):
                 self._weight_activation(),
             )
 
+            fusable = (self._weight_activation is nn.Sigmoid and element_size <= 4 and dimension <= 3)
+
             def weight_map(points):
                 element_list = self.adjacency()
+                if fusable and points.is_cuda and points.dtype == torch.float32:
+                    # fused sm_100a kernels (csrc/weight_map.cu): one launch per direction + a
+                    # deterministic per-vertex gather-sum instead of ~15 ATen kernels each way
+                    from . import ops
+                    adj32, inc_ptr, inc_idx = self._incidence(self._get_index(), element_list)
+                    params = [p for lin in (self._weight_network[0], self._weight_network[2],
+                                            self._weight_network[4], self._weight_network[6])
+                              for p in (lin.weight, lin.bias)]
+                    return ops.weight_map_apply(points.detach(), adj32, inc_ptr, inc_idx, params)
                 el_points = points[element_list].reshape(-1, element_size * dimension)
                 el_weights = self._weight_network(el_points)
                 weights = torch.zeros(points.shape[0], device=points.device)
@@ -98,6 +109,25 @@ class MeshHandler(nn.Module):
                 return weights.scatter_add(0, element_list.reshape(-1), el_weights.reshape(-1))
 
         self.weight_map = weight_map
+
+    def _incidence(self, level, element_list):
+        """int32 simplices + CSR of the (simplex, slot) incidences of every vertex for one level,
+        built once on the host (setup-time) and cached per device."""
+        cache = self.__dict__.setdefault("_wm_cache", {})
+        key = (level, str(element_list.device), element_list.data_ptr())
+        hit = cache.get(key)
+        if hit is None:
+            adj = element_list.detach().cpu().numpy()
+            flat = adj.reshape(-1)
+            n = int(self._points[level].shape[0])
+            order = np.argsort(flat, kind="stable").astype(np.int32)
+            inc_ptr = np.zeros(n + 1, dtype=np.int32)
+            np.cumsum(np.bincount(flat, minlength=n), out=inc_ptr[1:])
+            dev = element_list.device
+            hit = (torch.from_numpy(adj.astype(np.int32)).to(dev).contiguous(), torch.from_numpy(inc_ptr).to(dev),
+                   torch.from_numpy(order).to(dev))
+            cache[key] = hit
+        return hit
 
     # -- hierarchy construction (mesh_handler.py:161-212) ---------------------------------------
     def construct(self, point_seq, mirror=False, quad_map='param_quad', weight_map=True, quad_args=None):

@@ -318,6 +318,69 @@ def quadconv_apply(features, quad_w, hidden_ws, w_last, bias, tables, in_channel
 
 
 # ---------------------------------------------------------------------------------------------
+# learned quadrature weights (MeshHandler.weight_map, mesh_handler.py:101-112)
+# ---------------------------------------------------------------------------------------------
+
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[C.ptr(t) for t in tensors])
+
+
+@torch.library.custom_op("quadconv_b200::weight_map", mutates_args=())
+def weight_map(points: Tensor, adj32: Tensor, inc_ptr: Tensor, inc_idx: Tensor, params: Sequence[Tensor]) -> Tensor:
+    """weights[N] = scatter_add of the per-simplex MLP outputs; params = [W0,b0,W1,b1,W2,b2,W3,b3]."""
+    points = _f32c(points, "points")
+    params = [_f32c(p, "weight-network parameter") for p in params]
+    M, E = adj32.shape
+    N, d = points.shape
+    el_w = torch.empty((M, E), dtype=torch.float32, device=points.device)
+    C.check(C.lib().qc_weight_map_fwd(C.ptr(points), C.ptr(adj32), M, E, d, _ptr_array(params), C.ptr(el_w), C.stream()),
+            "qc_weight_map_fwd")
+    w = torch.empty(N, dtype=torch.float32, device=points.device)
+    C.check(C.lib().qc_vertex_sum(C.ptr(el_w), C.ptr(inc_ptr), C.ptr(inc_idx), N, C.ptr(w), C.stream()), "qc_vertex_sum")
+    return w
+
+
+@weight_map.register_fake
+def _(points, adj32, inc_ptr, inc_idx, params):
+    return points.new_empty(points.shape[0])
+
+
+@torch.library.custom_op("quadconv_b200::weight_map_bwd", mutates_args=())
+def weight_map_bwd(grad_w: Tensor, points: Tensor, adj32: Tensor, params: Sequence[Tensor]) -> List[Tensor]:
+    grad_w = _f32c(grad_w, "grad")
+    points = _f32c(points, "points")
+    params = [_f32c(p, "weight-network parameter") for p in params]
+    M, E = adj32.shape
+    grads = [torch.zeros_like(p) for p in params]
+    C.check(C.lib().qc_weight_map_bwd(C.ptr(points), C.ptr(adj32), M, E, points.shape[1], _ptr_array(params),
+                                      C.ptr(grad_w), _ptr_array(grads), C.stream()), "qc_weight_map_bwd")
+    return grads
+
+
+@weight_map_bwd.register_fake
+def _(grad_w, points, adj32, params):
+    return [torch.empty_like(p) for p in params]
+
+
+class _WeightMapFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, adj32, inc_ptr, inc_idx, *params):
+        ctx.save_for_backward(points, adj32, *params)
+        return weight_map(points, adj32, inc_ptr, inc_idx, list(params))
+
+    @staticmethod
+    def backward(ctx, grad_w):
+        points, adj32, *params = ctx.saved_tensors
+        grads = weight_map_bwd(grad_w, points, adj32, list(params))
+        return (None, None, None, None, *grads)
+
+
+def weight_map_apply(points, adj32, inc_ptr, inc_idx, params):
+    return _WeightMapFn.apply(points, adj32, inc_ptr, inc_idx, *params)
+
+
+# ---------------------------------------------------------------------------------------------
 # Mesh_MaxPool
 # ---------------------------------------------------------------------------------------------
 
