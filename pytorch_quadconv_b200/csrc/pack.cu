@@ -12,7 +12,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 k_pack(const float* __restrict__ x, int B, int C, int N, int Bp, float* __restrict__ xp)
 {
-    __shared__ float tile[4][32][33];  // [channel in group][batch lane][point]
+    __shared__ float tile[4][32 * 33 + 8];  // [channel in group][batch lane * 33 + point]; +8: the 4 planes hit distinct banks
     const int n0 = blockIdx.x * 32, cg = blockIdx.y, blk = blockIdx.z;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int CG = gridDim.y;
@@ -21,14 +21,14 @@ k_pack(const float* __restrict__ x, int B, int C, int N, int Bp, float* __restri
         const int c = cg * 4 + e, b = blk * 32 + bl, n = n0 + lane;
         float v = 0.f;
         if (c < C && b < B && n < N) v = x[((size_t)b * C + c) * N + n];
-        tile[e][bl][lane] = v;
+        tile[e][bl * 33 + lane] = v;
     }
     __syncthreads();
     // write: per point Bp*4 contiguous floats, (lane, channel-in-group) innermost
     for (int idx = threadIdx.x; idx < 32 * Bp * 4; idx += 256) {
         const int e = idx & 3, bl = (idx >> 2) % Bp, nl = (idx >> 2) / Bp;
         const int n = n0 + nl;
-        if (n < N) xp[((((size_t)blk * N + n) * CG + cg) * Bp + bl) * 4 + e] = tile[e][bl][nl];
+        if (n < N) xp[((((size_t)blk * N + n) * CG + cg) * Bp + bl) * 4 + e] = tile[e][bl * 33 + nl];
     }
 }
 
@@ -36,14 +36,14 @@ __global__ void __launch_bounds__(256)
 k_unpack(const float* __restrict__ xp, int B, int C, int N, int Bp, const float* __restrict__ bias,
          float* __restrict__ x)
 {
-    __shared__ float tile[4][32][33];
+    __shared__ float tile[4][32 * 33 + 8];
     const int n0 = blockIdx.x * 32, cg = blockIdx.y, blk = blockIdx.z;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int CG = gridDim.y;
     for (int idx = threadIdx.x; idx < 32 * Bp * 4; idx += 256) {
         const int e = idx & 3, bl = (idx >> 2) % Bp, nl = (idx >> 2) / Bp;
         const int n = n0 + nl;
-        tile[e][bl][nl] = n < N ? xp[((((size_t)blk * N + n) * CG + cg) * Bp + bl) * 4 + e] : 0.f;
+        tile[e][bl * 33 + nl] = n < N ? xp[((((size_t)blk * N + n) * CG + cg) * Bp + bl) * 4 + e] : 0.f;
     }
     __syncthreads();
     const int n = n0 + lane;
@@ -52,7 +52,7 @@ k_unpack(const float* __restrict__ xp, int B, int C, int N, int Bp, const float*
         const int c = cg * 4 + e, b = blk * 32 + bl;
         if (c < C && b < B && n < N) {
             const float bv = bias != nullptr ? bias[(size_t)c * N + n] : 0.f;
-            x[((size_t)b * C + c) * N + n] = tile[e][bl][lane] + bv;
+            x[((size_t)b * C + c) * N + n] = tile[e][bl * 33 + lane] + bv;
         }
     }
 }
