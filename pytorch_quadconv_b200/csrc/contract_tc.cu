@@ -40,7 +40,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     constexpr int TCOLS = KCH == 32 ? 256 : 512;   // TMEM columns allocated by this CTA
     constexpr int RBCOLS = 2 * KCH + 32;           // per row block: A_hi, A_lo, D
     constexpr int NG = CXC / 4, HQ = HP / 4;
-    constexpr int D = (DW ? 8 : (KCH == 32 ? 6 : 32)) / NG;   // gathered pairs in flight per warp (async smem ring)
+    constexpr int D = (DW ? 8 : (KCH == 32 ? 6 : 16)) / NG;   // gathered pairs in flight per warp (async smem ring)
     constexpr int RING = D * NG * 512;          // bytes per warp: slot = NG groups x 32 lanes x 16 B
     constexpr int PHS = PCH * HP + 4;
     extern __shared__ __align__(128) float smem[];
@@ -342,7 +342,7 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
     const int nkc = qc_ceil_div(a.Cx, CXC);
     const int nblk = qc_nblk(B);
     constexpr int NG = CXC / 4;
-    constexpr int RING = ((DW ? 8 : (KCH == 32 ? 6 : 32)) / NG) * NG * 512;
+    constexpr int RING = ((DW ? 8 : (KCH == 32 ? 6 : 16)) / NG) * NG * 512;
     size_t smem = ((size_t)nkc * 2 * BSLICE + 8 * PPW * (PCH * HP + 4) + 8 * PPW * PCH) * 4 + 32 + 8 * RING;
     int dw_in_smem = 0;
     if (DW) {
@@ -386,7 +386,8 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
 {
     constexpr int CXC = 64 / HP, Bp = 1 << LB, PPW = 32 >> LB;
     constexpr int NG = CXC / 4;
-    constexpr int D = 32 / NG;                  // gathered pairs in flight per warp (async smem ring)
+    constexpr int D = 16 / NG;                  // gathered pairs in flight per warp (async smem ring); the unrolled
+                                                // loop body must stay inside the 32 KB instruction cache
     constexpr int RING = D * NG * 512;
     constexpr int LH = HP == 8 ? 3 : 2;
     constexpr int NH = LB < LH ? LB : LH;
@@ -625,7 +626,7 @@ int launch_dtc(const DphiArgs& a, int B, cudaStream_t st)
     constexpr int CXC = 64 / HP, PPW = 32 >> LB;
     const int nkc = qc_ceil_div(a.Cx, CXC);
     const int nblk = qc_nblk(B);
-    constexpr int RING = (32 / (CXC / 4)) * (CXC / 4) * 512;
+    constexpr int RING = (16 / (CXC / 4)) * (CXC / 4) * 512;
     const size_t smem = ((size_t)nkc * 2 * WSLICE + 8 * PPW * PCH) * 4 + 64 + 8 * RING;
     if (smem > 227 * 1024) return 0;
     QC_CUDA(cudaFuncSetAttribute(k_dphi_tc<HP, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
