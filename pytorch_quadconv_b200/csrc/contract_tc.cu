@@ -30,11 +30,16 @@ constexpr int PCH = 64;  // pairs staged per chunk
 // blocks x (64 hi + 64 lo + 32 D) = 320 of 512 columns); KCH = 32 halves the register tile and the
 // TMEM footprint (2 x 96 = 192 -> a 256-column allocation) so that TWO CTAs share an SM: 16 warps
 // hide the latencies that 8 cannot.  The DW variant keeps KCH = 64 (its mini-GEMM tiles assume it).
-template <int HP, int KCH, int LB, bool DW>
-__global__ void __launch_bounds__(256, KCH == 32 ? 2 : 1)
+// NW = warps per CTA: 8 (two 128-row blocks) or 12 (three; 3 x 160 = 480 TMEM columns, 170 registers per
+// thread) -- more resident warps per scheduler to cover the FP32 pipe's dependency stalls.
+template <int HP, int KCH, int LB, bool DW, int NW>
+__global__ void __launch_bounds__(NW * 32, KCH == 32 ? 2 : 1)
 k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
 {
     static_assert(!DW || KCH == 64, "the dW mini-GEMM assumes 64-wide chunks");
+    static_assert(!DW || NW == 8, "the dW mini-GEMM assumes 256 threads");
+    static_assert(NW == 8 || (NW == 12 && KCH == 64), "supported CTA shapes");
+    constexpr int NT = NW * 32;
     constexpr int CXC = KCH / HP, Bp = 1 << LB, PPW = 32 >> LB;
     constexpr int BSLICE = 32 * KCH;            // floats per weight slice (N = 32 rows x K = KCH), hi or lo
     constexpr int TCOLS = KCH == 32 ? 256 : 512;   // TMEM columns allocated by this CTA
@@ -45,12 +50,12 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     constexpr int PHS = PCH * HP + 4;
     extern __shared__ __align__(128) float smem[];
     float* Bs = smem;                                              // [nkc][2][BSLICE] (hi, lo), canonical K-major
-    float* phi_s = Bs + (size_t)nkc * 2 * BSLICE;                  // [8*PPW][PHS]
-    int* idx_s = reinterpret_cast<int*>(phi_s + 8 * PPW * PHS);    // [8*PPW][PCH]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + 8 * PPW * PCH);  // [2] mbarriers + tmem base
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2);
-    float* ring_s = reinterpret_cast<float*>(bars + 4);            // [8 warps][RING bytes]
-    float* T_s = ring_s + 8 * RING / 4;                            // DW: [256][TS]
+    float* phi_s = Bs + (size_t)nkc * 2 * BSLICE;                  // [NW*PPW][PHS]
+    int* idx_s = reinterpret_cast<int*>(phi_s + NW * PPW * PHS);   // [NW*PPW][PCH]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + NW * PPW * PCH);  // [3] mbarriers + tmem base
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 3);
+    float* ring_s = reinterpret_cast<float*>(bars + 4);            // [NW warps][RING bytes]
+    float* T_s = ring_s + NW * RING / 4;                            // DW: [256][TS]
     float* Z_s = T_s + 256 * TS;                                   // DW: [256][ZS]
     float* dW_s = Z_s + 256 * ZS;                                  // DW && dw_in_smem: [nkc*64][32]
 
@@ -61,7 +66,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     const unsigned xrow = (unsigned)qc_cp4(a.Cx) * Bp;
     const size_t yrow = (size_t)qc_cp4(a.Cy) * Bp;
     const float* Xb = a.X + (size_t)blk * a.Nsrc * xrow + b * 4;
-    constexpr int ppt = 8 * PPW;
+    constexpr int ppt = NW * PPW;
     const int ntiles = (a.Ndst + ppt - 1) / ppt;
 
     // ---- one-time setup: TMEM, mbarriers, weight slices -------------------------------------
@@ -69,9 +74,10 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     if (tid == 32) {
         tc::mbar_init(&bars[0], 1);
         tc::mbar_init(&bars[1], 1);
+        tc::mbar_init(&bars[2], 1);
         tc::mbar_fence_init();
     }
-    for (int idx = tid; idx < nkc * BSLICE; idx += 256) {
+    for (int idx = tid; idx < nkc * BSLICE; idx += NT) {
         const int kc = idx / BSLICE, r = idx % BSLICE;
         const int n = r / KCH, k = r % KCH;                        // n = output channel j, k = (i, h)
         const int i = k / HP, h = k % HP;
@@ -334,7 +340,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
 }
 
-template <int HP, int KCH, int LB, bool DW>
+template <int HP, int KCH, int LB, bool DW, int NW>
 int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
 {
     constexpr int CXC = KCH / HP, PPW = 32 >> LB;
@@ -343,7 +349,7 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
     const int nblk = qc_nblk(B);
     constexpr int NG = CXC / 4;
     constexpr int RING = ((DW ? 8 : (KCH == 32 ? 6 : 16)) / NG) * NG * 512;
-    size_t smem = ((size_t)nkc * 2 * BSLICE + 8 * PPW * (PCH * HP + 4) + 8 * PPW * PCH) * 4 + 32 + 8 * RING;
+    size_t smem = ((size_t)nkc * 2 * BSLICE + NW * PPW * (PCH * HP + 4) + NW * PPW * PCH) * 4 + 32 + NW * RING;
     int dw_in_smem = 0;
     if (DW) {
         smem += (256 * TS + 256 * ZS) * 4;
@@ -360,14 +366,14 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
         if (smem > 113 * 1024) return 0;
     }
     if (smem > 227 * 1024) return 0;   // weight slices do not fit: use the FP32-pipe kernel
-    QC_CUDA(cudaFuncSetAttribute(k_contract_tc<HP, KCH, LB, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int ntiles = qc_ceil_div(a.Ndst, 8 * PPW);
+    QC_CUDA(cudaFuncSetAttribute(k_contract_tc<HP, KCH, LB, DW, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = qc_ceil_div(a.Ndst, NW * PPW);
     int gx = qc_num_sms() * CTAS;
     gx = (gx + nblk - 1) / nblk;
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     dim3 grid(gx, nblk);
-    k_contract_tc<HP, KCH, LB, DW><<<grid, 256, smem, st>>>(a, nkc, dw_in_smem);
+    k_contract_tc<HP, KCH, LB, DW, NW><<<grid, NW * 32, smem, st>>>(a, nkc, dw_in_smem);
     QC_CHECK_LAUNCH();
     return 1;
 }
@@ -655,11 +661,16 @@ int qc_contract_tc(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t s
     // CTAs halve the L1 hit rate, so the time is the same (4.0 ms); the one-CTA variant is the default.
     if (!dw && nullptr != getenv("QC_TC_K32")) {
         int rc;
-        if (HP == 4) rc = Bp == 8 ? launch_tc<4, 32, 3, false>(a, B, st) : launch_tc<4, 32, 5, false>(a, B, st);
-        else rc = Bp == 8 ? launch_tc<8, 32, 3, false>(a, B, st) : launch_tc<8, 32, 5, false>(a, B, st);
+        if (HP == 4) rc = Bp == 8 ? launch_tc<4, 32, 3, false, 8>(a, B, st) : launch_tc<4, 32, 5, false, 8>(a, B, st);
+        else rc = Bp == 8 ? launch_tc<8, 32, 3, false, 8>(a, B, st) : launch_tc<8, 32, 5, false, 8>(a, B, st);
         if (rc != 0) return rc;
     }
-#define QC_T(HPV, LBV) (dw ? launch_tc<HPV, 64, LBV, true>(a, B, st) : launch_tc<HPV, 64, LBV, false>(a, B, st))
+    // forward-type launches with H = 8: three 128-row blocks (12 warps) per CTA unless QC_TC_NW8=1
+    if (!dw && HP == 8 && nullptr == getenv("QC_TC_NW8")) {
+        const int rc = Bp == 8 ? launch_tc<8, 64, 3, false, 12>(a, B, st) : launch_tc<8, 64, 5, false, 12>(a, B, st);
+        if (rc != 0) return rc;
+    }
+#define QC_T(HPV, LBV) (dw ? launch_tc<HPV, 64, LBV, true, 8>(a, B, st) : launch_tc<HPV, 64, LBV, false, 8>(a, B, st))
     if (HP == 4) return Bp == 8 ? QC_T(4, 3) : QC_T(4, 5);
     return Bp == 8 ? QC_T(8, 3) : QC_T(8, 5);
 #undef QC_T
