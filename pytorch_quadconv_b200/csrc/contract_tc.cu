@@ -382,14 +382,16 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
 // ---------------------------------------------------------------------------------------------
 // d(phi) kernel with the dense stage  dT[row][(c,h)] = sum_j G[row][j] * W3[j][c][h]  on tcgen05:
 // the thread's grad_out row (hi/lo) is the A operand in TMEM (written once per tile), the W3 slices
-// of all channel chunks are the B operand in shared memory, D (64 columns) is double buffered in
-// TMEM so the MMAs of chunk kc+1 / kc+2 run while the FP32 pipe walks the pair list of chunk kc.
+// of all channel chunks are the B operand in shared memory; as soon as every thread of a row block has
+// pulled D (64 columns) of chunk kc into registers the MMAs of chunk kc+1 are issued into the same
+// TMEM columns and run while the FP32 pipe walks the pair list of chunk kc.  NW = 8 or 12 warps.
 constexpr int WSLICE = 64 * 32;  // floats per W3 slice: N = 64 rows (c,h) x K = 32 (j), hi or lo
 
-template <int HP, int LB>
-__global__ void __launch_bounds__(256, 1)
+template <int HP, int LB, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
 {
+    constexpr int NT = NW * 32;
     constexpr int CXC = 64 / HP, Bp = 1 << LB, PPW = 32 >> LB;
     constexpr int NG = CXC / 4;
     constexpr int D = 16 / NG;                  // gathered pairs in flight per warp (async smem ring); the unrolled
@@ -400,10 +402,10 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
     constexpr int NF = HP >> NH;
     extern __shared__ __align__(128) float smem[];
     float* Ws = smem;                                              // [nkc][2][WSLICE]
-    int* idx_s = reinterpret_cast<int*>(Ws + (size_t)nkc * 2 * WSLICE);   // [8*PPW][PCH]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + 8 * PPW * PCH);  // [2 row blocks][2 buffers]
+    int* idx_s = reinterpret_cast<int*>(Ws + (size_t)nkc * 2 * WSLICE);   // [NW*PPW][PCH]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + NW * PPW * PCH); // one mbarrier per row block
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 4);
-    float* ring_s = reinterpret_cast<float*>(bars + 8);                   // [8 warps][RING bytes]
+    float* ring_s = reinterpret_cast<float*>(bars + 8);                   // [NW warps][RING bytes]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rb = warp >> 2;
@@ -412,7 +414,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
     const unsigned xrow = (unsigned)qc_cp4(a.Cx) * Bp;
     const size_t grow = (size_t)qc_cp4(a.Cg) * Bp;
     const float* Xb = a.X + (size_t)blk * a.Nsrc * xrow + b * 4;
-    constexpr int ppt = 8 * PPW;
+    constexpr int ppt = NW * PPW;
     const int ntiles = (a.Ndst + ppt - 1) / ppt;
     const bool writer = (lane & ((1 << (LB - NH)) - 1)) == 0;
 
@@ -422,7 +424,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
         for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
         tc::mbar_fence_init();
     }
-    for (int idx = tid; idx < nkc * WSLICE; idx += 256) {
+    for (int idx = tid; idx < nkc * WSLICE; idx += NT) {
         const int kc = idx / WSLICE, r = idx % WSLICE;
         const int n = r >> 5, k = r & 31;                          // n = (i,h) of the chunk, k = j
         const int i = n / HP, h = n % HP;
@@ -440,19 +442,19 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_base_s;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    // TMEM columns per row block: A_hi [0,32) A_lo [32,64) D0 [64,128) D1 [128,192)
-    const uint32_t a_hi = tmem + rb * 192, a_lo = a_hi + 32, d0 = a_hi + 64;
+    // TMEM columns per row block: A_hi [0,32) A_lo [32,64) D [64,128)
+    const uint32_t a_hi = tmem + rb * 128, a_lo = a_hi + 32, d0 = a_hi + 64;
     const uint32_t idesc = tc::make_idesc_tf32(128, 64);
     const uint32_t ws_addr = tc::smem_u32(Ws);
-    uint64_t* mybars = bars + rb * 2;
-    uint32_t cnt[2] = {0u, 0u};   // completed waits per D buffer (phase bookkeeping)
+    uint64_t* mybar = bars + rb;
+    uint32_t cnt = 0u;            // completed waits on this row block's barrier (phase bookkeeping)
     const bool issuer = (warp & 3) == 0 && lane == 0;
 
     auto issue_mma = [&](int kc) {
-        // dT chunk kc -> D[kc & 1]
+        // dT chunk kc -> D
         const uint32_t whi = ws_addr + (uint32_t)(kc * 2) * WSLICE * 4, wlo = whi + WSLICE * 4;
         constexpr uint32_t SBO = (32 / 4) * 128;
-        const uint32_t d = d0 + (kc & 1) * 64;
+        const uint32_t d = d0;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const uint64_t dhi = tc::make_smem_desc(whi + ks * 256, 128, SBO);
@@ -461,7 +463,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
             tc::mma_tf32_ts(d, a_lo + ks * 8, dhi, idesc, true);
             tc::mma_tf32_ts(d, a_hi + ks * 8, dlo, idesc, true);
         }
-        tc::mma_commit(&mybars[kc & 1]);
+        tc::mma_commit(mybar);
     };
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -505,7 +507,6 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
             if (issuer) {
                 tc::fence_after_sync();
                 issue_mma(0);
-                if (nkc > 1) issue_mma(1);
             }
         }
 
@@ -513,14 +514,13 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
             const int cx0 = kc * CXC;
             const int nval = min(CXC, a.Cx - cx0);
             const int ngv = (nval + 3) >> 2;
-            const int q2 = kc & 1;
             // dT of this chunk: TMEM -> registers
-            tc::mbar_wait(&mybars[q2], cnt[q2] & 1);
-            ++cnt[q2];
+            tc::mbar_wait(mybar, cnt & 1);
+            ++cnt;
             tc::fence_after_sync();
             float dT[CXC][HP];
             {
-                const uint32_t d = lane_base + d0 + q2 * 64;
+                const uint32_t d = lane_base + d0;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t r[16];
@@ -530,13 +530,13 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                     for (int j = 0; j < 16; ++j) dT[(c * 16 + j) / HP][(c * 16 + j) % HP] = __uint_as_float(r[j]);
                 }
             }
-            if (kc + 2 < nkc) {
-                // D[q2] is free again once every thread of the row block has read it
+            if (kc + 1 < nkc) {
+                // D is free again once every thread of the row block has read it
                 tc::fence_before_sync();
                 tc::named_bar_sync(1 + rb, 128);
                 if (issuer) {
                     tc::fence_after_sync();
-                    issue_mma(kc + 2);
+                    issue_mma(kc + 1);
                 }
             }
 
@@ -626,23 +626,23 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-template <int HP, int LB>
+template <int HP, int LB, int NW>
 int launch_dtc(const DphiArgs& a, int B, cudaStream_t st)
 {
     constexpr int CXC = 64 / HP, PPW = 32 >> LB;
     const int nkc = qc_ceil_div(a.Cx, CXC);
     const int nblk = qc_nblk(B);
     constexpr int RING = (16 / (CXC / 4)) * (CXC / 4) * 512;
-    const size_t smem = ((size_t)nkc * 2 * WSLICE + 8 * PPW * PCH) * 4 + 64 + 8 * RING;
+    const size_t smem = ((size_t)nkc * 2 * WSLICE + NW * PPW * PCH) * 4 + 64 + NW * RING;
     if (smem > 227 * 1024) return 0;
-    QC_CUDA(cudaFuncSetAttribute(k_dphi_tc<HP, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int ntiles = qc_ceil_div(a.Ndst, 8 * PPW);
+    QC_CUDA(cudaFuncSetAttribute(k_dphi_tc<HP, LB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = qc_ceil_div(a.Ndst, NW * PPW);
     int gx = qc_num_sms();
     gx = (gx + nblk - 1) / nblk;
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     dim3 grid(gx, nblk);
-    k_dphi_tc<HP, LB><<<grid, 256, smem, st>>>(a, nkc, (size_t)a.P * HP);
+    k_dphi_tc<HP, LB, NW><<<grid, NW * 32, smem, st>>>(a, nkc, (size_t)a.P * HP);
     QC_CHECK_LAUNCH();
     return 1;
 }
@@ -682,6 +682,10 @@ int qc_dphi_tc(const DphiArgs& a, int HP, int B, cudaStream_t st)
     if (!qc_dphi_fast_ok(a.Nsrc, a.Cx, a.Cg, HP, B)) return 0;
     if (nullptr != getenv("QC_NO_TC")) return 0;
     const int Bp = qc_bp(B);
-    if (HP == 4) return Bp == 8 ? launch_dtc<4, 3>(a, B, st) : launch_dtc<4, 5>(a, B, st);
-    return Bp == 8 ? launch_dtc<8, 3>(a, B, st) : launch_dtc<8, 5>(a, B, st);
+    if (HP == 4) return Bp == 8 ? launch_dtc<4, 3, 8>(a, B, st) : launch_dtc<4, 5, 8>(a, B, st);
+    if (nullptr == getenv("QC_TC_NW8")) {   // H = 8: three 128-row blocks per CTA
+        const int rc = Bp == 8 ? launch_dtc<8, 3, 12>(a, B, st) : launch_dtc<8, 5, 12>(a, B, st);
+        if (rc != 0) return rc;
+    }
+    return Bp == 8 ? launch_dtc<8, 3, 8>(a, B, st) : launch_dtc<8, 5, 8>(a, B, st);
 }
