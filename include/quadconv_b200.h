@@ -198,6 +198,8 @@ int qc_weight_map_bwd(const float* pts, const int* adj, int M, int E, int d, con
  * A in TMEM and B through a K-major shared-memory descriptor, 3xTF32 split):
  * D[128][32] = A[128][64] * B[32][64]^T.  Used by tests only. */
 int qc_tc_selftest(const float* A, const float* B, float* D, void* stream);
+/* Same product with BOTH operands in shared memory (SS mode). Used by tests only. */
+int qc_tc_selftest_ss(const float* A, const float* B, float* D, void* stream);
 
 #ifdef __cplusplus
 }

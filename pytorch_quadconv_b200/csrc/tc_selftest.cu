@@ -88,7 +88,86 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict_
     if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+// Second building block: both operands from shared memory (SS mode), K-major no-swizzle descriptors:
+// D[128 x 32] = A[128 x 64] * B[32 x 64]^T in 3xTF32.
+__global__ void __launch_bounds__(128, 1) k_tc_selftest_ss(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                            float* __restrict__ D)
+{
+    extern __shared__ __align__(128) float dyn_smem[];
+    float* Ahi = dyn_smem;              // [128][64] K-major
+    float* Alo = Ahi + 128 * 64;
+    float* Bhi = Alo + 128 * 64;        // [32][64]
+    float* Blo = Bhi + 32 * 64;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 32);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_fence_init();
+    }
+    for (int k = 0; k < 64; ++k) {
+        const float v = A[(size_t)tid * 64 + k];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const uint32_t off = tc::kmajor_off_bytes(tid, k, 64) / 4;
+        Ahi[off] = hi;
+        Alo[off] = v - hi;
+    }
+    for (int idx = tid; idx < 32 * 64; idx += 128) {
+        const int n = idx / 64, k = idx % 64;
+        const float v = Bm[idx];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const uint32_t off = tc::kmajor_off_bytes(n, k, 64) / 4;
+        Bhi[off] = hi;
+        Blo[off] = v - hi;
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_tf32(128, 32);
+        constexpr uint32_t SBO = (64 / 4) * 128;
+        bool acc = false;
+        for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t ahi = tc::make_smem_desc(tc::smem_u32(Ahi) + ks * 256, 128, SBO);
+            const uint64_t alo = tc::make_smem_desc(tc::smem_u32(Alo) + ks * 256, 128, SBO);
+            const uint64_t bhi = tc::make_smem_desc(tc::smem_u32(Bhi) + ks * 256, 128, SBO);
+            const uint64_t blo = tc::make_smem_desc(tc::smem_u32(Blo) + ks * 256, 128, SBO);
+            tc::mma_tf32_ss(tmem, ahi, bhi, idesc, acc);
+            acc = true;
+            tc::mma_tf32_ss(tmem, alo, bhi, idesc, true);
+            tc::mma_tf32_ss(tmem, ahi, blo, idesc, true);
+        }
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    uint32_t q0[16], q1[16];
+    const uint32_t lb = (uint32_t)(warp * 32) << 16;
+    tc::tmem_ld16(lb + tmem, q0);
+    tc::tmem_ld16(lb + tmem + 16, q1);
+    tc::wait_ld();
+    for (int j = 0; j < 16; ++j) {
+        D[(size_t)tid * 32 + j] = __uint_as_float(q0[j]);
+        D[(size_t)tid * 32 + 16 + j] = __uint_as_float(q1[j]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 32);
+}
+
 }  // namespace
+
+extern "C" int qc_tc_selftest_ss(const float* A, const float* B, float* D, void* stream)
+{
+    const int smem = (2 * 128 * 64 + 2 * 32 * 64) * 4;
+    QC_CUDA(cudaFuncSetAttribute(k_tc_selftest_ss, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_tc_selftest_ss<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int qc_tc_selftest(const float* A, const float* B, float* D, void* stream)
 {

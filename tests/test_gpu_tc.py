@@ -23,3 +23,8 @@ def test_tcgen05_3xtf32_gemm(cuda_lib):
     C.check(cuda_lib.qc_tc_selftest(C.ptr(A2), C.ptr(B2), C.ptr(D), C.stream()), "qc_tc_selftest")
     ref2 = A2.double() @ B2.double().T
     assert float((D.double() - ref2).abs().max()) < 1e-3
+    # both operands through shared-memory descriptors (SS mode)
+    D.fill_(float("nan"))
+    C.check(cuda_lib.qc_tc_selftest_ss(C.ptr(A), C.ptr(B), C.ptr(D), C.stream()), "qc_tc_selftest_ss")
+    torch.cuda.synchronize()
+    assert float((D.double() - ref).norm() / ref.norm()) < 2e-6
