@@ -292,6 +292,8 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture the step in a CUDA graph and replay it (small meshes are launch-latency bound)")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel timing table (json) here")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -332,7 +334,7 @@ def main():
         x = x_host.to(dev)
         params = trainable_parameters([layer])      # the model owns the mesh (and its weight network)
         reducer = FlatGradAllReduce(params) if world > 1 else None
-        opt = torch.optim.Adam(params, lr=1e-3)
+        opt = torch.optim.Adam(params, lr=1e-3, capturable=args.graph)
 
         def step(xin):
             opt.zero_grad(set_to_none=True)
@@ -368,6 +370,28 @@ def main():
     for _ in range(args.warmup):
         step(x)
     P = layer.pairs() if is_ae else int(layer.eval_indices.shape[0])
+
+    if args.graph:
+        # whole step (forward, backward, optimiser / all-reduce excluded) as one CUDA graph on static buffers
+        assert world == 1, "--graph is a single-GPU option"
+        eager_step = step
+        x_static = x.detach().clone().requires_grad_(x.requires_grad)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                eager_step(x_static)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss_static = eager_step(x_static)
+
+        def step(xin):
+            if xin is not x_static:
+                x_static.data.copy_(xin.detach(), non_blocking=True)
+            graph.replay()
+            return loss_static
+        x = x_static
 
     # ---- device-resident timing --------------------------------------------------------------
     sync()
@@ -479,7 +503,8 @@ def main():
                        "parallelism": f"batch-sharded dp{world}, flat NCCL all-reduce of parameter grads",
                        "l2": "inputs larger than L2 (features+grads 1.6 GB/step > 126 MB)" if w["N"] >= 50000
                        else "working set fits in L2 (reference's own CPU-runnable case)",
-                       "includes": "MeshHandler.weights() (PyTorch autograd, mesh_handler.py:101-112) every step"},
+                       "includes": "MeshHandler.weights() (fused weight-map kernels, mesh_handler.py:101-112) every step",
+                       "cuda_graph": bool(args.graph)},
             "clocks": clk.summary(),
             "e2e": {"value": P * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
