@@ -118,6 +118,9 @@ class _StubMesh:
     (3, 900, 32, 16, 64, [4, 4], 0.2, True, None),     # fast path, two batch blocks (B = 64), H = 4
     (2, 600, 8, 8, 8, [8, 8], 0.25, False, None),      # fast path, ~118 pairs/point: several staged chunks
     (2, 500, 16, 16, 32, [4, 4], 0.3, True, 200),      # fast path, ~140 pairs/point, cross-level, B = 32
+    (2, 1200, 8, 8, 8, [8, 8], 0.012, True, 500),      # tensor-core path, tiny radius: most out points have NO pair
+    (3, 2000, 32, 32, 32, [8, 8], 0.05, False, None),  # tensor-core path, ~1 pair/point (self pairs), 3 row blocks
+    (2, 50, 8, 8, 32, [8, 8], 0.3, False, None),       # fewer points than one CTA tile
 ])
 def test_layer_matches_oracle(cuda_lib, d, n, ci, co, B, fs, r, bias, n_out):
     import pytorch_quadconv_b200 as q
