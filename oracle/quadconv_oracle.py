@@ -128,7 +128,7 @@ def quadconv_forward(out_pts, in_pts, quad_weights, filt_weights, features, eval
     for s in range(0, P, block_pairs):
         idx = eval_indices[s:s + block_pairs]
         w = quad_weights[idx[:, 1]]                                             # :247
-        eval_locs = out_pts[idx[:, 0]] - in_pts[idx[:, 1]]                      # :250-253
+        eval_locs = (out_pts[idx[:, 0]] - in_pts[idx[:, 1]]).to(features.dtype)  # :250-253 (fp32 subtract, as the reference)
         filters = filter_mlp(filt_weights, eval_locs).reshape(-1, in_channels, out_channels)  # :257,:91
         values = torch.einsum('n, nij, bin -> bjn', w, filters, features[:, :, idx[:, 1]])    # :216-219
         integral = integral.scatter_add(2, idx[:, 0].expand(B, out_channels, -1), values)    # :225

@@ -22,8 +22,14 @@
 
 namespace {
 
-constexpr int TS = 68;   // row stride of the T tile in shared memory (DW mini-GEMM)
-constexpr int ZS = 36;   // row stride of the Z tile
+// dW_last operand tiles (DW variant): K-major, K = the 128 rows of a row block.  A 144-byte step between
+// the 4-row core matrices makes the per-row scalar stores of a warp hit 32 distinct banks.
+constexpr int OP_LBO = 144;                 // bytes between core matrices adjacent in K (4 rows each)
+constexpr int OP_SBO = 32 * OP_LBO;         // bytes between 8-element groups in M / N
+constexpr int OP_A_BYTES = 8 * OP_SBO;      // T^T tile: 64 m  x 128 rows
+constexpr int OP_B_BYTES = 4 * OP_SBO;      // Z tile:   32 j  x 128 rows
+constexpr int OPBUF_BYTES = 2 * OP_A_BYTES + 2 * OP_B_BYTES;
+__host__ __device__ constexpr int op_off_words(int mn, int r) { return ((mn >> 3) * OP_SBO + (r >> 2) * OP_LBO + (mn & 7) * 16 + (r & 3) * 4) / 4; }
 constexpr int PCH = 64;  // pairs staged per chunk
 
 // KCH = K of one channel chunk = channels per chunk x HP.  KCH = 64 runs one CTA per SM (TMEM: 2 row
@@ -55,9 +61,12 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + NW * PPW * PCH);  // [3] mbarriers + tmem base
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 3);
     float* ring_s = reinterpret_cast<float*>(bars + 4);            // [NW warps][RING bytes]
-    float* T_s = ring_s + NW * RING / 4;                            // DW: [256][TS]
-    float* Z_s = T_s + 256 * TS;                                   // DW: [256][ZS]
-    float* dW_s = Z_s + 256 * ZS;                                  // DW && dw_in_smem: [nkc*64][32]
+    // DW: operand tiles of the dW_last GEMM, K-major with a 144-byte core-matrix step along K (= rows):
+    // T^T hi, T^T lo  [64 m][128 rows]  and  Z hi, Z lo  [32 j][128 rows]; one buffer, used by the two
+    // row blocks in turn under a lock.
+    float* opbuf = ring_s + NW * RING / 4;
+    uint64_t* opbar = reinterpret_cast<uint64_t*>(opbuf + OPBUF_BYTES / 4);
+    int* lockw = reinterpret_cast<int*>(opbar + 1);                // [0] lock, [1] commits so far, [2+kc] touched
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rb = warp >> 2;                                      // 128-row block of this warp
@@ -75,6 +84,10 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
         tc::mbar_init(&bars[0], 1);
         tc::mbar_init(&bars[1], 1);
         tc::mbar_init(&bars[2], 1);
+        if (DW) {
+            tc::mbar_init(opbar, 1);
+            for (int i = 0; i < 16; ++i) lockw[i] = 0;   // [0] lock, [1] commits, [2+kc] accumulator kc touched
+        }
         tc::mbar_fence_init();
     }
     for (int idx = tid; idx < nkc * BSLICE; idx += NT) {
@@ -89,8 +102,6 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
         Bs[(size_t)(kc * 2 + 0) * BSLICE + off] = hi;
         Bs[(size_t)(kc * 2 + 1) * BSLICE + off] = v - hi;
     }
-    if (DW && dw_in_smem)
-        for (int i = tid; i < nkc * 64 * 32; i += 256) dW_s[i] = 0.f;
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
@@ -115,23 +126,10 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
         const int* sidx = a.src_idx + beg;
         const int* pidx = a.phi_idx ? a.phi_idx + beg : nullptr;
 
-        if (DW) {
-            __syncthreads();  // the previous tile's last mini-GEMM is done with Z_s
-            float* zr = Z_s + (warp * 32 + lane) * ZS;
-            const float* zg = a.Z + ((size_t)blk * a.Ndst + (pvalid ? dstp : 0)) * yrow + b * 4;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pvalid && 4 * q < a.Cy) v = __ldg(reinterpret_cast<const float4*>(zg + (size_t)q * Bp * 4));
-                *reinterpret_cast<float4*>(zr + 4 * q) = v;
-            }
-        }
-
         for (int kc = 0; kc < nkc; ++kc) {
             const int cx0 = kc * CXC;
             const int nval = min(CXC, a.Cx - cx0);
             const int ngv = (nval + 3) >> 2;
-            if (DW) __syncthreads();  // T_s of the previous chunk is no longer read
 
             // ---- stage B: segmented gather-accumulate on the FP32 pipe ---------------------------
             float T[CXC][HP];
@@ -223,9 +221,48 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                 tc::tmem_st16(lane_base + a_lo + c * 16, lo);
             }
             tc::wait_st();
+            const bool leader = (warp & 3) == 0 && lane == 0;
+            int commits = 0;
+            if (DW && leader) {
+                // take the operand buffer: lock, then wait until the previous user's MMAs have read it
+                while (atomicCAS(&lockw[0], 0, 1) != 0) __nanosleep(64);
+                __threadfence_block();
+                commits = *reinterpret_cast<volatile int*>(&lockw[1]);
+                if (commits > 0) tc::mbar_wait(opbar, (commits - 1) & 1);
+            }
             tc::fence_before_sync();
             tc::named_bar_sync(1 + rb, 128);
-            if ((warp & 3) == 0 && lane == 0) {
+            if (DW) {
+                // this thread's row of T (hi/lo) and of Z (hi/lo) -> K-major operand tiles, K = row
+                const int r = (warp & 3) * 32 + lane;
+                float* Ahi = opbuf;
+                float* Alo = opbuf + OP_A_BYTES / 4;
+                float* Bhi = opbuf + 2 * OP_A_BYTES / 4;
+                float* Blo = Bhi + OP_B_BYTES / 4;
+#pragma unroll
+                for (int k = 0; k < 64; ++k) {
+                    const float v = T[k / HP][k % HP];
+                    const float hv = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                    Ahi[op_off_words(k, r)] = hv;
+                    Alo[op_off_words(k, r)] = v - hv;
+                }
+                const float* zg = a.Z + ((size_t)blk * a.Ndst + (pvalid ? dstp : 0)) * yrow + b * 4;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (pvalid && 4 * q < a.Cy) zv = __ldg(reinterpret_cast<const float4*>(zg + (size_t)q * Bp * 4));
+                    const float z4[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float hv = __uint_as_float(__float_as_uint(z4[e]) & 0xffffe000u);
+                        Bhi[op_off_words(4 * q + e, r)] = hv;
+                        Blo[op_off_words(4 * q + e, r)] = z4[e] - hv;
+                    }
+                }
+                tc::fence_proxy_async();
+                tc::named_bar_sync(1 + rb, 128);
+            }
+            if (leader) {
                 tc::fence_after_sync();
                 const uint32_t bhi = bs_addr + (uint32_t)(kc * 2) * BSLICE * 4, blo = bhi + BSLICE * 4;
                 constexpr uint32_t SBO = (KCH / 4) * 128;
@@ -238,68 +275,29 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                     tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dlo, idesc, true);
                 }
                 tc::mma_commit(&bars[rb]);
+                if (DW) {
+                    // dW2 chunk kc: D_dw[m][j] += sum_r T[r][m] * Z[r][j]  (M = 128: rows 64.. are don't-care)
+                    const uint32_t op = tc::smem_u32(opbuf);
+                    const uint32_t d_dw = tmem + 2 * RBCOLS + kc * 32;
+                    const bool fresh = lockw[2 + kc] == 0;   // first MMA group of this CTA into accumulator kc (under the lock)
+                    lockw[2 + kc] = 1;
+#pragma unroll 4
+                    for (int ks = 0; ks < 16; ++ks) {   // K = 128 rows, 8 per MMA = two 4-row core matrices
+                        const uint64_t ahi = tc::make_smem_desc(op + ks * 2 * OP_LBO, OP_LBO, OP_SBO);
+                        const uint64_t alo = tc::make_smem_desc(op + OP_A_BYTES + ks * 2 * OP_LBO, OP_LBO, OP_SBO);
+                        const uint64_t zhi = tc::make_smem_desc(op + 2 * OP_A_BYTES + ks * 2 * OP_LBO, OP_LBO, OP_SBO);
+                        const uint64_t zlo = tc::make_smem_desc(op + 2 * OP_A_BYTES + OP_B_BYTES + ks * 2 * OP_LBO, OP_LBO, OP_SBO);
+                        tc::mma_tf32_ss(d_dw, ahi, zhi, idesc, !(fresh && ks == 0));
+                        tc::mma_tf32_ss(d_dw, alo, zhi, idesc, true);
+                        tc::mma_tf32_ss(d_dw, ahi, zlo, idesc, true);
+                    }
+                    tc::mma_commit(opbar);
+                    *reinterpret_cast<volatile int*>(&lockw[1]) = commits + 1;
+                    __threadfence_block();
+                    atomicExch(&lockw[0], 0);
+                }
             }
             ++g;
-
-            if (DW) {
-                // dW2[(c,h)][j] += sum_rows T[row][(c,h)] * Z[row][j] for this chunk (FP32 pipe)
-                float* tr = T_s + (warp * 32 + lane) * TS;
-#pragma unroll
-                for (int i = 0; i < CXC; ++i)
-#pragma unroll
-                    for (int hq = 0; hq < HP / 4; ++hq)
-                        *reinterpret_cast<float4*>(tr + i * HP + 4 * hq) =
-                            make_float4(T[i][4 * hq], T[i][4 * hq + 1], T[i][4 * hq + 2], T[i][4 * hq + 3]);
-                __syncthreads();
-                const int half = tid >> 7, tq = tid & 127;
-                const int kq = tq >> 3, jq = tq & 7;
-                float c[4][4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) c[r][cc] = 0.f;
-                const float* tp = T_s + (half * 128) * TS + kq * 4;
-                const float* zp = Z_s + (half * 128) * ZS + jq * 4;
-#pragma unroll 4
-                for (int row = 0; row < 128; ++row) {
-                    const float4 tv = *reinterpret_cast<const float4*>(tp + row * TS);
-                    const float4 zv = *reinterpret_cast<const float4*>(zp + row * ZS);
-                    const float tva[4] = {tv.x, tv.y, tv.z, tv.w};
-                    const float zva[4] = {zv.x, zv.y, zv.z, zv.w};
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) c[r][cc] = fmaf(tva[r], zva[cc], c[r][cc]);
-                }
-                if (dw_in_smem) {
-                    float* dst = dW_s + ((size_t)kc * 64 + kq * 4) * 32 + jq * 4;
-                    if (half == 0) {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-#pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) dst[r * 32 + cc] += c[r][cc];
-                    }
-                    __syncthreads();
-                    if (half == 1) {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-#pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) dst[r * 32 + cc] += c[r][cc];
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int k = kq * 4 + r, i = k / HP, h = k % HP;
-                        if (i < nval && h < a.H) {
-#pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) {
-                                const int j = jq * 4 + cc;
-                                if (j < a.Cy) atomicAdd(a.dW2 + ((size_t)(cx0 + i) * a.H + h) * a.CyP + j, c[r][cc]);
-                            }
-                        }
-                    }
-                }
-            }
         }
 
         // ---- epilogue: D (TMEM) -> registers -> packed output rows ------------------------------
@@ -326,13 +324,29 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
         }
     }
 
-    if (DW && dw_in_smem) {
+    if (DW) {
+        // dW2 accumulators (TMEM lanes 0..63 = k index m, 32 columns = j, one block per chunk) -> global
         __syncthreads();
-        for (int idx = tid; idx < nkc * 64 * 32; idx += 256) {
-            const int kc = idx >> 11, k = (idx >> 5) & 63, j = idx & 31;
-            const int i = k / HP, h = k % HP;
-            const int cx = kc * CXC + i;
-            if (cx < a.Cx && h < a.H && j < a.Cy) atomicAdd(a.dW2 + ((size_t)cx * a.H + h) * a.CyP + j, dW_s[idx]);
+        const int commits = *reinterpret_cast<volatile int*>(&lockw[1]);
+        if (commits > 0) tc::mbar_wait(opbar, (commits - 1) & 1);
+        tc::fence_after_sync();
+        if (warp < 2 && commits > 0) {
+            const int m = warp * 32 + lane, i = m / HP, hh = m % HP;
+            for (int kc = 0; kc < nkc; ++kc) {
+                uint32_t v0[16], v1[16];
+                tc::tmem_ld16(lane_base + tmem + 2 * RBCOLS + kc * 32, v0);
+                tc::tmem_ld16(lane_base + tmem + 2 * RBCOLS + kc * 32 + 16, v1);
+                tc::wait_ld();
+                const int cx = kc * CXC + i;
+                if (cx < a.Cx && hh < a.H) {
+                    float* dst = a.dW2 + ((size_t)cx * a.H + hh) * a.CyP;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < a.Cy) atomicAdd(dst + j, __uint_as_float(v0[j]));
+                        if (16 + j < a.Cy) atomicAdd(dst + 16 + j, __uint_as_float(v1[j]));
+                    }
+                }
+            }
         }
     }
     tc::fence_before_sync();
@@ -352,11 +366,8 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
     size_t smem = ((size_t)nkc * 2 * BSLICE + NW * PPW * (PCH * HP + 4) + NW * PPW * PCH) * 4 + 32 + NW * RING;
     int dw_in_smem = 0;
     if (DW) {
-        smem += (256 * TS + 256 * ZS) * 4;
-        if (smem + (size_t)nkc * 64 * 32 * 4 <= 227 * 1024) {
-            dw_in_smem = 1;
-            smem += (size_t)nkc * 64 * 32 * 4;
-        }
+        smem += OPBUF_BYTES + 128;
+        if (2 * (2 * KCH + 32) + nkc * 32 > 512 || nkc > 12) return 0;   // TMEM: stage C blocks + one dW accumulator per chunk
     }
     constexpr int CTAS = KCH == 32 ? 2 : 1;
     if (CTAS == 2) {

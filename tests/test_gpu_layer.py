@@ -66,22 +66,34 @@ def test_dquadw_direct(cuda_lib):
 
 
 def _oracle_case(d, n, ci, co, B, fs, r, bias, seed, n_out=None):
-    """Fresh seeded problem; reference values from the oracle (torch fp32 restatement)."""
+    """Fresh seeded problem; reference values from the oracle's restatement of the reference path.
+    The oracle is evaluated in float64 on the fp32 inputs: torch's CPU fp32 bmm path showed run-to-run
+    deviations of up to 2.7e-5 (against float64) on the GPU boxes' hosts -- larger than the 1e-5 bound and
+    30x the kernels' own error (9e-7) -- so fp32-vs-fp32 comparison is anchored by the golden vectors of
+    the live reference (test_layer_matches_reference_golden) and these shape sweeps use the exact value."""
     from oracle import quadconv_oracle as O
     g = torch.Generator().manual_seed(seed)
     pts = torch.rand(n, d, generator=g)
     out_pts = pts if n_out is None else pts[torch.randperm(n, generator=g)[:n_out]].contiguous()
-    x = torch.randn(B, ci, n, generator=g).requires_grad_()
-    qw = (torch.rand(n, generator=g) + 0.5).requires_grad_()
+    x = torch.randn(B, ci, n, generator=g)
+    qw = torch.rand(n, generator=g) + 0.5
     dims = [d] + list(fs) + [ci * co]
-    ws = [(torch.randn(dims[l + 1], dims[l], generator=g) / np.sqrt(dims[l])).requires_grad_()
-          for l in range(len(dims) - 1)]
-    b = torch.randn(1, co, out_pts.shape[0], generator=g).requires_grad_() if bias else None
+    ws = [torch.randn(dims[l + 1], dims[l], generator=g) / np.sqrt(dims[l]) for l in range(len(dims) - 1)]
+    b = torch.randn(1, co, out_pts.shape[0], generator=g) if bias else None
     pairs = torch.from_numpy(O.eval_indices_c(out_pts.numpy(), pts.numpy(), r))
-    y = O.quadconv_forward(out_pts, pts, qw, ws, x, pairs, ci, co, b)
-    go = torch.randn(y.shape, generator=g)
-    (y * go).sum().backward()
-    return dict(pts=pts, out_pts=out_pts, x=x, qw=qw, ws=ws, b=b, pairs=pairs, y=y.detach(), go=go)
+    # float64 evaluation of the same formulas (offsets are formed in fp32 first, as the reference does)
+    x64, qw64 = x.double().requires_grad_(), qw.double().requires_grad_()
+    ws64 = [w.double().requires_grad_() for w in ws]
+    b64 = b.double().requires_grad_() if bias else None
+    y64 = O.quadconv_forward(out_pts, pts, qw64, ws64, x64, pairs, ci, co, b64)
+    go = torch.randn(y64.shape, generator=g)
+    (y64 * go.double()).sum().backward()
+    x.grad, qw.grad = x64.grad.float(), qw64.grad.float()
+    for w, w64 in zip(ws, ws64):
+        w.grad = w64.grad.float()
+    if bias:
+        b.grad = b64.grad.float()
+    return dict(pts=pts, out_pts=out_pts, x=x, qw=qw, ws=ws, b=b, pairs=pairs, y=y64.detach().float(), go=go)
 
 
 class _StubMesh:
@@ -217,7 +229,8 @@ def test_linearity_and_batch_independence_full_size(cuda_lib):
     mask = torch.isin(ev[:, 0], sel)
     sub = ev[mask].cpu()
     lin_w = [m.weight.detach().cpu() for m in layer.filter if isinstance(m, torch.nn.Linear)]
-    yo = O.quadconv_forward(pts, pts, w.cpu(), lin_w, x1[:4].cpu(), sub, 32, 32)
+    yo = O.quadconv_forward(pts, pts, w.cpu().double(), [v.double() for v in lin_w], x1[:4].cpu().double(), sub,
+                            32, 32).float()
     got = y1[:4][:, :, sel].cpu()
     assert relerr(got.numpy(), yo[:, :, sel.cpu()].numpy()) < TOL
 
