@@ -166,9 +166,10 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                     if (q < ngv) xv = *reinterpret_cast<const float4*>(my_ring_p + (slot * NG + q) * 128);
                     const float f[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2)
+                    for (int e2 = 0; e2 < 4; e2 += 2)
 #pragma unroll
-                        for (int h = 0; h < HP; ++h) T[4 * q + e2][h] = fmaf(f[e2], ph[h], T[4 * q + e2][h]);
+                        for (int h = 0; h < HP; ++h)
+                            tc::fma2(T[4 * q + e2][h], T[4 * q + e2 + 1][h], f[e2], f[e2 + 1], ph[h], ph[h]);
                 }
             };
             for (int c0 = 0; c0 < maxlen; c0 += PCH) {
@@ -592,7 +593,8 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
 #pragma unroll
                                     for (int e = 0; e < 4; ++e)
 #pragma unroll
-                                        for (int h = 0; h < HP; ++h) part[h] = fmaf(f[e], dT[4 * q + e][h], part[h]);
+                                        for (int h = 0; h < HP; h += 2)   // dT comes out of tcgen05.ld with h in adjacent registers
+                                            tc::fma2(part[h], part[h + 1], dT[4 * q + e][h], dT[4 * q + e][h + 1], f[e], f[e]);
                                 }
                             }
                             // reduce over the batch lanes of the sub-group (transposed butterfly)

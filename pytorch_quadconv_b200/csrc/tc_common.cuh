@@ -125,6 +125,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // ---- asynchronous global->shared copies (LDGSTS): completion is tracked per commit group in FIFO
 // order, NOT through the 6 per-warp scoreboards -- ptxas puts every gather LDG of an unrolled loop on
 // one scoreboard, which collapses a register-prefetch pipeline to a depth of one (profiles/README.md).
+// Packed FP32 FMA (Blackwell FFMA2): (d0, d1) += (a0, a1) * (b0, b1), each half rounded like fmaf.
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1)
+{
+    asm("{\n"
+        ".reg .b64 d, a, b;\n"
+        "mov.b64 d, {%0, %1};\n"
+        "mov.b64 a, {%2, %3};\n"
+        "mov.b64 b, {%4, %5};\n"
+        "fma.rn.f32x2 d, a, b, d;\n"
+        "mov.b64 {%0, %1}, d;\n"
+        "}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
