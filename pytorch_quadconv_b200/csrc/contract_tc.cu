@@ -102,6 +102,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
         Bs[(size_t)(kc * 2 + 0) * BSLICE + off] = hi;
         Bs[(size_t)(kc * 2 + 1) * BSLICE + off] = v - hi;
     }
+    for (int i = tid; i < NW * RING / 4; i += NT) ring_s[i] = 0.f;   // stale ring slots are read (and must be finite)
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
@@ -152,19 +153,24 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                 for (int q = 0; q < NG; ++q)
                     if (q < ngv) tc::cp_async16(my_ring + (slot * NG + q) * 512, xr + q * Bp);
             };
-            auto consume = [&](int slot, int e) {
-                float ph[HP];
+            // registers of one staged pair: its gathered channels and its phi row
+            struct Staged { float4 x[NG]; float4 ph[HQ]; };
+            auto load = [&](Staged& r, int slot, int e) {   // shared memory -> registers (slot has landed)
                 const float4* pr = reinterpret_cast<const float4*>(my_phi + e * HP);
 #pragma unroll
-                for (int q = 0; q < HQ; ++q) {
-                    const float4 v = pr[q];
-                    ph[4 * q] = v.x, ph[4 * q + 1] = v.y, ph[4 * q + 2] = v.z, ph[4 * q + 3] = v.w;
-                }
+                for (int q = 0; q < HQ; ++q) r.ph[q] = pr[q];
+#pragma unroll
+                for (int q = 0; q < NG; ++q)   // groups past ngv hold stale finite values; their W2 rows are zero
+                    r.x[q] = *reinterpret_cast<const float4*>(my_ring_p + (slot * NG + q) * 128);
+            };
+            auto fma = [&](const Staged& r) {
+                float ph[HP];
+#pragma unroll
+                for (int q = 0; q < HQ; ++q)
+                    ph[4 * q] = r.ph[q].x, ph[4 * q + 1] = r.ph[q].y, ph[4 * q + 2] = r.ph[q].z, ph[4 * q + 3] = r.ph[q].w;
 #pragma unroll
                 for (int q = 0; q < NG; ++q) {
-                    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (q < ngv) xv = *reinterpret_cast<const float4*>(my_ring_p + (slot * NG + q) * 128);
-                    const float f[4] = {xv.x, xv.y, xv.z, xv.w};
+                    const float f[4] = {r.x[q].x, r.x[q].y, r.x[q].z, r.x[q].w};
 #pragma unroll
                     for (int e2 = 0; e2 < 4; e2 += 2)
 #pragma unroll
@@ -190,15 +196,21 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                     if (d < clen) issue(d, d);
                     tc::cp_async_commit();
                 }
+                // software pipeline: while pair n is multiplied, pair n+1 moves shared -> registers
+                Staged cur, nxt;
+                tc::cp_async_wait<D - 1>();
+                load(cur, 0, 0);
                 for (int it = 0; it < cmax; it += D) {
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
-                        tc::cp_async_wait<D - 1>();       // the oldest group (slot d) has landed
+                        tc::cp_async_wait<D - 2>();       // the group of pair it+d+1 (slot d+1) has landed
+                        load(nxt, (d + 1) % D, it + d + 1);
                         if (it + d < clen) {
-                            consume(d, it + d);
+                            fma(cur);
                             if (it + d + D < clen) issue(d, it + d + D);
                         }
                         tc::cp_async_commit();
+                        cur = nxt;
                     }
                 }
             }
