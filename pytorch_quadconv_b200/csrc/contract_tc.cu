@@ -461,6 +461,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
         Ws[(size_t)(kc * 2 + 0) * WSLICE + off] = hi;
         Ws[(size_t)(kc * 2 + 1) * WSLICE + off] = v - hi;
     }
+    for (int i = tid; i < NW * RING / 4; i += NT) ring_s[i] = 0.f;   // stale ring slots are read (and must be finite)
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
@@ -587,10 +588,18 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                     if (d < clen) issue(d, d);
                     tc::cp_async_commit();
                 }
+                // software pipeline: pair n+1 moves shared -> registers under the dot products of pair n
+                float4 xc[NG], xn[NG];
+                tc::cp_async_wait<D - 1>();
+#pragma unroll
+                for (int q = 0; q < NG; ++q) xc[q] = *reinterpret_cast<const float4*>(my_ring_p + q * 128);
                 for (int it = 0; it < cmax; it += D) {
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
-                        tc::cp_async_wait<D - 1>();
+                        tc::cp_async_wait<D - 2>();
+#pragma unroll
+                        for (int q = 0; q < NG; ++q)   // groups past ngv: stale finite values times dT == 0
+                            xn[q] = *reinterpret_cast<const float4*>(my_ring_p + (((d + 1) % D) * NG + q) * 128);
                         if (it + d < cmax) {   // warp-uniform: the shuffles below need every lane
                             const bool act = it + d < clen;
                             float part[HP];
@@ -599,9 +608,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                             if (act) {
 #pragma unroll
                                 for (int q = 0; q < NG; ++q) {
-                                    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-                                    if (q < ngv) xv = *reinterpret_cast<const float4*>(my_ring_p + (d * NG + q) * 128);
-                                    const float f[4] = {xv.x, xv.y, xv.z, xv.w};
+                                    const float f[4] = {xc[q].x, xc[q].y, xc[q].z, xc[q].w};
 #pragma unroll
                                     for (int e = 0; e < 4; ++e)
 #pragma unroll
@@ -637,6 +644,8 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                             if (it + d + D < clen) issue(d, it + d + D);
                         }
                         tc::cp_async_commit();
+#pragma unroll
+                        for (int q = 0; q < NG; ++q) xc[q] = xn[q];
                     }
                 }
             }
