@@ -146,13 +146,13 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
             // per-warp ring; each lane copies and later reads back only its own 16 bytes per group
             const uint32_t my_ring = tc::smem_u32(ring_s) + warp * RING + lane * 16;
             const float* my_ring_p = ring_s + (warp * RING + lane * 16) / 4;
-            auto issue = [&](int slot, int e) {
-                const unsigned u = (unsigned)my_idx[e];
+            auto issue_u = [&](int slot, unsigned u) {
                 const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)(u * xrow));
 #pragma unroll
                 for (int q = 0; q < NG; ++q)
                     if (q < ngv) tc::cp_async16(my_ring + (slot * NG + q) * 512, xr + q * Bp);
             };
+            auto issue = [&](int slot, int e) { issue_u(slot, (unsigned)my_idx[e]); };
             // registers of one staged pair: its gathered channels and its phi row
             struct Staged { float4 x[NG]; float4 ph[HQ]; };
             auto load = [&](Staged& r, int slot, int e) {   // shared memory -> registers (slot has landed)
@@ -205,9 +205,10 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                     for (int d = 0; d < D; ++d) {
                         tc::cp_async_wait<D - 2>();       // the group of pair it+d+1 (slot d+1) has landed
                         load(nxt, (d + 1) % D, it + d + 1);
+                        const unsigned un = (unsigned)my_idx[it + d + D];   // read early; past the list it is unused
                         if (it + d < clen) {
                             fma(cur);
-                            if (it + d + D < clen) issue(d, it + d + D);
+                            if (it + d + D < clen) issue_u(d, un);
                         }
                         tc::cp_async_commit();
                         cur = nxt;
@@ -570,13 +571,13 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
             int* my_idx = idx_s + (warp * PPW + s) * PCH;
             const uint32_t my_ring = tc::smem_u32(ring_s) + warp * RING + lane * 16;
             const float* my_ring_p = ring_s + (warp * RING + lane * 16) / 4;
-            auto issue = [&](int slot, int e) {
-                const unsigned u = (unsigned)my_idx[e];
+            auto issue_u = [&](int slot, unsigned u) {
                 const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)(u * xrow));
 #pragma unroll
                 for (int q = 0; q < NG; ++q)
                     if (q < ngv) tc::cp_async16(my_ring + (slot * NG + q) * 512, xr + q * Bp);
             };
+            auto issue = [&](int slot, int e) { issue_u(slot, (unsigned)my_idx[e]); };
             for (int c0 = 0; c0 < maxlen; c0 += PCH) {
                 const int clen = min(PCH, len - c0);
                 const int cmax = min(PCH, maxlen - c0);
@@ -600,6 +601,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
 #pragma unroll
                         for (int q = 0; q < NG; ++q)   // groups past ngv: stale finite values times dT == 0
                             xn[q] = *reinterpret_cast<const float4*>(my_ring_p + (((d + 1) % D) * NG + q) * 128);
+                        const unsigned un = (unsigned)my_idx[it + d + D];   // read early; past the list it is unused
                         if (it + d < cmax) {   // warp-uniform: the shuffles below need every lane
                             const bool act = it + d < clen;
                             float part[HP];
@@ -641,7 +643,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
 #pragma unroll
                                 for (int k = 0; k < NF; ++k) dst[k] = part[k];
                             }
-                            if (it + d + D < clen) issue(d, it + d + D);
+                            if (it + d + D < clen) issue_u(d, un);
                         }
                         tc::cp_async_commit();
 #pragma unroll
