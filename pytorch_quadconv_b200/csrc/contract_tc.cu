@@ -443,6 +443,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
     constexpr int ppt = NW * PPW;
     const int ntiles = (a.Ndst + ppt - 1) / ppt;
     const bool writer = (lane & ((1 << (LB - NH)) - 1)) == 0;
+    const int hsel = (lane >> (LB - NH)) & ((1 << NH) - 1);   // the h this lane ends up holding after the butterfly
 
     if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
     if (tid == 32) {
@@ -556,6 +557,22 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
 #pragma unroll
                     for (int j = 0; j < 16; ++j) dT[(c * 16 + j) / HP][(c * 16 + j) % HP] = __uint_as_float(r[j]);
                 }
+                // permute the h slots of this lane (slot k <-> h = k ^ hsel) so that the butterfly below
+                // always keeps its low slots and sends its high ones: no selects in the per-pair loop
+#pragma unroll
+                for (int st = 0; st < NH; ++st) {
+                    const int bit = HP >> (st + 1);
+                    const bool upper = (lane & (1 << (LB - 1 - st))) != 0;
+#pragma unroll
+                    for (int c = 0; c < CXC; ++c)
+#pragma unroll
+                        for (int k = 0; k < HP; ++k)
+                            if (!(k & bit)) {
+                                const float x = dT[c][k], y = dT[c][k | bit];
+                                dT[c][k] = upper ? y : x;
+                                dT[c][k | bit] = upper ? x : y;
+                            }
+                }
             }
             if (kc + 1 < nkc) {
                 // D is free again once every thread of the row block has read it
@@ -619,20 +636,14 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                                 }
                             }
                             // reduce over the batch lanes of the sub-group (transposed butterfly)
-                            int hsel = 0;
 #pragma unroll
                             for (int st = 0; st < LB; ++st) {
                                 const int mask = 1 << (LB - 1 - st);
                                 if (st < NH) {
                                     const int half = HP >> (st + 1);
-                                    const bool upper = (lane & mask) != 0;
 #pragma unroll
-                                    for (int k = 0; k < half; ++k) {
-                                        const float send = upper ? part[k] : part[k + half];
-                                        const float keep = upper ? part[k + half] : part[k];
-                                        part[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-                                    }
-                                    hsel = (hsel << 1) | (upper ? 1 : 0);
+                                    for (int k = 0; k < half; ++k)
+                                        part[k] += __shfl_xor_sync(0xffffffffu, part[k + half], mask);
                                 } else {
                                     part[0] += __shfl_xor_sync(0xffffffffu, part[0], mask);
                                 }
