@@ -424,8 +424,15 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                                                 // loop body must stay inside the 32 KB instruction cache
     constexpr int RING = D * NG * 512;
     constexpr int LH = HP == 8 ? 3 : 2;
-    constexpr int NH = LB < LH ? LB : LH;
+    // With 32 batch lanes two pairs are reduced together: lane bit 4 picks the pair a half-warp ends up
+    // with, the low LBr = 4 bits reduce that pair (16 shuffles per two pairs instead of 2 x 9, and half
+    // the dependent stages per pair).
+    constexpr bool TWO = LB == 5;
+    constexpr int LBr = TWO ? 4 : LB;
+    constexpr int NH = LBr < LH ? LBr : LH;
     constexpr int NF = HP >> NH;
+    static_assert(NF == 1, "the butterfly ends with one value per lane");
+    static_assert(D % 2 == 0, "two-pair steps walk the ring two slots at a time");
     extern __shared__ __align__(128) float smem[];
     float* Ws = smem;                                              // [nkc][2][WSLICE]
     int* idx_s = reinterpret_cast<int*>(Ws + (size_t)nkc * 2 * WSLICE);   // [NW*PPW][PCH]
@@ -442,8 +449,9 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
     const float* Xb = a.X + (size_t)blk * a.Nsrc * xrow + b * 4;
     constexpr int ppt = NW * PPW;
     const int ntiles = (a.Ndst + ppt - 1) / ppt;
-    const bool writer = (lane & ((1 << (LB - NH)) - 1)) == 0;
-    const int hsel = (lane >> (LB - NH)) & ((1 << NH) - 1);   // the h this lane ends up holding after the butterfly
+    const bool writer = (lane & ((1 << (LBr - NH)) - 1)) == 0;
+    const int hsel = (lane >> (LBr - NH)) & ((1 << NH) - 1);   // the h this lane ends up holding after the butterfly
+    const int up = TWO ? (lane >> 4) & 1 : 0;                  // which pair of a two-pair step this half-warp keeps
 
     if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
     if (tid == 32) {
@@ -562,7 +570,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
 #pragma unroll
                 for (int st = 0; st < NH; ++st) {
                     const int bit = HP >> (st + 1);
-                    const bool upper = (lane & (1 << (LB - 1 - st))) != 0;
+                    const bool upper = (lane & (1 << (LBr - 1 - st))) != 0;
 #pragma unroll
                     for (int c = 0; c < CXC; ++c)
 #pragma unroll
@@ -606,59 +614,120 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                     if (d < clen) issue(d, d);
                     tc::cp_async_commit();
                 }
-                // software pipeline: pair n+1 moves shared -> registers under the dot products of pair n
-                float4 xc[NG], xn[NG];
-                tc::cp_async_wait<D - 1>();
+                if constexpr (TWO) {
+                    // two pairs per step: this half-warp accumulates the pair it keeps ("own", slot d + up)
+                    // into acc0 and the other half-warp's pair into acc1, so the first exchange needs no select
+                    const float* own_p = my_ring_p + up * (NG * 128);
+                    const float* oth_p = my_ring_p + (1 - up) * (NG * 128);
+                    for (int it = 0; it < cmax; it += D) {
 #pragma unroll
-                for (int q = 0; q < NG; ++q) xc[q] = *reinterpret_cast<const float4*>(my_ring_p + q * 128);
-                for (int it = 0; it < cmax; it += D) {
+                        for (int d = 0; d < D; d += 2) {
+                            tc::cp_async_wait<D - 2>();       // slots d and d+1 have landed
+                            const bool v0 = it + d < clen;
+                            if (v0) {
+                                float4 xa[NG], xb[NG];
 #pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        tc::cp_async_wait<D - 2>();
+                                for (int q = 0; q < NG; ++q) {   // groups past ngv: stale finite values times dT == 0
+                                    xa[q] = *reinterpret_cast<const float4*>(own_p + (d * NG + q) * 128);
+                                    xb[q] = *reinterpret_cast<const float4*>(oth_p + (d * NG + q) * 128);
+                                }
+                                const unsigned u0 = (unsigned)my_idx[it + d + D], u1 = (unsigned)my_idx[it + d + 1 + D];
+                                float acc0[HP], acc1[HP];
 #pragma unroll
-                        for (int q = 0; q < NG; ++q)   // groups past ngv: stale finite values times dT == 0
-                            xn[q] = *reinterpret_cast<const float4*>(my_ring_p + (((d + 1) % D) * NG + q) * 128);
-                        const unsigned un = (unsigned)my_idx[it + d + D];   // read early; past the list it is unused
-                        if (it + d < cmax) {   // warp-uniform: the shuffles below need every lane
-                            const bool act = it + d < clen;
-                            float part[HP];
-#pragma unroll
-                            for (int h = 0; h < HP; ++h) part[h] = 0.f;
-                            if (act) {
+                                for (int h = 0; h < HP; ++h) acc0[h] = 0.f, acc1[h] = 0.f;
 #pragma unroll
                                 for (int q = 0; q < NG; ++q) {
-                                    const float f[4] = {xc[q].x, xc[q].y, xc[q].z, xc[q].w};
+                                    const float fa[4] = {xa[q].x, xa[q].y, xa[q].z, xa[q].w};
+                                    const float fb[4] = {xb[q].x, xb[q].y, xb[q].z, xb[q].w};
 #pragma unroll
                                     for (int e = 0; e < 4; ++e)
 #pragma unroll
-                                        for (int h = 0; h < HP; h += 2)   // dT comes out of tcgen05.ld with h in adjacent registers
-                                            tc::fma2(part[h], part[h + 1], dT[4 * q + e][h], dT[4 * q + e][h + 1], f[e], f[e]);
+                                        for (int h = 0; h < HP; h += 2) {
+                                            tc::fma2(acc0[h], acc0[h + 1], dT[4 * q + e][h], dT[4 * q + e][h + 1], fa[e], fa[e]);
+                                            tc::fma2(acc1[h], acc1[h + 1], dT[4 * q + e][h], dT[4 * q + e][h + 1], fb[e], fb[e]);
+                                        }
                                 }
-                            }
-                            // reduce over the batch lanes of the sub-group (transposed butterfly)
 #pragma unroll
-                            for (int st = 0; st < LB; ++st) {
-                                const int mask = 1 << (LB - 1 - st);
-                                if (st < NH) {
-                                    const int half = HP >> (st + 1);
+                                for (int k = 0; k < HP; ++k) acc0[k] += __shfl_xor_sync(0xffffffffu, acc1[k], 16);
 #pragma unroll
-                                    for (int k = 0; k < half; ++k)
-                                        part[k] += __shfl_xor_sync(0xffffffffu, part[k + half], mask);
-                                } else {
-                                    part[0] += __shfl_xor_sync(0xffffffffu, part[0], mask);
+                                for (int st = 0; st < LBr; ++st) {
+                                    const int mask = 1 << (LBr - 1 - st);
+                                    if (st < NH) {
+                                        const int half = HP >> (st + 1);
+#pragma unroll
+                                        for (int k = 0; k < half; ++k)
+                                            acc0[k] += __shfl_xor_sync(0xffffffffu, acc0[k + half], mask);
+                                    } else {
+                                        acc0[0] += __shfl_xor_sync(0xffffffffu, acc0[0], mask);
+                                    }
                                 }
+                                if (writer && it + d + up < clen)
+                                    a.dphi[(size_t)(blk * nkc + kc) * slice_stride + (size_t)(beg + c0 + it + d + up) * HP + hsel] = acc0[0];
+                                if (it + d + D < clen) issue_u(d, u0);
+                                tc::cp_async_commit();
+                                if (it + d + 1 + D < clen) issue_u(d + 1, u1);
+                                tc::cp_async_commit();
+                            } else {
+                                tc::cp_async_commit();
+                                tc::cp_async_commit();
                             }
-                            if (act && writer) {
-                                float* dst = a.dphi + (size_t)(blk * nkc + kc) * slice_stride +
-                                             (size_t)(beg + c0 + it + d) * HP + hsel * NF;
-#pragma unroll
-                                for (int k = 0; k < NF; ++k) dst[k] = part[k];
-                            }
-                            if (it + d + D < clen) issue_u(d, un);
                         }
-                        tc::cp_async_commit();
-#pragma unroll
-                        for (int q = 0; q < NG; ++q) xc[q] = xn[q];
+                    }
+                } else {
+                    // software pipeline: pair n+1 moves shared -> registers under the dot products of pair n
+                    float4 xc[NG], xn[NG];
+                    tc::cp_async_wait<D - 1>();
+    #pragma unroll
+                    for (int q = 0; q < NG; ++q) xc[q] = *reinterpret_cast<const float4*>(my_ring_p + q * 128);
+                    for (int it = 0; it < cmax; it += D) {
+    #pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            tc::cp_async_wait<D - 2>();
+    #pragma unroll
+                            for (int q = 0; q < NG; ++q)   // groups past ngv: stale finite values times dT == 0
+                                xn[q] = *reinterpret_cast<const float4*>(my_ring_p + (((d + 1) % D) * NG + q) * 128);
+                            const unsigned un = (unsigned)my_idx[it + d + D];   // read early; past the list it is unused
+                            if (it + d < cmax) {   // warp-uniform: the shuffles below need every lane
+                                const bool act = it + d < clen;
+                                float part[HP];
+    #pragma unroll
+                                for (int h = 0; h < HP; ++h) part[h] = 0.f;
+                                if (act) {
+    #pragma unroll
+                                    for (int q = 0; q < NG; ++q) {
+                                        const float f[4] = {xc[q].x, xc[q].y, xc[q].z, xc[q].w};
+    #pragma unroll
+                                        for (int e = 0; e < 4; ++e)
+    #pragma unroll
+                                            for (int h = 0; h < HP; h += 2)   // dT comes out of tcgen05.ld with h in adjacent registers
+                                                tc::fma2(part[h], part[h + 1], dT[4 * q + e][h], dT[4 * q + e][h + 1], f[e], f[e]);
+                                    }
+                                }
+                                // reduce over the batch lanes of the sub-group (transposed butterfly)
+    #pragma unroll
+                                for (int st = 0; st < LB; ++st) {
+                                    const int mask = 1 << (LB - 1 - st);
+                                    if (st < NH) {
+                                        const int half = HP >> (st + 1);
+    #pragma unroll
+                                        for (int k = 0; k < half; ++k)
+                                            part[k] += __shfl_xor_sync(0xffffffffu, part[k + half], mask);
+                                    } else {
+                                        part[0] += __shfl_xor_sync(0xffffffffu, part[0], mask);
+                                    }
+                                }
+                                if (act && writer) {
+                                    float* dst = a.dphi + (size_t)(blk * nkc + kc) * slice_stride +
+                                                 (size_t)(beg + c0 + it + d) * HP + hsel * NF;
+    #pragma unroll
+                                    for (int k = 0; k < NF; ++k) dst[k] = part[k];
+                                }
+                                if (it + d + D < clen) issue_u(d, un);
+                            }
+                            tc::cp_async_commit();
+    #pragma unroll
+                            for (int q = 0; q < NG; ++q) xc[q] = xn[q];
+                        }
                     }
                 }
             }
