@@ -4,55 +4,111 @@
 // repacks of the last filter-MLP layer.  Pure HBM-bound copies: every global access is a full
 // 32-float (128 B) segment on one side and a Bp-float segment on the other, staged through a
 // padded shared-memory tile.
+#include <cstdint>
 #include "common.cuh"
 
 namespace {
 
-// grid: (ceil(N/32), CP4/4, nblk); block 256 = 8 warps.  Tile: 32 points x 4 channels x Bp lanes.
+// grid: (ceil(N/64), CP4/4, nblk); block 256.  Tile: 64 points x 4 channels x Bp batch lanes, held as
+// 4*Bp rows of 64 points with an odd row stride (65): the [B,C,N] side moves whole 256-byte row pieces
+// as float4 per lane (VEC: every row start is 16-byte aligned, i.e. N % 4 == 0), the packed side moves
+// 16 bytes per lane = the 4 channels of one (point, batch lane), 512 contiguous bytes per warp.
+constexpr int PT = 64, RS = 65;
+
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_pack(const float* __restrict__ x, int B, int C, int N, int Bp, float* __restrict__ xp)
 {
-    __shared__ float tile[4][32 * 33 + 8];  // [channel in group][batch lane * 33 + point]; +8: the 4 planes hit distinct banks
-    const int n0 = blockIdx.x * 32, cg = blockIdx.y, blk = blockIdx.z;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __shared__ float tile[4 * 32 * RS];   // [(channel in group) * Bp + batch lane][point]
+    const int n0 = blockIdx.x * PT, cg = blockIdx.y, blk = blockIdx.z;
     const int CG = gridDim.y;
-    for (int r = w; r < 4 * Bp; r += 8) {
-        const int e = r / Bp, bl = r % Bp;
-        const int c = cg * 4 + e, b = blk * 32 + bl, n = n0 + lane;
-        float v = 0.f;
-        if (c < C && b < B && n < N) v = x[((size_t)b * C + c) * N + n];
-        tile[e][bl * 33 + lane] = v;
+    const int rows = 4 * Bp;
+    if (VEC) {
+        const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;   // half-warp per row, float4 per lane
+        const int n = n0 + hl * 4;
+        for (int r = hw; r < rows; r += 16) {
+            const int e = r / Bp, bl = r % Bp;
+            const int c = cg * 4 + e, b = blk * 32 + bl;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < C && b < B && n < N) v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)b * C + c) * N + n));
+            float* t = tile + r * RS + hl * 4;
+            t[0] = v.x, t[1] = v.y, t[2] = v.z, t[3] = v.w;
+        }
+    } else {
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int r = w; r < rows; r += 8) {
+            const int e = r / Bp, bl = r % Bp;
+            const int c = cg * 4 + e, b = blk * 32 + bl;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int n = n0 + half * 32 + lane;
+                float v = 0.f;
+                if (c < C && b < B && n < N) v = x[((size_t)b * C + c) * N + n];
+                tile[r * RS + half * 32 + lane] = v;
+            }
+        }
     }
     __syncthreads();
-    // write: per point Bp*4 contiguous floats, (lane, channel-in-group) innermost
-    for (int idx = threadIdx.x; idx < 32 * Bp * 4; idx += 256) {
-        const int e = idx & 3, bl = (idx >> 2) % Bp, nl = (idx >> 2) / Bp;
+    for (int idx = threadIdx.x; idx < PT * Bp; idx += 256) {
+        const int bl = idx % Bp, nl = idx / Bp;
         const int n = n0 + nl;
-        if (n < N) xp[((((size_t)blk * N + n) * CG + cg) * Bp + bl) * 4 + e] = tile[e][bl * 33 + nl];
+        if (n < N) {
+            const float4 v = make_float4(tile[(0 * Bp + bl) * RS + nl], tile[(1 * Bp + bl) * RS + nl],
+                                         tile[(2 * Bp + bl) * RS + nl], tile[(3 * Bp + bl) * RS + nl]);
+            *reinterpret_cast<float4*>(xp + ((((size_t)blk * N + n) * CG + cg) * Bp + bl) * 4) = v;
+        }
     }
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_unpack(const float* __restrict__ xp, int B, int C, int N, int Bp, const float* __restrict__ bias,
          float* __restrict__ x)
 {
-    __shared__ float tile[4][32 * 33 + 8];
-    const int n0 = blockIdx.x * 32, cg = blockIdx.y, blk = blockIdx.z;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __shared__ float tile[4 * 32 * RS];
+    const int n0 = blockIdx.x * PT, cg = blockIdx.y, blk = blockIdx.z;
     const int CG = gridDim.y;
-    for (int idx = threadIdx.x; idx < 32 * Bp * 4; idx += 256) {
-        const int e = idx & 3, bl = (idx >> 2) % Bp, nl = (idx >> 2) / Bp;
+    const int rows = 4 * Bp;
+    for (int idx = threadIdx.x; idx < PT * Bp; idx += 256) {
+        const int bl = idx % Bp, nl = idx / Bp;
         const int n = n0 + nl;
-        tile[e][bl * 33 + nl] = n < N ? xp[((((size_t)blk * N + n) * CG + cg) * Bp + bl) * 4 + e] : 0.f;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < N) v = __ldg(reinterpret_cast<const float4*>(xp + ((((size_t)blk * N + n) * CG + cg) * Bp + bl) * 4));
+        tile[(0 * Bp + bl) * RS + nl] = v.x;
+        tile[(1 * Bp + bl) * RS + nl] = v.y;
+        tile[(2 * Bp + bl) * RS + nl] = v.z;
+        tile[(3 * Bp + bl) * RS + nl] = v.w;
     }
     __syncthreads();
-    const int n = n0 + lane;
-    for (int r = w; r < 4 * Bp; r += 8) {
-        const int e = r / Bp, bl = r % Bp;
-        const int c = cg * 4 + e, b = blk * 32 + bl;
-        if (c < C && b < B && n < N) {
-            const float bv = bias != nullptr ? bias[(size_t)c * N + n] : 0.f;
-            x[((size_t)b * C + c) * N + n] = tile[e][bl * 33 + lane] + bv;
+    if (VEC) {
+        const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
+        const int n = n0 + hl * 4;
+        for (int r = hw; r < rows; r += 16) {
+            const int e = r / Bp, bl = r % Bp;
+            const int c = cg * 4 + e, b = blk * 32 + bl;
+            if (c < C && b < B && n < N) {
+                const float* t = tile + r * RS + hl * 4;
+                float4 v = make_float4(t[0], t[1], t[2], t[3]);
+                if (bias != nullptr) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + (size_t)c * N + n));
+                    v.x += bv.x, v.y += bv.y, v.z += bv.z, v.w += bv.w;
+                }
+                *reinterpret_cast<float4*>(x + ((size_t)b * C + c) * N + n) = v;
+            }
+        }
+    } else {
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int r = w; r < rows; r += 8) {
+            const int e = r / Bp, bl = r % Bp;
+            const int c = cg * 4 + e, b = blk * 32 + bl;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int n = n0 + half * 32 + lane;
+                if (c < C && b < B && n < N) {
+                    const float bv = bias != nullptr ? bias[(size_t)c * N + n] : 0.f;
+                    x[((size_t)b * C + c) * N + n] = tile[r * RS + half * 32 + lane] + bv;
+                }
+            }
         }
     }
 }
@@ -105,8 +161,11 @@ extern "C" {
 int qc_pack_features(const float* x, int B, int C, int N, float* xp, void* stream)
 {
     if (B <= 0 || C <= 0 || N <= 0 || C > 4 * 65535) return QC_EINVAL;
-    dim3 grid(qc_ceil_div(N, 32), qc_cp4(C) / 4, qc_nblk(B));
-    k_pack<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, C, N, qc_bp(B), xp);
+    dim3 grid(qc_ceil_div(N, PT), qc_cp4(C) / 4, qc_nblk(B));
+    if (N % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+        k_pack<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, C, N, qc_bp(B), xp);
+    else
+        k_pack<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, C, N, qc_bp(B), xp);
     QC_CHECK_LAUNCH();
     return 0;
 }
@@ -114,8 +173,13 @@ int qc_pack_features(const float* x, int B, int C, int N, float* xp, void* strea
 int qc_unpack_features(const float* xp, int B, int C, int N, const float* bias, float* x, void* stream)
 {
     if (B <= 0 || C <= 0 || N <= 0 || C > 4 * 65535) return QC_EINVAL;
-    dim3 grid(qc_ceil_div(N, 32), qc_cp4(C) / 4, qc_nblk(B));
-    k_unpack<<<grid, 256, 0, (cudaStream_t)stream>>>(xp, B, C, N, qc_bp(B), bias, x);
+    dim3 grid(qc_ceil_div(N, PT), qc_cp4(C) / 4, qc_nblk(B));
+    const bool vec = N % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                     (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+    if (vec)
+        k_unpack<true><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, B, C, N, qc_bp(B), bias, x);
+    else
+        k_unpack<false><<<grid, 256, 0, (cudaStream_t)stream>>>(xp, B, C, N, qc_bp(B), bias, x);
     QC_CHECK_LAUNCH();
     return 0;
 }
