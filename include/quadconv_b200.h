@@ -152,6 +152,23 @@ int qc_dphi(const float* Xp, int Nsrc, int Cx, const float* Gp, int Cg, const in
             const int* src_idx, const float* W3, int H, int HP, const int* order, int Ndst, int B,
             int64_t P, float* dphi, void* stream);
 
+/* Wide layers (last hidden width H > 8, or more than 32 channels on the dense side): the same
+ * factorised evaluation of quadconv.py:213-227 with the intermediate written to HBM once, so that the
+ * dense stage is a plain row-major GEMM done by the caller (cuBLAS / torch.matmul in fp32):
+ *     T[b][t][c*H + h]   = sum_{q in S(t)} phi[phi_idx[q]][h] * Xp[src_idx[q]][c][b]     (accumulate)
+ *     Y[b][t][:]         = T[b][t][:] * W2            W2[(c*H+h)][j] = W_last[c*Co+j][h]
+ * and, backward, dT = G * W2^T followed by
+ *     dphi[s][q][h]      = sum_{b,c in slice s} Xp[src_idx[q]][c][b] * dT[b][t][c*H + h]  (dot)
+ * T / dT are [B][Ndst][Cx*H] floats, unpadded.  dphi is [qc_gather_dot_num_slices][P][HP] (one slice per
+ * block of 32 batch entries, no initialisation needed; summed by qc_pair_phi_bwd).  qc_gather_supported returns 1 when the shape is handled. */
+int qc_gather_supported(int Cx, int H, int HP, int B);
+int qc_gather_dot_num_slices(int Cx, int HP, int B);
+int qc_gather_accumulate(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, const int* src_idx,
+                         const int* phi_idx, const float* phi, int H, int HP, const int* order, int Ndst,
+                         int B, float* T, void* stream);
+int qc_gather_dot(const float* Xp, int Nsrc, int Cx, const float* dT, const int* seg_ptr, const int* src_idx,
+                  int H, int HP, const int* order, int Ndst, int B, int64_t P, float* dphi, void* stream);
+
 /* Repack the last Linear weight W_last [Ci*Co][H] (filter.{2L}.weight, quadconv.py:143):
  *   mode 0: W2[(i*H+h)*CoP + j]  (forward)        mode 1: W2[(j*H+h)*CiP + i]  (d features)
  *   mode 2: W3[(j*Ci+i)*HP + h]  (d phi)

@@ -51,6 +51,12 @@ _SIGNATURES = {
     "qc_dphi_num_slices": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "qc_dphi": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                         c_int, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),
+    "qc_gather_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "qc_gather_dot_num_slices": (c_int, [c_int, c_int, c_int]),
+    "qc_gather_accumulate": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                     c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "qc_gather_dot": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                              c_int, c_int64, c_void_p, c_void_p]),
     "qc_repack_wlast": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qc_unpack_dwlast": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qc_segmax_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -12,6 +12,8 @@ FLOP of the path runs in libquadconv_b200.so.  Ops (namespace `quadconv_b200`):
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -171,6 +173,34 @@ def _unpack(xp: Tensor, B: int, Cc: int, N: int, bias: Optional[Tensor]) -> Tens
     return x
 
 
+_WIDE_MAX_BYTES = 16 << 30   # largest materialised intermediate the wide path may allocate
+
+
+def _use_wide(Ci: int, Co: int, H: int, HP: int, B: int, n_rows: int) -> bool:
+    """Wide layers (H > 8 or more than 32 channels on a dense side) do not fit the fused tcgen05
+    kernels' shared-memory / TMEM budget: their gather stages run as qc_gather_accumulate /
+    qc_gather_dot with the intermediate T in HBM and the dense stage as fp32 GEMMs (csrc/contract_wide.cu)."""
+    if os.environ.get("QC_NO_WIDE"):
+        return False
+    if HP <= 8 and max(Ci, Co) <= 32:
+        return False
+    L = C.lib()
+    if not (L.qc_gather_supported(Ci, H, HP, B) and L.qc_gather_supported(Co, H, HP, B)):
+        return False
+    return B * n_rows * max(Ci, Co) * H * 4 <= _WIDE_MAX_BYTES
+
+
+class _fp32_matmul:
+    """The dense stage of the wide path must be a true fp32 GEMM (1e-5 parity bound)."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
 @torch.library.custom_op("quadconv_b200::qc_forward", mutates_args=())
 def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor,
                hidden_ws: Sequence[Tensor], w_last: Tensor, bias: Optional[Tensor],
@@ -199,6 +229,16 @@ def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor
     C.check(L.qc_pair_phi_fwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row), C.ptr(pair_col),
                               P, d, mlp, HP, C.ptr(phi), st), "qc_pair_phi_fwd")
     xp = _pack(features)
+    if P > 0 and _use_wide(Ci, Co, H, HP, B, max(No, Ni)):
+        T = torch.empty((B, No, Ci * H), dtype=torch.float32, device=dev)
+        C.check(L.qc_gather_accumulate(C.ptr(xp), Ni, Ci, C.ptr(row_ptr), C.ptr(pair_col), None, C.ptr(phi), H, HP,
+                                       C.ptr(order_out), No, B, C.ptr(T), st), "qc_gather_accumulate")
+        W2 = w_last.view(Ci, Co, H).permute(0, 2, 1).reshape(Ci * H, Co)      # [(i,h), j]
+        with _fp32_matmul():
+            out = torch.matmul(W2.t(), T.transpose(1, 2))                     # [B, Co, No]
+        if bias is not None:
+            out = out + _f32c(bias, "bias").reshape(1, Co, No)
+        return out.contiguous(), phi, xp
     CoP = (Co + 3) & ~3
     W2 = torch.empty((Ci * H, CoP), dtype=torch.float32, device=dev)
     C.check(L.qc_repack_wlast(C.ptr(w_last), Ci, Co, H, HP, 0, C.ptr(W2), st), "qc_repack_wlast")
@@ -247,6 +287,38 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
     if has_bias:
         d_bias = torch.empty((1, Co, No), **f32)
         C.check(L.qc_batch_sum(C.ptr(grad_out), B, Co, No, C.ptr(d_bias), st), "qc_batch_sum")
+
+    if P > 0 and _use_wide(Ci, Co, H, HP, B, max(No, Ni)):
+        wl = w_last.view(Ci, Co, H)
+        with _fp32_matmul():
+            # d phi: dT = G * W2^T as a GEMM, then the per-pair dots against the gathered features
+            W2 = wl.permute(0, 2, 1).reshape(Ci * H, Co)
+            dT = torch.matmul(grad_out.transpose(1, 2), W2.t())               # [B, No, Ci*H]
+            nsl = L.qc_gather_dot_num_slices(Ci, HP, B)
+            dphi = torch.empty((nsl, P, HP), **f32)
+            C.check(L.qc_gather_dot(C.ptr(xp), Ni, Ci, C.ptr(dT), C.ptr(row_ptr), C.ptr(pair_col), H, HP,
+                                    C.ptr(order_out), No, B, P, C.ptr(dphi), st), "qc_gather_dot")
+            del dT
+            d_hidden = [torch.zeros_like(w) for w in hidden_ws]
+            d_quad_w = torch.zeros(Ni, **f32)
+            mlp = C.make_mlp(d, hidden_ws)
+            import ctypes
+            dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
+            C.check(L.qc_pair_phi_bwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row),
+                                      C.ptr(pair_col), P, d, mlp, HP, C.ptr(dphi), nsl, dptrs, C.ptr(d_quad_w), st),
+                    "qc_pair_phi_bwd")
+            del dphi
+            # d features and d W_last from T'[b][n][(j,h)] = sum_p phi[p][h] G[out(p)][b][j] (CSC view)
+            Tp = torch.empty((B, Ni, Co * H), **f32)
+            C.check(L.qc_gather_accumulate(C.ptr(gp), No, Co, C.ptr(csc_ptr), C.ptr(csc_row), C.ptr(csc_pair),
+                                           C.ptr(phi), H, HP, C.ptr(order_in), Ni, B, C.ptr(Tp), st),
+                    "qc_gather_accumulate (backward)")
+            W2t = wl.permute(1, 2, 0).reshape(Co * H, Ci)                     # [(j,h), i]
+            d_features = torch.matmul(W2t.t(), Tp.transpose(1, 2)).contiguous()   # [B, Ci, Ni]
+            x = _unpack(xp, B, Ci, Ni, None)
+            dWt = torch.matmul(x.permute(1, 0, 2).reshape(Ci, B * Ni), Tp.reshape(B * Ni, Co * H))   # [i, (j,h)]
+            d_w_last = dWt.reshape(Ci * Co, H)
+        return [d_features, d_quad_w, d_w_last, d_bias] + d_hidden
 
     # d phi (grouped by out point), then back through the hidden layers per pair
     W3 = torch.empty((Co, Ci, HP), **f32)

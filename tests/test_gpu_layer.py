@@ -133,6 +133,12 @@ class _StubMesh:
     (2, 1200, 8, 8, 8, [8, 8], 0.012, True, 500),      # tensor-core path, tiny radius: most out points have NO pair
     (3, 2000, 32, 32, 32, [8, 8], 0.05, False, None),  # tensor-core path, ~1 pair/point (self pairs), 3 row blocks
     (2, 50, 8, 8, 32, [8, 8], 0.3, False, None),       # fewer points than one CTA tile
+    (2, 500, 64, 40, 8, [32, 32], 0.15, False, None),  # wide path (C4-like): H = 32, batch 8, > 32 channels
+    (2, 400, 12, 36, 32, [16], 0.12, True, 150),       # wide path: H = 16, batch 32, cross-level, bias
+    (3, 600, 8, 8, 6, [20], 0.2, False, None),         # wide path: H = 20 padded to 32, batch 6 -> 8 lanes
+    (2, 300, 5, 34, 7, [10], 0.15, True, None),        # wide path: H = 10 (scalar row pieces), odd channels
+    (2, 700, 40, 8, 32, [8, 8], 0.3, False, None),     # wide path with H = 8 (Ci > 32), > 64 pairs per point
+    (2, 450, 36, 4, 70, [4], 0.1, False, None),        # wide path with H = 4, three batch blocks
 ])
 def test_layer_matches_oracle(cuda_lib, d, n, ci, co, B, fs, r, bias, n_out):
     import pytorch_quadconv_b200 as q
