@@ -68,7 +68,8 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     uint64_t* opbar = reinterpret_cast<uint64_t*>(opbuf + OPBUF_BYTES / 4);
     int* lockw = reinterpret_cast<int*>(opbar + 1);                // [0] lock, [1] commits so far, [2+kc] touched
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // broadcast: the compiler then knows it is warp-uniform
     const int rb = warp >> 2;                                      // 128-row block of this warp
     const int s = lane >> LB, b = lane & (Bp - 1);
     const int blk = blockIdx.y;
@@ -440,7 +441,8 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 4);
     float* ring_s = reinterpret_cast<float*>(bars + 8);                   // [NW warps][RING bytes]
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // broadcast: the compiler then knows it is warp-uniform
     const int rb = warp >> 2;
     const int s = lane >> LB, b = lane & (Bp - 1);
     const int blk = blockIdx.y;

@@ -69,7 +69,8 @@ k_gather_acc(const WideArgs a)
     int* idx_s = reinterpret_cast<int*>(phi_s + NW * PHS);       // [NW][IDS]
     float* ring_s = reinterpret_cast<float*>(idx_s + NW * IDS);  // [NW][RING bytes]
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // broadcast: the compiler then knows it is warp-uniform
     const int g = lane >> LB, b = lane & (Bp - 1);
     const int blk = blockIdx.y;
     const int bglob = blk * 32 + b;
@@ -232,7 +233,8 @@ k_gather_dot(const WideArgs a, const size_t slice_stride)
     int* idx_s = reinterpret_cast<int*>(smem);                     // [NW][IDS]
     float* ring_s = reinterpret_cast<float*>(idx_s + NW * IDS);    // [NW][RING bytes]
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // broadcast: the compiler then knows it is warp-uniform
     const int g = lane >> LB, b = lane & (Bp - 1);
     const int blk = blockIdx.y;
     const int bglob = blk * 32 + b;
