@@ -143,6 +143,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
             const float* Xc = Xb + (size_t)(cx0 >> 2) * (Bp * 4);
             float* my_phi = phi_s + (warp * PPW + s) * PHS;
             int* my_idx = idx_s + (warp * PPW + s) * PCH;
+            const uint32_t my_idx_sa = tc::smem_u32(my_idx);
             // gathers go global -> shared asynchronously (cp.async, one commit group per pair) into a
             // per-warp ring; each lane copies and later reads back only its own 16 bytes per group
             const uint32_t my_ring = tc::smem_u32(ring_s) + warp * RING + lane * 16;
@@ -206,7 +207,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                     for (int d = 0; d < D; ++d) {
                         tc::cp_async_wait<D - 2>();       // the group of pair it+d+1 (slot d+1) has landed
                         load(nxt, (d + 1) % D, it + d + 1);
-                        const unsigned un = (unsigned)my_idx[it + d + D];   // read early; past the list it is unused
+                        const unsigned un = tc::lds_u32_early(my_idx_sa + (it + d + D) * 4);   // past the list it is unused
                         if (it + d < clen) {
                             fma(cur);
                             if (it + d + D < clen) issue_u(d, un);
@@ -596,6 +597,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
 
             const float* Xc = Xb + (size_t)(cx0 >> 2) * (Bp * 4);
             int* my_idx = idx_s + (warp * PPW + s) * PCH;
+            const uint32_t my_idx_sa = tc::smem_u32(my_idx);
             const uint32_t my_ring = tc::smem_u32(ring_s) + warp * RING + lane * 16;
             const float* my_ring_p = ring_s + (warp * RING + lane * 16) / 4;
             auto issue_u = [&](int slot, unsigned u) {
@@ -633,7 +635,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                                     xa[q] = *reinterpret_cast<const float4*>(own_p + (d * NG + q) * 128);
                                     xb[q] = *reinterpret_cast<const float4*>(oth_p + (d * NG + q) * 128);
                                 }
-                                const unsigned u0 = (unsigned)my_idx[it + d + D], u1 = (unsigned)my_idx[it + d + 1 + D];
+                                const unsigned u0 = tc::lds_u32_early(my_idx_sa + (it + d + D) * 4), u1 = tc::lds_u32_early(my_idx_sa + (it + d + 1 + D) * 4);
                                 float acc0[HP], acc1[HP];
 #pragma unroll
                                 for (int h = 0; h < HP; ++h) acc0[h] = 0.f, acc1[h] = 0.f;

@@ -86,6 +86,7 @@ k_gather_acc(const WideArgs a)
 
     float* my_phi = phi_s + warp * PHS;
     int* my_idx = idx_s + warp * IDS;
+    const uint32_t my_idx_sa = tc::smem_u32(my_idx);
     const uint32_t my_ring = tc::smem_u32(ring_s) + warp * RING + lane * 16;
     const float* my_ring_p = ring_s + (warp * RING + lane * 16) / 4;
 
@@ -170,7 +171,7 @@ k_gather_acc(const WideArgs a)
                         for (int d = 0; d < D; ++d) {
                             tc::cp_async_wait<D - 2>();
                             load(nxt, (d + 1) % D, min(it + d + 1, PCH - 1));
-                            const unsigned un = (unsigned)my_idx[it + d + D];
+                            const unsigned un = tc::lds_u32_early(my_idx_sa + (it + d + D) * 4);
                             if (it + d < clen) {
                                 fma(cur);
                                 if (it + d + D < clen) issue_u(d, un);
@@ -253,6 +254,7 @@ k_gather_dot(const WideArgs a, const size_t slice_stride)
     __syncthreads();
 
     int* my_idx = idx_s + warp * IDS;
+    const uint32_t my_idx_sa = tc::smem_u32(my_idx);
     const uint32_t my_ring = tc::smem_u32(ring_s) + warp * RING + lane * 16;
     const float* my_ring_p = ring_s + (warp * RING + lane * 16) / 4;
     const float* own_p = my_ring_p + up * (NG * 128);
@@ -346,7 +348,7 @@ k_gather_dot(const WideArgs a, const size_t slice_stride)
                                     xa[q] = *reinterpret_cast<const float4*>(own_p + (d * NG + q) * 128);
                                     xb[q] = *reinterpret_cast<const float4*>(oth_p + (d * NG + q) * 128);
                                 }
-                                const unsigned u0 = (unsigned)my_idx[it + d + D], u1 = (unsigned)my_idx[it + d + 1 + D];
+                                const unsigned u0 = tc::lds_u32_early(my_idx_sa + (it + d + D) * 4), u1 = tc::lds_u32_early(my_idx_sa + (it + d + 1 + D) * 4);
                                 const bool wr = writer && it + d + up < clen;
                                 float* dst = dslice + (size_t)(beg + c0 + it + d + up) * a.HP + hh * HC + hsel;
                                 const float old = (wr && !first) ? *dst : 0.f;

@@ -140,6 +140,14 @@ __device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, f
         : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+// Shared-memory load the compiler may not sink to its use (used to start a dependent address chain early).
+__device__ __forceinline__ uint32_t lds_u32_early(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
