@@ -183,16 +183,20 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
             for (int c0 = 0; c0 < maxlen; c0 += PCH) {
                 const int clen = min(PCH, len - c0);
                 const int cmax = min(PCH, maxlen - c0);
-                __syncwarp();
-                for (int e = b; e < clen; e += Bp) {
-                    const int p = c0 + e;
-                    my_idx[e] = sidx[p];
-                    const int pp = pidx ? pidx[p] : beg + p;
-                    const float4* php = reinterpret_cast<const float4*>(a.phi + (size_t)pp * HP);
+                // pair indices and phi rows of this piece of the segment; a segment that fits in one piece
+                // (the usual case) is staged once per tile and reused by every channel chunk
+                if (kc == 0 || maxlen > PCH) {
+                    __syncwarp();
+                    for (int e = b; e < clen; e += Bp) {
+                        const int p = c0 + e;
+                        my_idx[e] = sidx[p];
+                        const int pp = pidx ? pidx[p] : beg + p;
+                        const float4* php = reinterpret_cast<const float4*>(a.phi + (size_t)pp * HP);
 #pragma unroll
-                    for (int q = 0; q < HQ; ++q) reinterpret_cast<float4*>(my_phi + e * HP)[q] = __ldg(php + q);
+                        for (int q = 0; q < HQ; ++q) reinterpret_cast<float4*>(my_phi + e * HP)[q] = __ldg(php + q);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     if (d < clen) issue(d, d);
@@ -610,9 +614,11 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
             for (int c0 = 0; c0 < maxlen; c0 += PCH) {
                 const int clen = min(PCH, len - c0);
                 const int cmax = min(PCH, maxlen - c0);
-                __syncwarp();
-                for (int e = b; e < clen; e += Bp) my_idx[e] = sidx[c0 + e];
-                __syncwarp();
+                if (kc == 0 || maxlen > PCH) {   // a segment that fits in one piece is staged once per tile
+                    __syncwarp();
+                    for (int e = b; e < clen; e += Bp) my_idx[e] = sidx[c0 + e];
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     if (d < clen) issue(d, d);
