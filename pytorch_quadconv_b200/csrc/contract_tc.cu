@@ -222,6 +222,16 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                 }
             }
 
+            // DW: this row of Z, fetched now so that its latency is not paid while holding the operand buffer
+            float4 zrow[DW ? 8 : 1];
+            if (DW) {
+                const float* zg = a.Z + ((size_t)blk * a.Ndst + (pvalid ? dstp : 0)) * yrow + b * 4;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    zrow[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (pvalid && 4 * q < a.Cy) zrow[q] = __ldg(reinterpret_cast<const float4*>(zg + (size_t)q * Bp * 4));
+                }
+            }
             // ---- stage C on the tensor cores: T (hi/lo) -> TMEM, 3xTF32 MMAs into D ---------------
             if (g > 0) {
                 tc::mbar_wait(&bars[rb], (g - 1) & 1);   // previous group has finished reading A
@@ -266,12 +276,9 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                     Ahi[op_off_words(k, r)] = hv;
                     Alo[op_off_words(k, r)] = v - hv;
                 }
-                const float* zg = a.Z + ((size_t)blk * a.Ndst + (pvalid ? dstp : 0)) * yrow + b * 4;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (pvalid && 4 * q < a.Cy) zv = __ldg(reinterpret_cast<const float4*>(zg + (size_t)q * Bp * 4));
-                    const float z4[4] = {zv.x, zv.y, zv.z, zv.w};
+                    const float z4[4] = {zrow[q].x, zrow[q].y, zrow[q].z, zrow[q].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float hv = __uint_as_float(__float_as_uint(z4[e]) & 0xffffe000u);
