@@ -78,7 +78,10 @@ k_pair_phi_fwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
 // Backward.  Block = 128 pairs per sweep.  Per layer the block stages (da, x) of its pairs in
 // shared memory and every thread owns a fixed set of dW[o][k] entries, so the weight gradient is
 // reduced without atomics inside the block; one atomicAdd per entry per block at the end.
-template <int WMAX>
+// LT > 0: the number of hidden layers is a compile-time constant, so the per-layer activations and
+// cosines live in registers (with a runtime layer count they are dynamically indexed and ptxas puts
+// them in local memory); LT == 0 is the general version.
+template <int WMAX, int LT>
 __global__ void __launch_bounds__(128)
 k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_pts,
                const float* __restrict__ quad_w, const int* __restrict__ pair_row,
@@ -95,14 +98,15 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
     for (int t = threadIdx.x; t < m.n_hidden * WMAX * WMAX; t += NT) dWs[t] = 0.f;
     __syncthreads();
     const int H = m.dims[m.n_hidden];
-    const int L = m.n_hidden;
+    constexpr int LMAX = LT > 0 ? LT : QC_MAX_MLP_LAYERS;
+    const int L = LT > 0 ? LT : m.n_hidden;
 
     for (int64_t base = (int64_t)blockIdx.x * NT; base < P; base += (int64_t)gridDim.x * NT) {
         const int64_t p = base + threadIdx.x;
         const bool valid = p < P;
         // forward recompute, keeping every layer input and the cosine of every pre-activation
-        float xs[QC_MAX_MLP_LAYERS + 1][WMAX];
-        float cs[QC_MAX_MLP_LAYERS][WMAX];
+        float xs[LMAX + 1][WMAX];
+        float cs[LMAX][WMAX];
         int r = 0, c = 0;
         if (valid) {
             r = pair_row[p];
@@ -115,7 +119,9 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
             for (int k = 0; k < 3; ++k)
                 if (k < d && k < WMAX) xs[0][k] = __fsub_rn(out_pts[(size_t)r * d + k], in_pts[(size_t)c * d + k]);
         }
-        for (int l = 0; l < L; ++l) {
+#pragma unroll(LT > 0 ? LMAX : 1)
+        for (int l = 0; l < LMAX; ++l) {
+            if (l >= L) break;
             const float* W = Wsm + l * WMAX * WMAX;
 #pragma unroll
             for (int o = 0; o < WMAX; ++o) {
@@ -136,12 +142,14 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
             float g = 0.f;
             if (valid && h < H && h < HP)
                 for (int sl = 0; sl < nslices; ++sl) g += dphi[((size_t)sl * P + p) * HP + h];
-            dwq = fmaf(g, xs[L][h], dwq);
+            dwq = fmaf(g, LT > 0 ? xs[LT][h] : xs[L][h], dwq);
             dx[h] = wq * g;
         }
         if (valid && d_quad_w) atomicAdd(&d_quad_w[c], dwq);
 
-        for (int l = L - 1; l >= 0; --l) {
+#pragma unroll(LT > 0 ? LMAX : 1)
+        for (int l = LMAX - 1; l >= 0; --l) {
+            if (l >= L) continue;
             const float* W = Wsm + l * WMAX * WMAX;
             float da[WMAX];
 #pragma unroll
@@ -217,15 +225,15 @@ int launch_fwd(const float* out_pts, const float* in_pts, const float* quad_w, c
     return 0;
 }
 
-template <int WMAX>
+template <int WMAX, int LT>
 int launch_bwd(const float* out_pts, const float* in_pts, const float* quad_w, const int* pair_row,
                const int* pair_col, int64_t P, int d, const MlpDev& m, int HP, const float* dphi,
                int nslices, float* d_quad_w, cudaStream_t st)
 {
     size_t smem = ((size_t)2 * m.n_hidden * WMAX * WMAX + 2 * 128 * WMAX) * 4;
-    QC_CUDA(cudaFuncSetAttribute(k_pair_phi_bwd<WMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA(cudaFuncSetAttribute(k_pair_phi_bwd<WMAX, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 4);
-    k_pair_phi_bwd<WMAX><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w);
+    k_pair_phi_bwd<WMAX, LT><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w);
     QC_CHECK_LAUNCH();
     return 0;
 }
@@ -273,12 +281,15 @@ int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad
     if (wmax < 0 || HP < H || HP > 32 || (HP & 3)) return QC_EUNSUP;
     cudaStream_t st = (cudaStream_t)stream;
     const int wsel = wmax > HP ? wmax : HP;
-    switch (wsel) {
-        case 4: return launch_bwd<4>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
-        case 8: return launch_bwd<8>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
-        case 16: return launch_bwd<16>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
-        case 32: return launch_bwd<32>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
+#define QC_BWD(W, LTV) return launch_bwd<W, LTV>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st)
+    const int L = m.n_hidden;
+    switch (wsel) {   // register-resident activations when (2L+1)*W floats fit comfortably, else the general kernel
+        case 4: if (L == 1) QC_BWD(4, 1); if (L == 2) QC_BWD(4, 2); if (L == 3) QC_BWD(4, 3); if (L == 4) QC_BWD(4, 4); QC_BWD(4, 0);
+        case 8: if (L == 1) QC_BWD(8, 1); if (L == 2) QC_BWD(8, 2); if (L == 3) QC_BWD(8, 3); if (L == 4) QC_BWD(8, 4); QC_BWD(8, 0);
+        case 16: if (L == 1) QC_BWD(16, 1); if (L == 2) QC_BWD(16, 2); QC_BWD(16, 0);
+        case 32: QC_BWD(32, 0);   // 160+ registers per thread: the occupancy loss costs more than the local-memory traffic
     }
+#undef QC_BWD
     return QC_EUNSUP;
 }
 
