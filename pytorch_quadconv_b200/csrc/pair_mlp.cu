@@ -159,13 +159,44 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
                 x_s[threadIdx.x * WMAX + o] = xs[l][o];
             }
             __syncthreads();
-            // dW_l[o][k] += sum_q da[q][o] * x[q][k]
-            for (int t = threadIdx.x; t < WMAX * WMAX; t += NT) {
-                int o = t / WMAX, k = t % WMAX;
-                float acc = 0.f;
-#pragma unroll 8
-                for (int q = 0; q < NT; ++q) acc = fmaf(da_s[q * WMAX + o], x_s[q * WMAX + k], acc);
-                dWs[l * WMAX * WMAX + t] += acc;
+            // dW_l[o][k] += sum_q da[q][o] * x[q][k]: a register-tiled mini-GEMM over the block's 128 pairs.
+            // Every thread owns a TL x TL tile of (o,k) and a range of q; vector loads of TL values feed
+            // TL*TL FMAs; the q ranges are combined with shared-memory atomics.
+            {
+                constexpr int TL = WMAX >= 16 ? 4 : 2;
+                constexpr int TPR = WMAX / TL, NTILE = TPR * TPR;
+                constexpr int NQR = NT / NTILE, QL = NT / NQR;
+                const int tile = threadIdx.x % NTILE, qr = threadIdx.x / NTILE;
+                const int o0 = (tile / TPR) * TL, k0 = (tile % TPR) * TL;
+                float acc[TL][TL];
+#pragma unroll
+                for (int i = 0; i < TL; ++i)
+#pragma unroll
+                    for (int j = 0; j < TL; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+                for (int q = qr * QL; q < (qr + 1) * QL; ++q) {
+                    float dv[TL], xv[TL];
+                    if (TL == 4) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(da_s + q * WMAX + o0);
+                        const float4 b4 = *reinterpret_cast<const float4*>(x_s + q * WMAX + k0);
+                        dv[0] = a4.x, dv[1] = a4.y, dv[TL - 2] = a4.z, dv[TL - 1] = a4.w;
+                        xv[0] = b4.x, xv[1] = b4.y, xv[TL - 2] = b4.z, xv[TL - 1] = b4.w;
+                    } else {
+                        const float2 a2 = *reinterpret_cast<const float2*>(da_s + q * WMAX + o0);
+                        const float2 b2 = *reinterpret_cast<const float2*>(x_s + q * WMAX + k0);
+                        dv[0] = a2.x, dv[1] = a2.y;
+                        xv[0] = b2.x, xv[1] = b2.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < TL; ++i)
+#pragma unroll
+                        for (int j = 0; j < TL; ++j) acc[i][j] = fmaf(dv[i], xv[j], acc[i][j]);
+                }
+#pragma unroll
+                for (int i = 0; i < TL; ++i)
+#pragma unroll
+                    for (int j = 0; j < TL; ++j)
+                        atomicAdd(&dWs[l * WMAX * WMAX + (o0 + i) * WMAX + k0 + j], acc[i][j]);
             }
             if (l > 0) {
 #pragma unroll
