@@ -137,11 +137,23 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
         const float wq = (valid && quad_w) ? quad_w[c] : 1.f;
         float dx[WMAX];
         float dwq = 0.f;
+        float gs[WMAX];   // d loss / d phi of this pair: the slices are summed in a fixed order, 128 bits at a time
+#pragma unroll
+        for (int h = 0; h < WMAX; ++h) gs[h] = 0.f;
+        if (valid) {
+            for (int sl = 0; sl < nslices; ++sl) {
+                const float4* src = reinterpret_cast<const float4*>(dphi + ((size_t)sl * P + p) * HP);
+#pragma unroll
+                for (int q = 0; q < WMAX / 4; ++q)
+                    if (4 * q < HP) {
+                        const float4 v = __ldg(src + q);
+                        gs[4 * q] += v.x, gs[4 * q + 1] += v.y, gs[4 * q + 2] += v.z, gs[4 * q + 3] += v.w;
+                    }
+            }
+        }
 #pragma unroll
         for (int h = 0; h < WMAX; ++h) {
-            float g = 0.f;
-            if (valid && h < H && h < HP)
-                for (int sl = 0; sl < nslices; ++sl) g += dphi[((size_t)sl * P + p) * HP + h];
+            const float g = h < H ? gs[h] : 0.f;
             dwq = fmaf(g, LT > 0 ? xs[LT][h] : xs[L][h], dwq);
             dx[h] = wq * g;
         }
