@@ -53,12 +53,15 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     constexpr int NG = CXC / 4, HQ = HP / 4;
     constexpr int D = (DW ? 8 : (KCH == 32 ? 6 : 16)) / NG;   // gathered pairs in flight per warp (async smem ring)
     constexpr int RING = D * NG * 512;          // bytes per warp: slot = NG groups x 32 lanes x 16 B
-    constexpr int PHS = PCH * HP + 4;
+    // pairs staged per piece: the dW variant with 8 batch lanes holds 4 points per warp next to the 108 KB
+    // operand buffer, so its pieces are shorter
+    constexpr int PCHK = (DW && LB == 3) ? 16 : PCH;
+    constexpr int PHS = PCHK * HP + 4;
     extern __shared__ __align__(128) float smem[];
     float* Bs = smem;                                              // [nkc][2][BSLICE] (hi, lo), canonical K-major
     float* phi_s = Bs + (size_t)nkc * 2 * BSLICE;                  // [NW*PPW][PHS]
     int* idx_s = reinterpret_cast<int*>(phi_s + NW * PPW * PHS);   // [NW*PPW][PCH]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + NW * PPW * PCH);  // [3] mbarriers + tmem base
+    uint64_t* bars = reinterpret_cast<uint64_t*>(idx_s + NW * PPW * PCHK);  // [3] mbarriers + tmem base
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 3);
     float* ring_s = reinterpret_cast<float*>(bars + 4);            // [NW warps][RING bytes]
     // DW: operand tiles of the dW_last GEMM, K-major with a 144-byte core-matrix step along K (= rows):
@@ -142,7 +145,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
 
             const float* Xc = Xb + (size_t)(cx0 >> 2) * (Bp * 4);
             float* my_phi = phi_s + (warp * PPW + s) * PHS;
-            int* my_idx = idx_s + (warp * PPW + s) * PCH;
+            int* my_idx = idx_s + (warp * PPW + s) * PCHK;
             const uint32_t my_idx_sa = tc::smem_u32(my_idx);
             // gathers go global -> shared asynchronously (cp.async, one commit group per pair) into a
             // per-warp ring; each lane copies and later reads back only its own 16 bytes per group
@@ -180,12 +183,12 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
                             tc::fma2(T[4 * q + e2][h], T[4 * q + e2 + 1][h], f[e2], f[e2 + 1], ph[h], ph[h]);
                 }
             };
-            for (int c0 = 0; c0 < maxlen; c0 += PCH) {
-                const int clen = min(PCH, len - c0);
-                const int cmax = min(PCH, maxlen - c0);
+            for (int c0 = 0; c0 < maxlen; c0 += PCHK) {
+                const int clen = min(PCHK, len - c0);
+                const int cmax = min(PCHK, maxlen - c0);
                 // pair indices and phi rows of this piece of the segment; a segment that fits in one piece
                 // (the usual case) is staged once per tile and reused by every channel chunk
-                if (kc == 0 || maxlen > PCH) {
+                if (kc == 0 || maxlen > PCHK) {
                     __syncwarp();
                     for (int e = b; e < clen; e += Bp) {
                         const int p = c0 + e;
@@ -390,7 +393,8 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
     const int nblk = qc_nblk(B);
     constexpr int NG = CXC / 4;
     constexpr int RING = ((DW ? 8 : (KCH == 32 ? 6 : 16)) / NG) * NG * 512;
-    size_t smem = ((size_t)nkc * 2 * BSLICE + NW * PPW * (PCH * HP + 4) + NW * PPW * PCH) * 4 + 32 + NW * RING;
+    constexpr int PCHK = (DW && LB == 3) ? 16 : PCH;
+    size_t smem = ((size_t)nkc * 2 * BSLICE + NW * PPW * (PCHK * HP + 4) + NW * PPW * PCHK) * 4 + 32 + NW * RING;
     int dw_in_smem = 0;
     if (DW) {
         smem += OPBUF_BYTES + 128;
