@@ -51,7 +51,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     constexpr int TCOLS = KCH == 32 ? 256 : 512;   // TMEM columns allocated by this CTA
     constexpr int RBCOLS = 2 * KCH + 32;           // per row block: A_hi, A_lo, D
     constexpr int NG = CXC / 4, HQ = HP / 4;
-    constexpr int D = (DW ? 8 : (KCH == 32 ? 6 : 16)) / NG;   // gathered pairs in flight per warp (async smem ring)
+    constexpr int D = (DW ? 8 : (KCH == 32 ? 6 : 8)) / NG;   // gathered pairs in flight per warp (async smem ring)
     constexpr int RING = D * NG * 512;          // bytes per warp: slot = NG groups x 32 lanes x 16 B
     // pairs staged per piece: the dW variant with 8 batch lanes holds 4 points per warp next to the 108 KB
     // operand buffer, so its pieces are shorter
@@ -437,7 +437,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
     constexpr int NT = NW * 32;
     constexpr int CXC = 64 / HP, Bp = 1 << LB, PPW = 32 >> LB;
     constexpr int NG = CXC / 4;
-    constexpr int D = 16 / NG;                  // gathered pairs in flight per warp (async smem ring); the unrolled
+    constexpr int D = 8 / NG;                   // gathered pairs in flight per warp (async smem ring); the unrolled
                                                 // loop body must stay inside the 32 KB instruction cache
     constexpr int RING = D * NG * 512;
     constexpr int LH = HP == 8 ? 3 : 2;
