@@ -32,6 +32,12 @@ constexpr int OPBUF_BYTES = 2 * OP_A_BYTES + 2 * OP_B_BYTES;
 __host__ __device__ constexpr int op_off_words(int mn, int r) { return ((mn >> 3) * OP_SBO + (r >> 2) * OP_LBO + (mn & 7) * 16 + (r & 3) * 4) / 4; }
 constexpr int PCH = 64;  // pairs staged per chunk
 
+// Ring depth (gathered pairs in flight per warp) of the two kernel families; NG = 16-byte groups per pair.
+// Measured at C3: depth 4 beats 8 by 3-4 % (shorter unrolled body; the shared memory it frees, i.e. the larger
+// L1, made no measurable difference on its own), depth 2 loses the overlap (+45 %).
+__host__ __device__ constexpr int ctc_ring_depth(bool dw, int kch, int ng) { return (dw ? 8 : (kch == 32 ? 6 : 8)) / ng; }
+__host__ __device__ constexpr int dtc_ring_depth(int ng) { return 8 / ng; }
+
 // KCH = K of one channel chunk = channels per chunk x HP.  KCH = 64 runs one CTA per SM (TMEM: 2 row
 // blocks x (64 hi + 64 lo + 32 D) = 320 of 512 columns); KCH = 32 halves the register tile and the
 // TMEM footprint (2 x 96 = 192 -> a 256-column allocation) so that TWO CTAs share an SM: 16 warps
@@ -51,7 +57,7 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     constexpr int TCOLS = KCH == 32 ? 256 : 512;   // TMEM columns allocated by this CTA
     constexpr int RBCOLS = 2 * KCH + 32;           // per row block: A_hi, A_lo, D
     constexpr int NG = CXC / 4, HQ = HP / 4;
-    constexpr int D = (DW ? 8 : (KCH == 32 ? 6 : 8)) / NG;   // gathered pairs in flight per warp (async smem ring)
+    constexpr int D = ctc_ring_depth(DW, KCH, NG);   // gathered pairs in flight per warp (async smem ring)
     constexpr int RING = D * NG * 512;          // bytes per warp: slot = NG groups x 32 lanes x 16 B
     // pairs staged per piece: the dW variant with 8 batch lanes holds 4 points per warp next to the 108 KB
     // operand buffer, so its pieces are shorter
@@ -392,7 +398,7 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
     const int nkc = qc_ceil_div(a.Cx, CXC);
     const int nblk = qc_nblk(B);
     constexpr int NG = CXC / 4;
-    constexpr int RING = ((DW ? 8 : (KCH == 32 ? 6 : 16)) / NG) * NG * 512;
+    constexpr int RING = ctc_ring_depth(DW, KCH, NG) * NG * 512;
     constexpr int PCHK = (DW && LB == 3) ? 16 : PCH;
     size_t smem = ((size_t)nkc * 2 * BSLICE + NW * PPW * (PCHK * HP + 4) + NW * PPW * PCHK) * 4 + 32 + NW * RING;
     int dw_in_smem = 0;
@@ -437,7 +443,7 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
     constexpr int NT = NW * 32;
     constexpr int CXC = 64 / HP, Bp = 1 << LB, PPW = 32 >> LB;
     constexpr int NG = CXC / 4;
-    constexpr int D = 8 / NG;                   // gathered pairs in flight per warp (async smem ring); the unrolled
+    constexpr int D = dtc_ring_depth(NG);       // gathered pairs in flight per warp (async smem ring); the unrolled
                                                 // loop body must stay inside the 32 KB instruction cache
     constexpr int RING = D * NG * 512;
     constexpr int LH = HP == 8 ? 3 : 2;
@@ -770,7 +776,7 @@ int launch_dtc(const DphiArgs& a, int B, cudaStream_t st)
     constexpr int CXC = 64 / HP, PPW = 32 >> LB;
     const int nkc = qc_ceil_div(a.Cx, CXC);
     const int nblk = qc_nblk(B);
-    constexpr int RING = (16 / (CXC / 4)) * (CXC / 4) * 512;
+    constexpr int RING = dtc_ring_depth(CXC / 4) * (CXC / 4) * 512;
     const size_t smem = ((size_t)nkc * 2 * WSLICE + NW * PPW * PCH) * 4 + 64 + NW * RING;
     if (smem > 227 * 1024) return 0;
     QC_CUDA(cudaFuncSetAttribute(k_dphi_tc<HP, LB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
