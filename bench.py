@@ -487,7 +487,10 @@ def main():
         stageB = 2.0 * P * B * hL
         dense = 2.0 * w["N"] * B * ci * co * hL
         alg = {"qc_contract.fwd": stageB * ci + dense, "qc_contract.bwd": stageB * co + 2 * dense,
-               "qc_dphi.bwd": stageB * ci + dense}.get(dom, 0.0)
+               "qc_dphi.bwd": stageB * ci + dense,
+               # wide path (csrc/contract_wide.cu): the gather kernels hold only stage B, the dense stage is cuBLAS
+               "qc_gather_accumulate.fwd": stageB * ci, "qc_gather_accumulate.bwd": stageB * co,
+               "qc_gather_dot.bwd": stageB * ci}.get(dom, 0.0)
         peak = bf16 / 6.0     # fp32 mode on tensor cores = 3xTF32 ~ bf16/6
         ach = alg / (dom_ms * 1e-3) / 1e12
         traffic = None
