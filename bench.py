@@ -185,14 +185,15 @@ class ClockSampler:
 # our arm
 # --------------------------------------------------------------------------------------------
 
-def build_problem(w, dev, cache=True):
+def build_problem(w, dev, cache=True, filter_dtype=torch.float32):
     import pytorch_quadconv_b200 as q
     torch.manual_seed(0)
     pts = torch.rand(w["N"], w["d"])
     x_host = torch.randn(w["B"], w["ci"], w["N"]).pin_memory()
     mesh = q.MeshHandler(pts).construct([w["N"]], quad_args={"point_args": {}, "weight_args": weight_args(w["d"])})
     layer = q.QuadConv(spatial_dim=w["d"], in_points=w["N"], out_points=w["N"], in_channels=w["ci"],
-                       out_channels=w["co"], filter_seq=w["fs"], output_same=True, decay_param=w["r"], cache=cache)
+                       out_channels=w["co"], filter_seq=w["fs"], output_same=True, decay_param=w["r"], cache=cache,
+                       filter_dtype=filter_dtype)
     return mesh.to(dev), layer.to(dev), x_host
 
 
@@ -295,6 +296,9 @@ def main():
     ap.add_argument("--no-cache", action="store_true",
                     help="QuadConv(cache=False): the neighbour search runs inside every forward "
                          "(the mode of the reference's py_scripts/quadconv_layer_profile.py:46)")
+    ap.add_argument("--filter-dtype", default="f32", choices=["f32", "bf16"],
+                    help="bf16: the filter MLP takes bf16 operands with fp32 accumulation (C4's definition in "
+                         "BASELINE.json); the rest of the layer stays fp32 (single-layer workloads)")
     ap.add_argument("--graph", action="store_true",
                     help="capture the step in a CUDA graph and replay it (small meshes are launch-latency bound)")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel timing table (json) here")
@@ -349,7 +353,8 @@ def main():
             opt.step()
             return loss
     else:
-        mesh, layer, x_host = build_problem(w, dev, cache=not args.no_cache)
+        mesh, layer, x_host = build_problem(w, dev, cache=not args.no_cache,
+                                            filter_dtype=torch.bfloat16 if args.filter_dtype == "bf16" else torch.float32)
         x = x_host.to(dev).requires_grad_()
         params = trainable_parameters([layer, mesh])
         reducer = FlatGradAllReduce(params) if world > 1 else None
@@ -533,7 +538,7 @@ def main():
                        "l2": "inputs larger than L2 (features+grads 1.6 GB/step > 126 MB)" if w["N"] >= 50000
                        else "working set fits in L2 (reference's own CPU-runnable case)",
                        "includes": "MeshHandler.weights() (fused weight-map kernels, mesh_handler.py:101-112) every step",
-                       "cuda_graph": bool(args.graph), "cache": not args.no_cache},
+                       "cuda_graph": bool(args.graph), "cache": not args.no_cache, "filter_mlp_operands": args.filter_dtype},
             "clocks": clk.summary(),
             "e2e": {"value": P * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

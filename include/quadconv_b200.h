@@ -105,6 +105,8 @@ typedef struct {
     int n_hidden;
     int dims[QC_MAX_MLP_LAYERS + 1];
     const float* w[QC_MAX_MLP_LAYERS];
+    int operand_bf16;   /* != 0: every Linear of the filter MLP takes bf16 operands (weights as loaded and layer
+                           inputs rounded to nearest even), fp32 accumulate; phi is w * bf16(last activation) */
 } qc_mlp_t;
 
 int qc_pair_phi_fwd(const float* out_pts, const float* in_pts, const float* quad_w,

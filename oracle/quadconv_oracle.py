@@ -101,11 +101,22 @@ def eval_indices_torch(out_pts: torch.Tensor, in_pts: torch.Tensor, decay_param,
 # filter MLP + integral
 # ---------------------------------------------------------------------------------------------
 
-def filter_mlp(weights, z: torch.Tensor) -> torch.Tensor:
+def _rnd_bf16(t: torch.Tensor) -> torch.Tensor:
+    """Round to the nearest bf16 value (ties to even), keeping the dtype; straight-through for autograd (the
+    gradient passes unrounded -- routing it through the casts would round the gradient to bf16 as well)."""
+    r = t.detach().to(torch.float32).to(torch.bfloat16).to(t.dtype)
+    return t + (r - t.detach())
+
+
+def filter_mlp(weights, z: torch.Tensor, operand_bf16: bool = False) -> torch.Tensor:
     """quadconv.py:130-145: Linear(bias=False) at even positions, Sin (utils/misc.py:18-19)
-    between, no activation after the last Linear.  `weights` is the list filter.{0,2,..}.weight."""
+    between, no activation after the last Linear.  `weights` is the list filter.{0,2,..}.weight.
+    operand_bf16: the 'bf16 filter MLP' mode of the product (not in the reference): every Linear takes
+    bf16-rounded weights and inputs, accumulates in the working precision."""
     h = z
     for l, W in enumerate(weights):
+        if operand_bf16:
+            h, W = _rnd_bf16(h), _rnd_bf16(W)
         h = torch.nn.functional.linear(h, W)
         if l + 1 < len(weights):
             h = torch.sin(h)
@@ -113,7 +124,7 @@ def filter_mlp(weights, z: torch.Tensor) -> torch.Tensor:
 
 
 def quadconv_forward(out_pts, in_pts, quad_weights, filt_weights, features, eval_indices,
-                     in_channels, out_channels, bias=None, block_pairs: int = 1 << 18):
+                     in_channels, out_channels, bias=None, block_pairs: int = 1 << 18, operand_bf16: bool = False):
     """Restatement of QuadConv.forward + _integrate (quadconv.py:238-265, :213-227), blocked over
     pairs so that the materialised [pairs, Ci, Co] filter tensor fits in memory at any mesh size.
     Differentiable w.r.t. quad_weights, filt_weights, features, bias through torch autograd, like
@@ -129,7 +140,7 @@ def quadconv_forward(out_pts, in_pts, quad_weights, filt_weights, features, eval
         idx = eval_indices[s:s + block_pairs]
         w = quad_weights[idx[:, 1]]                                             # :247
         eval_locs = (out_pts[idx[:, 0]] - in_pts[idx[:, 1]]).to(features.dtype)  # :250-253 (fp32 subtract, as the reference)
-        filters = filter_mlp(filt_weights, eval_locs).reshape(-1, in_channels, out_channels)  # :257,:91
+        filters = filter_mlp(filt_weights, eval_locs, operand_bf16).reshape(-1, in_channels, out_channels)  # :257,:91
         values = torch.einsum('n, nij, bin -> bjn', w, filters, features[:, :, idx[:, 1]])    # :216-219
         integral = integral.scatter_add(2, idx[:, 0].expand(B, out_channels, -1), values)    # :225
     if bias is not None:

@@ -21,7 +21,8 @@ class QcMlp(ctypes.Structure):
     """qc_mlp_t"""
     _fields_ = [("n_hidden", c_int),
                 ("dims", c_int * (QC_MAX_MLP_LAYERS + 1)),
-                ("w", c_void_p * QC_MAX_MLP_LAYERS)]
+                ("w", c_void_p * QC_MAX_MLP_LAYERS),
+                ("operand_bf16", c_int)]
 
 
 _SIGNATURES = {
@@ -119,8 +120,9 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def make_mlp(d: int, hidden_ws) -> QcMlp:
+def make_mlp(d: int, hidden_ws, operand_bf16: bool = False) -> QcMlp:
     m = QcMlp()
+    m.operand_bf16 = 1 if operand_bf16 else 0
     n = len(hidden_ws)
     if n > QC_MAX_MLP_LAYERS:
         raise RuntimeError(f"filter MLP with {n} hidden layers exceeds QC_MAX_MLP_LAYERS={QC_MAX_MLP_LAYERS}")

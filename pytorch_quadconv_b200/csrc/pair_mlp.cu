@@ -9,16 +9,23 @@
 // and its backward.  The hidden widths are tiny (4..32), so this is CUDA-core work: the weights sit
 // zero-padded in shared memory and are read as warp-uniform broadcasts; activations stay in
 // registers.  sinf/cosf are the accurate versions (no fast-math) to hold the 1e-5 fp32 bound.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
 
 struct MlpDev {
+    int bf16;   // operands of every Linear rounded to bf16 (qc_mlp_t::operand_bf16)
     int n_hidden;
     int dims[QC_MAX_MLP_LAYERS + 1];
     const float* w[QC_MAX_MLP_LAYERS];
     float* dw[QC_MAX_MLP_LAYERS];
 };
+
+__device__ __forceinline__ float rnd_operand(float v, int bf16)
+{
+    return bf16 ? __bfloat162float(__float2bfloat16_rn(v)) : v;
+}
 
 template <int WMAX>
 __device__ __forceinline__ void load_weights(const MlpDev& m, float* Wsm)
@@ -28,7 +35,7 @@ __device__ __forceinline__ void load_weights(const MlpDev& m, float* Wsm)
         const int nin = m.dims[l], nout = m.dims[l + 1];
         for (int t = threadIdx.x; t < WMAX * WMAX; t += blockDim.x) {
             int o = t / WMAX, k = t % WMAX;
-            Wsm[l * WMAX * WMAX + t] = (o < nout && k < nin) ? m.w[l][o * nin + k] : 0.f;
+            Wsm[l * WMAX * WMAX + t] = (o < nout && k < nin) ? rnd_operand(m.w[l][o * nin + k], m.bf16) : 0.f;
         }
     }
 }
@@ -53,6 +60,8 @@ k_pair_phi_fwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
 #pragma unroll
         for (int k = 0; k < 3; ++k)
             if (k < d && k < WMAX) a[k] = __fsub_rn(out_pts[(size_t)r * d + k], in_pts[(size_t)c * d + k]);
+#pragma unroll
+        for (int k = 0; k < WMAX; ++k) a[k] = rnd_operand(a[k], m.bf16);
         for (int l = 0; l < m.n_hidden; ++l) {
             const float* W = Wsm + l * WMAX * WMAX;
             float t[WMAX];
@@ -61,7 +70,7 @@ k_pair_phi_fwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
                 float acc = 0.f;
 #pragma unroll
                 for (int k = 0; k < WMAX; ++k) acc = fmaf(W[o * WMAX + k], a[k], acc);
-                t[o] = sinf(acc);
+                t[o] = rnd_operand(sinf(acc), m.bf16);
             }
 #pragma unroll
             for (int o = 0; o < WMAX; ++o) a[o] = t[o];
@@ -117,7 +126,8 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
         if (valid) {
 #pragma unroll
             for (int k = 0; k < 3; ++k)
-                if (k < d && k < WMAX) xs[0][k] = __fsub_rn(out_pts[(size_t)r * d + k], in_pts[(size_t)c * d + k]);
+                if (k < d && k < WMAX)
+                    xs[0][k] = rnd_operand(__fsub_rn(out_pts[(size_t)r * d + k], in_pts[(size_t)c * d + k]), m.bf16);
         }
 #pragma unroll(LT > 0 ? LMAX : 1)
         for (int l = 0; l < LMAX; ++l) {
@@ -130,7 +140,7 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
                 for (int k = 0; k < WMAX; ++k) acc = fmaf(W[o * WMAX + k], xs[l][k], acc);
                 float sv, cv;
                 sincosf(acc, &sv, &cv);
-                xs[l + 1][o] = sv;
+                xs[l + 1][o] = rnd_operand(sv, m.bf16);   // straight-through: the derivative ignores the rounding
                 cs[l][o] = cv;
             }
         }
@@ -248,6 +258,7 @@ int fill_dev(const qc_mlp_t* mlp, int d, MlpDev& m)
     if (mlp->n_hidden < 0 || mlp->n_hidden > QC_MAX_MLP_LAYERS) return QC_EUNSUP;
     if (mlp->dims[0] != d) return QC_EINVAL;
     m.n_hidden = mlp->n_hidden;
+    m.bf16 = mlp->operand_bf16 != 0;
     for (int l = 0; l <= QC_MAX_MLP_LAYERS; ++l) m.dims[l] = l <= mlp->n_hidden ? mlp->dims[l] : 0;
     for (int l = 0; l < QC_MAX_MLP_LAYERS; ++l) {
         m.w[l] = l < mlp->n_hidden ? mlp->w[l] : nullptr;

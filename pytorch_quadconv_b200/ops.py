@@ -205,12 +205,16 @@ class _fp32_matmul:
 def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor,
                hidden_ws: Sequence[Tensor], w_last: Tensor, bias: Optional[Tensor],
                pair_row: Tensor, pair_col: Tensor, row_ptr: Tensor, order_out: Optional[Tensor],
-               in_channels: int, out_channels: int) -> Tuple[Tensor, Tensor, Tensor]:
-    """Returns (out [B,Co,No], phi [P,HP], packed features) -- the last two are saved for backward."""
+               in_channels: int, out_channels: int, mlp_bf16: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+    """Returns (out [B,Co,No], phi [P,HP], packed features) -- the last two are saved for backward.
+    mlp_bf16: every Linear of the filter MLP takes bf16 operands (weights and layer inputs rounded to nearest
+    even), fp32 accumulate -- the 'bf16 filter MLP' mode; everything else stays fp32."""
     features = _f32c(features, "features")
     out_pts, in_pts, quad_w = _f32c(out_pts, "points"), _f32c(in_pts, "points"), _f32c(quad_w, "weights")
     hidden_ws = [_f32c(w, "filter weight") for w in hidden_ws]
     w_last = _f32c(w_last, "filter weight")
+    if mlp_bf16:
+        w_last = w_last.to(torch.bfloat16).to(torch.float32)
     B, Ci, Ni = features.shape
     No, d = out_pts.shape
     Co = out_channels
@@ -224,7 +228,7 @@ def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor
     dev = features.device
     L = C.lib()
     st = C.stream()
-    mlp = C.make_mlp(d, hidden_ws)
+    mlp = C.make_mlp(d, hidden_ws, mlp_bf16)
     phi = torch.empty((max(P, 1), HP), dtype=torch.float32, device=dev)
     C.check(L.qc_pair_phi_fwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row), C.ptr(pair_col),
                               P, d, mlp, HP, C.ptr(phi), st), "qc_pair_phi_fwd")
@@ -254,7 +258,7 @@ def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor
 
 @qc_forward.register_fake
 def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair_col, row_ptr, order_out,
-      in_channels, out_channels):
+      in_channels, out_channels, mlp_bf16=False):
     B, Ci, Ni = features.shape
     No = out_pts.shape[0]
     HP = _hp(w_last.shape[1])
@@ -267,11 +271,13 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
                 hidden_ws: Sequence[Tensor], w_last: Tensor, pair_row: Tensor, pair_col: Tensor,
                 row_ptr: Tensor, csc_ptr: Tensor, csc_pair: Tensor, csc_row: Tensor,
                 order_out: Optional[Tensor], order_in: Optional[Tensor], batch: int, in_channels: int,
-                out_channels: int, has_bias: bool) -> List[Tensor]:
+                out_channels: int, has_bias: bool, mlp_bf16: bool = False) -> List[Tensor]:
     """Returns [d_features, d_quad_w, d_w_last, d_bias (or empty), *d_hidden_ws]."""
     grad_out = _f32c(grad_out, "grad_out")
     hidden_ws = [_f32c(w, "filter weight") for w in hidden_ws]
     w_last = _f32c(w_last, "filter weight")
+    if mlp_bf16:   # straight-through: gradients are taken at the rounded operands, applied to the fp32 weights
+        w_last = w_last.to(torch.bfloat16).to(torch.float32)
     B, Ci, Co = batch, in_channels, out_channels
     Ni, No, d = in_pts.shape[0], out_pts.shape[0], out_pts.shape[1]
     H = w_last.shape[1]
@@ -301,7 +307,7 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
             del dT
             d_hidden = [torch.zeros_like(w) for w in hidden_ws]
             d_quad_w = torch.zeros(Ni, **f32)
-            mlp = C.make_mlp(d, hidden_ws)
+            mlp = C.make_mlp(d, hidden_ws, mlp_bf16)
             import ctypes
             dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
             C.check(L.qc_pair_phi_bwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row),
@@ -329,7 +335,7 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
                       C.ptr(order_out), No, B, P, C.ptr(dphi), st), "qc_dphi")
     d_hidden = [torch.zeros_like(w) for w in hidden_ws]
     d_quad_w = torch.zeros(Ni, **f32)
-    mlp = C.make_mlp(d, hidden_ws)
+    mlp = C.make_mlp(d, hidden_ws, mlp_bf16)
     import ctypes
     dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
     C.check(L.qc_pair_phi_bwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row), C.ptr(pair_col),
@@ -352,7 +358,7 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
 
 @qc_backward.register_fake
 def _(grad_out, xp, phi, out_pts, in_pts, quad_w, hidden_ws, w_last, pair_row, pair_col, row_ptr, csc_ptr,
-      csc_pair, csc_row, order_out, order_in, batch, in_channels, out_channels, has_bias):
+      csc_pair, csc_row, order_out, order_in, batch, in_channels, out_channels, has_bias, mlp_bf16=False):
     Ni, No = in_pts.shape[0], out_pts.shape[0]
     e = grad_out.new_empty
     return [e((batch, in_channels, Ni)), e(Ni), e(w_last.shape),
@@ -365,28 +371,29 @@ class _QuadConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, features, quad_w, w_last, bias, tables, dims, *hidden_ws):
         out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = tables
-        Ci, Co = dims
+        Ci, Co, mlp_bf16 = dims
         out, phi, xp = qc_forward(features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
-                                  pair_col, row_ptr, order_out, Ci, Co)
+                                  pair_col, row_ptr, order_out, Ci, Co, mlp_bf16)
         ctx.save_for_backward(xp, phi, quad_w, w_last, *hidden_ws)
         ctx.tables = tables
-        ctx.dims = (features.shape[0], Ci, Co, bias is not None)
+        ctx.dims = (features.shape[0], Ci, Co, bias is not None, mlp_bf16)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         xp, phi, quad_w, w_last, *hidden_ws = ctx.saved_tensors
         out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = ctx.tables
-        B, Ci, Co, has_bias = ctx.dims
+        B, Ci, Co, has_bias, mlp_bf16 = ctx.dims
         res = qc_backward(grad_out, xp, phi, out_pts, in_pts, quad_w, list(hidden_ws), w_last, pair_row, pair_col,
-                          row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in, B, Ci, Co, has_bias)
+                          row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in, B, Ci, Co, has_bias, mlp_bf16)
         d_features, d_quad_w, d_w_last, d_bias = res[:4]
         d_hidden = res[4:]
         return (d_features, d_quad_w, d_w_last, d_bias if has_bias else None, None, None, *d_hidden)
 
 
-def quadconv_apply(features, quad_w, hidden_ws, w_last, bias, tables, in_channels, out_channels):
-    return _QuadConvFn.apply(features, quad_w, w_last, bias, tables, (in_channels, out_channels), *hidden_ws)
+def quadconv_apply(features, quad_w, hidden_ws, w_last, bias, tables, in_channels, out_channels, mlp_bf16=False):
+    return _QuadConvFn.apply(features, quad_w, w_last, bias, tables, (in_channels, out_channels, bool(mlp_bf16)),
+                             *hidden_ws)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -65,7 +65,7 @@ def test_dquadw_direct(cuda_lib):
     assert relerr(w.grad.cpu().numpy(), L["dquad_w"]) < TOL
 
 
-def _oracle_case(d, n, ci, co, B, fs, r, bias, seed, n_out=None):
+def _oracle_case(d, n, ci, co, B, fs, r, bias, seed, n_out=None, operand_bf16=False):
     """Fresh seeded problem; reference values from the oracle's restatement of the reference path.
     The oracle is evaluated in float64 on the fp32 inputs: torch's CPU fp32 bmm path showed run-to-run
     deviations of up to 2.7e-5 (against float64) on the GPU boxes' hosts -- larger than the 1e-5 bound and
@@ -85,7 +85,7 @@ def _oracle_case(d, n, ci, co, B, fs, r, bias, seed, n_out=None):
     x64, qw64 = x.double().requires_grad_(), qw.double().requires_grad_()
     ws64 = [w.double().requires_grad_() for w in ws]
     b64 = b.double().requires_grad_() if bias else None
-    y64 = O.quadconv_forward(out_pts, pts, qw64, ws64, x64, pairs, ci, co, b64)
+    y64 = O.quadconv_forward(out_pts, pts, qw64, ws64, x64, pairs, ci, co, b64, operand_bf16=operand_bf16)
     go = torch.randn(y64.shape, generator=g)
     (y64 * go.double()).sum().backward()
     x.grad, qw.grad = x64.grad.float(), qw64.grad.float()
@@ -179,6 +179,48 @@ def test_layer_matches_oracle(cuda_lib, d, n, ci, co, B, fs, r, bias, n_out):
         assert relerr(m.weight.grad.cpu().numpy(), w.grad.numpy()) < TOL
     if bias:
         assert relerr(layer.bias.grad.cpu().numpy(), c["b"].grad.numpy()) < TOL
+
+
+@pytest.mark.parametrize("d,n,ci,co,B,fs,r", [
+    (2, 700, 8, 8, 8, [8, 8], 0.09),        # tcgen05 kernels
+    (3, 900, 32, 32, 32, [8, 8], 0.2),      # tcgen05 kernels, C3-like
+    (2, 500, 16, 40, 8, [32, 32], 0.15),    # wide path, C4-like ("bf16 filter MLP" in BASELINE.json's config 4)
+    (2, 400, 5, 6, 3, [6], 0.12),           # general kernel
+])
+def test_bf16_filter_mlp_mode(cuda_lib, d, n, ci, co, B, fs, r):
+    """filter_dtype=torch.bfloat16: every Linear of the filter MLP takes bf16 operands (weights and layer inputs
+    rounded to nearest even) with fp32 accumulation; the rest of the layer is fp32.  Stated bounds: the mode
+    reproduces the same arithmetic done by the oracle (float64 accumulation) to 1e-4 normwise -- operand
+    roundings can flip where the fp32 and float64 activations straddle a bf16 boundary -- and stays within
+    2e-2 of the fp32 layer."""
+    import pytorch_quadconv_b200 as q
+    TOL_MODE, TOL_FP32 = 1e-4, 2e-2
+    c = _oracle_case(d, n, ci, co, B, fs, r, True, seed=4000 + n + ci, operand_bf16=True)
+    c32 = _oracle_case(d, n, ci, co, B, fs, r, True, seed=4000 + n + ci)
+    layer = q.QuadConv(spatial_dim=d, in_points=n, out_points=n, in_channels=ci, out_channels=co,
+                       filter_seq=fs, bias=True, output_same=True, decay_param=r,
+                       filter_dtype=torch.bfloat16).cuda()
+    with torch.no_grad():
+        lin = [m for m in layer.filter if isinstance(m, torch.nn.Linear)]
+        for m, w in zip(lin, c["ws"]):
+            m.weight.copy_(w.detach())
+        layer.bias.copy_(c["b"].detach())
+    w_dev = c["qw"].detach().cuda().requires_grad_()
+    mesh = _StubMesh(c["pts"].cuda(), c["out_pts"].cuda(), w_dev)
+    x = c["x"].detach().cuda().requires_grad_()
+    y = layer(mesh, x)
+    assert relerr(y.detach().cpu().numpy(), c["y"].numpy()) < TOL_MODE
+    dev32 = relerr(y.detach().cpu().numpy(), c32["y"].numpy())
+    assert 1e-5 < dev32 < TOL_FP32, dev32          # the mode really rounds, and stays inside its stated bound
+    (y * c["go"].cuda()).sum().backward()
+    assert relerr(x.grad.cpu().numpy(), c["x"].grad.numpy()) < TOL_MODE
+    assert relerr(w_dev.grad.cpu().numpy(), c["qw"].grad.numpy()) < TOL_MODE
+    for m, w in zip(lin, c["ws"]):
+        assert relerr(m.weight.grad.cpu().numpy(), w.grad.numpy()) < 5 * TOL_MODE
+    assert relerr(layer.bias.grad.cpu().numpy(), c["b"].grad.numpy()) < TOL_MODE
+    with pytest.raises(ValueError):
+        q.QuadConv(spatial_dim=d, in_points=n, out_points=n, in_channels=ci, out_channels=co, filter_seq=fs,
+                   filter_dtype=torch.float16)
 
 
 def test_cache_false_and_injected_pairs(cuda_lib):
