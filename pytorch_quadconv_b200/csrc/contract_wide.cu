@@ -117,7 +117,7 @@ k_gather_acc(const WideArgs a)
                     for (int h = 0; h < HC; ++h) T[i][h] = 0.f;
 
                 auto issue_u = [&](int slot, unsigned u) {
-                    const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)(u * xrow));
+                    const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)u * xrow);
 #pragma unroll
                     for (int q = 0; q < NG; ++q)
                         if (gv[q]) tc::cp_async16(my_ring + (slot * NG + q) * 512, xr + q * 32);
@@ -322,7 +322,7 @@ k_gather_dot(const WideArgs a, const size_t slice_stride)
                     }
                 }
                 auto issue_u = [&](int slot, unsigned u) {
-                    const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)(u * xrow));
+                    const float4* xr = reinterpret_cast<const float4*>(Xc + (size_t)u * xrow);
 #pragma unroll
                     for (int q = 0; q < NG; ++q)
                         if (gv[q]) tc::cp_async16(my_ring + (slot * NG + q) * 512, xr + q * 32);
