@@ -171,6 +171,14 @@ int qc_gather_accumulate(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, 
 int qc_gather_dot(const float* Xp, int Nsrc, int Cx, const float* dT, const int* seg_ptr, const int* src_idx,
                   int H, int HP, const int* order, int Ndst, int B, int64_t P, float* dphi, void* stream);
 
+/* Dense stage of the wide path on the tensor cores: D[m][n] = sum_k A[m][k] * B[n][k] with A [M x K] and
+ * B [N x K] row-major fp32, three kind::tf32 MMAs per product (fp32-accurate: ~2e-7 normwise).
+ * rows_per_batch == 0: D is [M x N] row-major.  rows_per_batch = R > 0 (M a multiple of R): D is
+ * [M/R][N][R], i.e. every block of R rows is written transposed -- the reference's [B, C, N] layout when
+ * the rows are (batch, point).  K must be a multiple of 4 and A, B 16-byte aligned (QC_EUNSUP otherwise). */
+int qc_gemm_nt_tf32x3(const float* A, const float* B, float* D, long long M, int N, int K,
+                      long long rows_per_batch, void* stream);
+
 /* Repack the last Linear weight W_last [Ci*Co][H] (filter.{2L}.weight, quadconv.py:143):
  *   mode 0: W2[(i*H+h)*CoP + j]  (forward)        mode 1: W2[(j*H+h)*CiP + i]  (d features)
  *   mode 2: W3[(j*Ci+i)*HP + h]  (d phi)

@@ -58,6 +58,7 @@ _SIGNATURES = {
                                      c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "qc_gather_dot": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                               c_int, c_int64, c_void_p, c_void_p]),
+    "qc_gemm_nt_tf32x3": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, ctypes.c_longlong, c_void_p]),
     "qc_repack_wlast": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qc_unpack_dwlast": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qc_segmax_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -8,6 +8,8 @@ struct ContractArgs {
     float* Y;
     const float* Z;
     float* dW2;
+    float* dW_scratch;   // tcgen05 dW variant: per-CTA slots of partial dW2 accumulators [cta][slot][chunk][64][32]
+    int* dW_counts;      // ... and the number of slots every CTA wrote
     const int* seg_ptr;
     const int* src_idx;
     const int* phi_idx;

@@ -37,6 +37,7 @@ constexpr int PCH = 64;  // pairs staged per chunk
 // L1, made no measurable difference on its own), depth 2 loses the overlap (+45 %).
 __host__ __device__ constexpr int ctc_ring_depth(bool dw, int kch, int ng) { return (dw ? 8 : (kch == 32 ? 6 : 8)) / ng; }
 __host__ __device__ constexpr int dtc_ring_depth(int ng) { return 8 / ng; }
+constexpr int DW_FLUSH = 8;   // uses of the dW operand buffer between two flushes of the TMEM dW accumulators
 
 // KCH = K of one channel chunk = channels per chunk x HP.  KCH = 64 runs one CTA per SM (TMEM: 2 row
 // blocks x (64 hi + 64 lo + 32 D) = 320 of 512 columns); KCH = 32 halves the register tile and the
@@ -46,7 +47,7 @@ __host__ __device__ constexpr int dtc_ring_depth(int ng) { return 8 / ng; }
 // thread) -- more resident warps per scheduler to cover the FP32 pipe's dependency stalls.
 template <int HP, int KCH, int LB, bool DW, int NW>
 __global__ void __launch_bounds__(NW * 32, KCH == 32 ? 2 : 1)
-k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
+k_contract_tc(const ContractArgs a, const int nkc, const int dw_nslots)
 {
     static_assert(!DW || KCH == 64, "the dW mini-GEMM assumes 64-wide chunks");
     static_assert(!DW || NW == 8, "the dW mini-GEMM assumes 256 threads");
@@ -123,6 +124,38 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
     const uint32_t idesc = tc::make_idesc_tf32(128, 32);
     const uint32_t bs_addr = tc::smem_u32(Bs);
     uint32_t g = 0;  // MMA groups committed so far on this row block (same value in all its threads)
+
+    // DW: the dW2 accumulators live in TMEM (lanes 0..63 = k index m, 32 columns = j, one block per chunk).
+    // tcgen05.mma accumulates with truncation, so a long chain of accumulations loses ~2e-8 (relative) per
+    // MMA (measured: 1.5e-4 on dW_last at C3 when the chain ran for the whole kernel).  Every DW_FLUSH uses
+    // of the operand buffer (96 MMAs per accumulator, ~2e-6) the accumulators are therefore written out as
+    // one more partial result (plain stores into this CTA's next slot of the scratch buffer) and restarted;
+    // k_dw_reduce sums the slots in fp32 (round to nearest) into dW2.  Called by the warps that own TMEM
+    // lanes 0..63 (warp & 3 < 2) while no dW MMA is in flight.
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+    float* dw_slots = DW ? a.dW_scratch + (size_t)cta * dw_nslots * ((size_t)nkc * 64 * 32) : nullptr;
+    auto flush_dw = [&](int slot) {
+        const int m = (warp & 3) * 32 + lane;
+        for (int kc = 0; kc < nkc; ++kc) {
+            float4* row = reinterpret_cast<float4*>(dw_slots + ((size_t)slot * nkc + kc) * (64 * 32) + (size_t)m * 32);
+            if (*reinterpret_cast<volatile int*>(&lockw[2 + kc]) == 0) {   // nothing accumulated since the last flush
+#pragma unroll
+                for (int q = 0; q < 8; ++q) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
+            uint32_t v0[16], v1[16];
+            tc::tmem_ld16(lane_base + tmem + 2 * RBCOLS + kc * 32, v0);
+            tc::tmem_ld16(lane_base + tmem + 2 * RBCOLS + kc * 32 + 16, v1);
+            tc::wait_ld();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                row[q] = make_float4(__uint_as_float(v0[4 * q]), __uint_as_float(v0[4 * q + 1]),
+                                     __uint_as_float(v0[4 * q + 2]), __uint_as_float(v0[4 * q + 3]));
+                row[4 + q] = make_float4(__uint_as_float(v1[4 * q]), __uint_as_float(v1[4 * q + 1]),
+                                         __uint_as_float(v1[4 * q + 2]), __uint_as_float(v1[4 * q + 3]));
+            }
+        }
+    };
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int t = tile * ppt + warp * PPW + s;
@@ -272,6 +305,18 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
             tc::fence_before_sync();
             tc::named_bar_sync(1 + rb, 128);
             if (DW) {
+                // (the leader holds the lock and has seen the previous user's MMAs complete)
+                const int done = *reinterpret_cast<volatile int*>(&lockw[1]);
+                if (done > 0 && done % DW_FLUSH == 0) {
+                    tc::fence_after_sync();
+                    if ((warp & 3) < 2) flush_dw(done / DW_FLUSH - 1);
+                    tc::fence_before_sync();
+                    tc::named_bar_sync(1 + rb, 128);
+                    if (leader)
+                        for (int k2 = 0; k2 < nkc; ++k2) lockw[2 + k2] = 0;   // the next MMA group overwrites
+                }
+            }
+            if (DW) {
                 // this thread's row of T (hi/lo) and of Z (hi/lo) -> K-major operand tiles, K = row
                 const int r = (warp & 3) * 32 + lane;
                 float* Ahi = opbuf;
@@ -366,28 +411,42 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_in_smem)
         const int commits = *reinterpret_cast<volatile int*>(&lockw[1]);
         if (commits > 0) tc::mbar_wait(opbar, (commits - 1) & 1);
         tc::fence_after_sync();
-        if (warp < 2 && commits > 0) {
-            const int m = warp * 32 + lane, i = m / HP, hh = m % HP;
-            for (int kc = 0; kc < nkc; ++kc) {
-                uint32_t v0[16], v1[16];
-                tc::tmem_ld16(lane_base + tmem + 2 * RBCOLS + kc * 32, v0);
-                tc::tmem_ld16(lane_base + tmem + 2 * RBCOLS + kc * 32 + 16, v1);
-                tc::wait_ld();
-                const int cx = kc * CXC + i;
-                if (cx < a.Cx && hh < a.H) {
-                    float* dst = a.dW2 + ((size_t)cx * a.H + hh) * a.CyP;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (j < a.Cy) atomicAdd(dst + j, __uint_as_float(v0[j]));
-                        if (16 + j < a.Cy) atomicAdd(dst + 16 + j, __uint_as_float(v1[j]));
-                    }
-                }
-            }
-        }
+        // the remainder goes to the next slot; the number of slots this CTA wrote is recorded for k_dw_reduce
+        const int nfl = commits / DW_FLUSH;            // periodic flushes done (the one at `commits` itself has not run)
+        const int used = commits > 0 ? (commits % DW_FLUSH == 0 ? nfl - 1 : nfl) : 0;   // slots written so far
+        if (warp < 2 && commits > 0) flush_dw(used);
+        if (tid == 0) a.dW_counts[cta] = commits > 0 ? used + 1 : 0;
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
+}
+
+// dW2[(c*H+h)][j] += sum over the slots written by every CTA (fp32, fixed order inside a CTA's slots).
+// grid (nkc*64*32 / 256, CTAs of the main kernel); entry e = (chunk, m, j).
+template <int HP>
+__global__ void __launch_bounds__(256)
+k_dw_reduce(const float* __restrict__ scratch, const int* __restrict__ counts, int nslots, int nkc, int Cx, int H,
+            int Cy, int CyP, float* __restrict__ dW2)
+{
+    constexpr int CXC = 64 / HP;
+    const int e = blockIdx.x * 256 + threadIdx.x, cta = blockIdx.y;
+    const int per = nkc * 64 * 32;
+    if (e >= per) return;
+    const int n = counts[cta];
+    const float* p = scratch + (size_t)cta * nslots * per + e;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int f = 0;
+    for (; f + 4 <= n; f += 4) {
+        s0 += p[(size_t)f * per];
+        s1 += p[(size_t)(f + 1) * per];
+        s2 += p[(size_t)(f + 2) * per];
+        s3 += p[(size_t)(f + 3) * per];
+    }
+    for (; f < n; ++f) s0 += p[(size_t)f * per];
+    const int j = e & 31, m = (e >> 5) & 63, kc = e >> 11;
+    const int cx = kc * CXC + m / HP, hh = m % HP;
+    if (n > 0 && cx < Cx && hh < H && j < Cy) atomicAdd(dW2 + ((size_t)cx * H + hh) * CyP + j, (s0 + s1) + (s2 + s3));
 }
 
 template <int HP, int KCH, int LB, bool DW, int NW>
@@ -401,7 +460,6 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
     constexpr int RING = ctc_ring_depth(DW, KCH, NG) * NG * 512;
     constexpr int PCHK = (DW && LB == 3) ? 16 : PCH;
     size_t smem = ((size_t)nkc * 2 * BSLICE + NW * PPW * (PCHK * HP + 4) + NW * PPW * PCHK) * 4 + 32 + NW * RING;
-    int dw_in_smem = 0;
     if (DW) {
         smem += OPBUF_BYTES + 128;
         if (2 * (2 * KCH + 32) + nkc * 32 > 512 || nkc > 12) return 0;   // TMEM: stage C blocks + one dW accumulator per chunk
@@ -421,7 +479,30 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     dim3 grid(gx, nblk);
-    k_contract_tc<HP, KCH, LB, DW, NW><<<grid, NW * 32, smem, st>>>(a, nkc, dw_in_smem);
+    if (DW) {
+        // slots for the periodic flushes of the TMEM dW accumulators (see flush_dw): stream-ordered scratch
+        ContractArgs a2 = a;
+        const int tiles_per_cta = qc_ceil_div(ntiles, gx);
+        const int max_commits = tiles_per_cta * (NW / 4) * nkc;
+        const int nslots = (max_commits - 1) / DW_FLUSH + 1;
+        const int nctas = gx * nblk, per = nkc * 64 * 32;
+        const size_t fbytes = (size_t)nctas * nslots * per * sizeof(float);
+        char* buf = nullptr;
+        QC_CUDA(cudaMallocAsync((void**)&buf, fbytes + (size_t)nctas * sizeof(int), st));
+        a2.dW_scratch = reinterpret_cast<float*>(buf);
+        a2.dW_counts = reinterpret_cast<int*>(buf + fbytes);
+        k_contract_tc<HP, KCH, LB, DW, NW><<<grid, NW * 32, smem, st>>>(a2, nkc, nslots);
+        cudaError_t le = cudaGetLastError();
+        if (le == cudaSuccess) {
+            k_dw_reduce<HP><<<dim3(qc_ceil_div(per, 256), nctas), 256, 0, st>>>(a2.dW_scratch, a2.dW_counts, nslots, nkc,
+                                                                                 a.Cx, a.H, a.Cy, a.CyP, a.dW2);
+            le = cudaGetLastError();
+        }
+        cudaFreeAsync(buf, st);
+        if (le != cudaSuccess) return (int)le;
+        return 1;
+    }
+    k_contract_tc<HP, KCH, LB, DW, NW><<<grid, NW * 32, smem, st>>>(a, nkc, 0);
     QC_CHECK_LAUNCH();
     return 1;
 }

@@ -1,0 +1,228 @@
+// gemm_tc.cu -- fp32-accurate dense stage of the WIDE layer path on the tcgen05 tensor cores.
+//
+//     D[m][n] = sum_k A[m][k] * B[n][k]          A [M x K], B [N x K] row-major fp32 ("NT" GEMM)
+//
+// computed as three kind::tf32 MMAs per product (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, the same error-
+// compensated split the fused kernels use: 2e-7 against float64 where one TF32 pass gives 5e-4).
+// Both operands are K-major in global memory, which is what contract_wide.cu produces and consumes:
+//     Y  = T  * W2^T   (A = T   [B*No x Ci*H], B = W2^T [Co   x Ci*H])      output transposed per batch
+//     dT = G^T * W2    (A = G^T [B*No x Co],   B = W2   [Ci*H x Co])        output row-major
+//     dX = T' * W2t^T  (A = T'  [B*Ni x Co*H], B = W2t^T[Ci   x Co*H])      output transposed per batch
+// (the fourth GEMM of the path, dW = X * T', reduces over the ROW index of T' and stays on cuBLAS.)
+//
+// One CTA = 4 warps = a 128-row x BN-column tile with the accumulator in TMEM.  Per 32-wide K chunk
+// every thread fetches its A row piece (and B row piece) with 128-bit loads one chunk ahead, splits it
+// into tf32 hi / lo and writes it as 16-byte pieces into the canonical K-major no-swizzle operand tiles
+// of a two-stage shared-memory ring; one thread issues the 12 MMAs of the chunk and commits them to the
+// stage's mbarrier, which the loaders wait on before they overwrite that stage.
+//
+// tcgen05.mma accumulates with truncation (~2e-8 relative per MMA, measured: 1.5e-5 after K = 2048), so the
+// TMEM accumulation only runs over groups of GROUP chunks (48 MMAs); two TMEM accumulators alternate, and
+// while one group is multiplied the previous group's result is added to fp32 registers (round to nearest).
+#include <cstdint>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int GK = 32;        // K chunk
+constexpr int GSTAGES = 2;
+constexpr int GROUP = 4;      // K chunks accumulated in TMEM before the partial sum moves to registers
+
+struct GemmArgs {
+    const float* A;
+    const float* B;
+    float* D;
+    long long M;
+    int N, K;
+    long long rows_per_batch;   // 0: D[m*N + n];  > 0: D[((m / rpb) * N + n) * rpb + m % rpb]
+};
+
+template <int BN>
+__global__ void __launch_bounds__(128, 1)
+k_gemm_tf32x3(const GemmArgs g)
+{
+    constexpr int A_TILE = 128 * GK;             // floats per A tile (hi or lo)
+    constexpr int B_TILE = BN * GK;
+    constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+    constexpr int BROWS = (BN + 127) / 128;      // B rows per thread (BN <= 128 -> 1)
+    static_assert(BN == 64 || BN == 128, "tile widths");
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bars[GSTAGES];
+    __shared__ __align__(8) uint64_t gbars[2];     // one per TMEM accumulator: its group of MMAs has finished
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long m0 = (long long)blockIdx.x * 128;
+    const int n0 = blockIdx.y * BN;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 2 * BN);
+    if (tid == 0) {
+        for (int i = 0; i < GSTAGES; ++i) tc::mbar_init(&bars[i], 1);
+        tc::mbar_init(&gbars[0], 1);
+        tc::mbar_init(&gbars[1], 1);
+        tc::mbar_fence_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+
+    const long long m = m0 + tid;
+    const bool mvalid = m < g.M;
+    const float* arow = g.A + (mvalid ? m : 0) * (long long)g.K;
+    const int nrow = n0 + tid;                                  // this thread's B row (BN <= 128)
+    const bool nvalid = tid < BN && nrow < g.N;
+    const float* brow = g.B + (long long)(nvalid ? nrow : 0) * g.K;
+    const int nk = (g.K + GK - 1) / GK;
+
+    float4 ra[GK / 4], rb[GK / 4];
+    auto fetch = [&](int kc) {
+        const int k0 = kc * GK;
+#pragma unroll
+        for (int q = 0; q < GK / 4; ++q) {
+            ra[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + 4 * q < g.K) {   // K is a multiple of 4 (checked by the host)
+                if (mvalid) ra[q] = __ldg(reinterpret_cast<const float4*>(arow + k0) + q);
+                if (nvalid) rb[q] = __ldg(reinterpret_cast<const float4*>(brow + k0) + q);
+            }
+        }
+    };
+    auto split_store = [&](float* hi_t, float* lo_t, int row, const float4 (&r)[GK / 4]) {
+#pragma unroll
+        for (int q = 0; q < GK / 4; ++q) {
+            const float v[4] = {r[q].x, r[q].y, r[q].z, r[q].w};
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                h[e] = __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
+                l[e] = v[e] - h[e];
+            }
+            const uint32_t off = tc::kmajor_off_bytes(row, 4 * q, GK) / 4;
+            *reinterpret_cast<float4*>(hi_t + off) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(lo_t + off) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+    };
+
+    const uint32_t idesc = tc::make_idesc_tf32(128, BN);
+    constexpr uint32_t SBO = (GK / 4) * 128;
+    uint32_t phase[GSTAGES] = {0u, 0u};
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int ngroups = (nk + GROUP - 1) / GROUP;
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    int gread = 0;     // groups already added to acc
+    auto take_group = [&](int gi) {   // acc += D[gi & 1] once the group's MMAs have finished
+        tc::mbar_wait(&gbars[gi & 1], (gi >> 1) & 1);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < BN / 16; ++c) {
+            uint32_t r[16];
+            tc::tmem_ld16(lane_base + tmem + (gi & 1) * BN + c * 16, r);
+            tc::wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c * 16 + j] += __uint_as_float(r[j]);
+        }
+    };
+
+    fetch(0);
+    for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % GSTAGES;
+        float* st = smem + (size_t)s * STAGE;
+        if (kc >= GSTAGES) {   // the MMAs that read this stage two chunks ago have finished
+            tc::mbar_wait(&bars[s], phase[s] & 1);
+            ++phase[s];
+        }
+        split_store(st, st + A_TILE, tid, ra);
+        if (tid < BN) split_store(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, tid, rb);
+        if (kc + 1 < nk) fetch(kc + 1);     // in flight while this chunk is multiplied
+        const int gi = kc / GROUP;
+        if (kc % GROUP == GROUP / 2 && gi >= 1) {   // the previous group finished long ago: no stall
+            take_group(gi - 1);
+            gread = gi;
+        }
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t ahi = tc::smem_u32(st), alo = ahi + A_TILE * 4;
+            const uint32_t bhi = ahi + 2 * A_TILE * 4, blo = bhi + B_TILE * 4;
+#pragma unroll
+            for (int ks = 0; ks < GK / 8; ++ks) {
+                const uint64_t dah = tc::make_smem_desc(ahi + ks * 256, 128, SBO);
+                const uint64_t dal = tc::make_smem_desc(alo + ks * 256, 128, SBO);
+                const uint64_t dbh = tc::make_smem_desc(bhi + ks * 256, 128, SBO);
+                const uint64_t dbl = tc::make_smem_desc(blo + ks * 256, 128, SBO);
+                const uint32_t d = tmem + (gi & 1) * BN;
+                tc::mma_tf32_ss(d, dah, dbh, idesc, !(kc % GROUP == 0 && ks == 0));
+                tc::mma_tf32_ss(d, dal, dbh, idesc, true);
+                tc::mma_tf32_ss(d, dah, dbl, idesc, true);
+            }
+            tc::mma_commit(&bars[s]);
+            if (kc % GROUP == GROUP - 1 || kc == nk - 1) tc::mma_commit(&gbars[gi & 1]);
+        }
+    }
+    // the groups not yet taken (their commits also cover every stage's last MMAs)
+    for (int gi = gread; gi < ngroups; ++gi) take_group(gi);
+
+    // epilogue: thread = row
+    long long obase = 0, ostride = 1;
+    if (g.rows_per_batch > 0) {
+        const long long bb = m / g.rows_per_batch, o = m % g.rows_per_batch;
+        obase = bb * g.N * g.rows_per_batch + o;        // + n * rows_per_batch
+        ostride = g.rows_per_batch;
+    } else {
+        obase = m * g.N;
+    }
+    if (mvalid) {
+        if (g.rows_per_batch > 0) {
+#pragma unroll
+            for (int j = 0; j < BN; ++j)
+                if (n0 + j < g.N) g.D[obase + (long long)(n0 + j) * ostride] = acc[j];   // lanes = consecutive rows: coalesced
+        } else {
+            float* dst = g.D + obase + n0;
+#pragma unroll
+            for (int q = 0; q < BN / 4; ++q) {
+                if ((g.N & 3) == 0 && n0 + 4 * q + 4 <= g.N) {
+                    reinterpret_cast<float4*>(dst)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (n0 + 4 * q + e < g.N) dst[4 * q + e] = acc[4 * q + e];
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 2 * BN);
+}
+
+template <int BN>
+int launch_gemm(const GemmArgs& g, cudaStream_t st)
+{
+    const size_t smem = (size_t)GSTAGES * (2 * 128 * GK + 2 * BN * GK) * 4;
+    QC_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long mt = (g.M + 127) / 128;
+    const int nt = (g.N + BN - 1) / BN;
+    if (mt > 2147483647LL || nt > 65535) return QC_EUNSUP;
+    k_gemm_tf32x3<BN><<<dim3((unsigned)mt, (unsigned)nt), 128, smem, st>>>(g);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int qc_gemm_nt_tf32x3(const float* A, const float* B, float* D, long long M, int N, int K,
+                                  long long rows_per_batch, void* stream)
+{
+    if (M <= 0 || N <= 0 || K <= 0 || rows_per_batch < 0) return QC_EINVAL;
+    if ((K & 3) != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0 || (reinterpret_cast<uintptr_t>(B) & 15) != 0)
+        return QC_EUNSUP;   // 128-bit row pieces
+    if (rows_per_batch > 0 && M % rows_per_batch != 0) return QC_EINVAL;
+    GemmArgs g{A, B, D, M, N, K, rows_per_batch};
+    cudaStream_t st = (cudaStream_t)stream;
+    return N <= 64 ? launch_gemm<64>(g, st) : launch_gemm<128>(g, st);
+}

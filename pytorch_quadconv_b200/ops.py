@@ -190,6 +190,22 @@ def _use_wide(Ci: int, Co: int, H: int, HP: int, B: int, n_rows: int) -> bool:
     return B * n_rows * max(Ci, Co) * H * 4 <= _WIDE_MAX_BYTES
 
 
+def _gemm_nt(A: Tensor, Bm: Tensor, rows_per_batch: int = 0) -> Tensor:
+    """D = A @ Bm^T for row-major A [M,K], Bm [N,K] on the tensor cores in 3xTF32 (csrc/gemm_tc.cu).
+    rows_per_batch = R > 0 returns [M/R, N, R] (each block of R rows transposed), else [M, N]."""
+    M, K = A.shape
+    N = Bm.shape[0]
+    A, Bm = A.contiguous(), Bm.contiguous()
+    if K % 4 != 0:      # 128-bit row pieces; not reachable with H % 4 == 0
+        D = torch.matmul(A, Bm.t())
+        return D.reshape(M // rows_per_batch, rows_per_batch, N).transpose(1, 2).contiguous() if rows_per_batch else D
+    shape = (M // rows_per_batch, N, rows_per_batch) if rows_per_batch else (M, N)
+    D = torch.empty(shape, dtype=torch.float32, device=A.device)
+    C.check(C.lib().qc_gemm_nt_tf32x3(C.ptr(A), C.ptr(Bm), C.ptr(D), M, N, K, rows_per_batch, C.stream()),
+            "qc_gemm_nt_tf32x3")
+    return D
+
+
 class _fp32_matmul:
     """The dense stage of the wide path must be a true fp32 GEMM (1e-5 parity bound)."""
 
@@ -237,12 +253,12 @@ def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor
         T = torch.empty((B, No, Ci * H), dtype=torch.float32, device=dev)
         C.check(L.qc_gather_accumulate(C.ptr(xp), Ni, Ci, C.ptr(row_ptr), C.ptr(pair_col), None, C.ptr(phi), H, HP,
                                        C.ptr(order_out), No, B, C.ptr(T), st), "qc_gather_accumulate")
-        W2 = w_last.view(Ci, Co, H).permute(0, 2, 1).reshape(Ci * H, Co)      # [(i,h), j]
+        W2T = w_last.view(Ci, Co, H).permute(1, 0, 2).reshape(Co, Ci * H)     # [j, (i,h)]
         with _fp32_matmul():
-            out = torch.matmul(W2.t(), T.transpose(1, 2))                     # [B, Co, No]
+            out = _gemm_nt(T.view(B * No, Ci * H), W2T, No)                   # [B, Co, No]
         if bias is not None:
             out = out + _f32c(bias, "bias").reshape(1, Co, No)
-        return out.contiguous(), phi, xp
+        return out, phi, xp
     CoP = (Co + 3) & ~3
     W2 = torch.empty((Ci * H, CoP), dtype=torch.float32, device=dev)
     C.check(L.qc_repack_wlast(C.ptr(w_last), Ci, Co, H, HP, 0, C.ptr(W2), st), "qc_repack_wlast")
@@ -298,8 +314,8 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
         wl = w_last.view(Ci, Co, H)
         with _fp32_matmul():
             # d phi: dT = G * W2^T as a GEMM, then the per-pair dots against the gathered features
-            W2 = wl.permute(0, 2, 1).reshape(Ci * H, Co)
-            dT = torch.matmul(grad_out.transpose(1, 2), W2.t())               # [B, No, Ci*H]
+            W2 = wl.permute(0, 2, 1).reshape(Ci * H, Co)                       # [(i,h), j]
+            dT = _gemm_nt(grad_out.transpose(1, 2).reshape(B * No, Co), W2)    # [B*No, Ci*H]
             nsl = L.qc_gather_dot_num_slices(Ci, HP, B)
             dphi = torch.empty((nsl, P, HP), **f32)
             C.check(L.qc_gather_dot(C.ptr(xp), Ni, Ci, C.ptr(dT), C.ptr(row_ptr), C.ptr(pair_col), H, HP,
@@ -319,8 +335,7 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
             C.check(L.qc_gather_accumulate(C.ptr(gp), No, Co, C.ptr(csc_ptr), C.ptr(csc_row), C.ptr(csc_pair),
                                            C.ptr(phi), H, HP, C.ptr(order_in), Ni, B, C.ptr(Tp), st),
                     "qc_gather_accumulate (backward)")
-            W2t = wl.permute(1, 2, 0).reshape(Co * H, Ci)                     # [(j,h), i]
-            d_features = torch.matmul(W2t.t(), Tp.transpose(1, 2)).contiguous()   # [B, Ci, Ni]
+            d_features = _gemm_nt(Tp.view(B * Ni, Co * H), wl.reshape(Ci, Co * H), Ni)   # [B, Ci, Ni]
             x = _unpack(xp, B, Ci, Ni, None)
             dWt = torch.matmul(x.permute(1, 0, 2).reshape(Ci, B * Ni), Tp.reshape(B * Ni, Co * H))   # [i, (j,h)]
             d_w_last = dWt.reshape(Ci * Co, H)

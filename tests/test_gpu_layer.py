@@ -283,6 +283,42 @@ def test_linearity_and_batch_independence_full_size(cuda_lib):
     assert relerr(got.numpy(), yo[:, :, sel.cpu()].numpy()) < TOL
 
 
+def test_dw_last_accuracy_full_size(cuda_lib):
+    """d loss / d W_last at the C3 shape against the defining sum evaluated in float64 (torch on the GPU, pair
+    blocks).  The tcgen05 accumulators of this gradient run for the whole kernel; tcgen05.mma accumulates with
+    truncation, so without the periodic flush of csrc/contract_tc.cu the result drifts to 1.5e-4 at this size
+    while every small-mesh test still passes."""
+    import pytorch_quadconv_b200 as q
+    torch.manual_seed(0)
+    N, Ci, Co, B, H = 100_000, 32, 32, 32, 8
+    pts = torch.rand(N, 3)
+    r = (150 / (4 * np.pi * N)) ** (1 / 3)
+    layer = q.QuadConv(spatial_dim=3, in_points=N, out_points=N, in_channels=Ci, out_channels=Co,
+                       filter_seq=[8, H], output_same=True, decay_param=r).cuda()
+    w = torch.rand(N).cuda() + 0.5
+    pc = pts.cuda()
+    mesh = _StubMesh(pc, pc, w)
+    x = torch.randn(B, Ci, N, device="cuda")
+    y = layer(mesh, x)
+    go = torch.randn_like(y)
+    (y * go).sum().backward()
+    lin = [m for m in layer.filter if isinstance(m, torch.nn.Linear)]
+    got = lin[-1].weight.grad.view(Ci, Co, H).double()
+    with torch.no_grad():
+        ev = layer.eval_indices
+        ref = torch.zeros(Ci, Co, H, dtype=torch.float64, device="cuda")
+        for s0 in range(0, ev.shape[0], 1 << 16):
+            io, ii = ev[s0:s0 + (1 << 16), 0], ev[s0:s0 + (1 << 16), 1]
+            h = (pc[io] - pc[ii]).double()                                   # quadconv.py:250-253 (fp32 subtract)
+            for m in lin[:-1]:
+                h = torch.sin(h @ m.weight.double().t())
+            phi = w.double()[ii].unsqueeze(1) * h                            # [c, H]
+            cp = torch.einsum("bic,bjc->cij", x[:, :, ii].double(), go[:, :, io].double())
+            ref += torch.einsum("cij,ch->ijh", cp, phi)
+    err = float((got - ref).norm() / ref.norm())
+    assert err < TOL, err
+
+
 @pytest.mark.parametrize("d,n", [(2, 700), (3, 500)])
 def test_fused_weight_map_matches_torch_composition(cuda_lib, d, n):
     """MeshHandler.weights() (mesh_handler.py:101-112): fused kernels vs the reference's own op sequence

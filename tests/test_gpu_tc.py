@@ -28,3 +28,22 @@ def test_tcgen05_3xtf32_gemm(cuda_lib):
     C.check(cuda_lib.qc_tc_selftest_ss(C.ptr(A), C.ptr(B), C.ptr(D), C.stream()), "qc_tc_selftest_ss")
     torch.cuda.synchronize()
     assert float((D.double() - ref).norm() / ref.norm()) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K,rpb", [(1000, 40, 68, 0), (1000, 40, 68, 250), (384, 128, 2048, 128), (700, 200, 128, 0),
+                                       (130, 64, 36, 65), (50, 7, 4, 0)])
+def test_tcgen05_gemm_nt_3xtf32(cuda_lib, M, N, K, rpb):
+    """Dense stage of the wide path (csrc/gemm_tc.cu): D = A * B^T in 3xTF32, row-major or per-batch transposed
+    output, ragged M / N / K tiles."""
+    from pytorch_quadconv_b200 import _cabi as C
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = torch.randn(N, K, generator=g).cuda()
+    D = torch.full((M * N,), float("nan"), device="cuda")
+    C.check(cuda_lib.qc_gemm_nt_tf32x3(C.ptr(A), C.ptr(B), C.ptr(D), M, N, K, rpb, C.stream()), "qc_gemm_nt_tf32x3")
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().T                                    # [M, N]
+    if rpb:
+        ref = ref.reshape(M // rpb, rpb, N).transpose(1, 2).contiguous()   # [M/R, N, R]
+    err = float((D.double().reshape(ref.shape) - ref).norm() / ref.norm())
+    assert err < 2e-6, err
