@@ -141,7 +141,11 @@ int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad
 int qc_contract(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, const int* src_idx,
                 const int* phi_idx, const float* phi, int H, int HP, const float* W2, int Cy,
                 const int* order, int Ndst, int B, float* Yp, const float* Zp, float* dW2,
-                void* stream);
+                void* workspace, size_t workspace_bytes, void* stream);
+/* Workspace of the dW2 variant (Zp / dW2 non-NULL): the tensor-core kernel writes partial accumulators there
+ * (tcgen05 accumulates with truncation, so its accumulation chains are kept short).  0 = none needed.  A NULL
+ * or too small workspace makes qc_contract use a stream-ordered allocation instead (slower, not for graphs). */
+size_t qc_contract_workspace_bytes(int Cx, int H, int HP, int Cy, int Ndst, int B);
 
 /* d loss / d phi (grouped by out point):
  *     dT[t; b, c, h] = sum_j Gp[t][j][b] * W3[j][c][h]          W3[j][c][h] = W_last[c*Co+j][h]

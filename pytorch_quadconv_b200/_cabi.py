@@ -46,9 +46,10 @@ _SIGNATURES = {
     "qc_pair_phi_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                 ctypes.POINTER(QcMlp), c_int, c_void_p, c_int, ctypes.POINTER(c_void_p),
                                 c_void_p, c_void_p]),
+    "qc_contract_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "qc_contract": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                             c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                            c_void_p]),
+                            c_void_p, c_size_t, c_void_p]),
     "qc_dphi_num_slices": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "qc_dphi": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                         c_int, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),

@@ -401,10 +401,16 @@ int dispatch_dphi(const DphiArgs& a, int LB, int nksplit, int nblk, cudaStream_t
 
 extern "C" {
 
+size_t qc_contract_workspace_bytes(int Cx, int H, int HP, int Cy, int Ndst, int B)
+{
+    (void)H;
+    return qc_contract_tc_ws_bytes(Ndst, Cx, Cy, HP, B);
+}
+
 int qc_contract(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, const int* src_idx,
                 const int* phi_idx, const float* phi, int H, int HP, const float* W2, int Cy,
                 const int* order, int Ndst, int B, float* Yp, const float* Zp, float* dW2,
-                void* stream)
+                void* workspace, size_t workspace_bytes, void* stream)
 {
     if (Nsrc <= 0 || Ndst <= 0 || Cx <= 0 || Cy <= 0 || B <= 0 || H <= 0 || H > HP) return QC_EINVAL;
     if (!(HP == 4 || HP == 8 || HP == 16 || HP == 32)) return QC_EUNSUP;
@@ -415,6 +421,7 @@ int qc_contract(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, const int
     const int NKC = qc_ceil_div(Cx, CXC);
     ContractArgs a;
     a.X = Xp; a.Y = Yp; a.Z = Zp; a.dW2 = dW2; a.dW_scratch = nullptr; a.dW_counts = nullptr;
+    a.ws = workspace; a.ws_bytes = workspace_bytes;
     a.seg_ptr = seg_ptr; a.src_idx = src_idx; a.phi_idx = phi_idx; a.phi = phi; a.W2 = W2; a.order = order;
     a.Nsrc = Nsrc; a.Ndst = Ndst; a.Cx = Cx; a.Cy = Cy; a.CyP = (Cy + 3) & ~3; a.CyS = (Cy + 31) & ~31;
     a.H = H; a.LB = ilog2(Bp);

@@ -10,6 +10,8 @@ struct ContractArgs {
     float* dW2;
     float* dW_scratch;   // tcgen05 dW variant: per-CTA slots of partial dW2 accumulators [cta][slot][chunk][64][32]
     int* dW_counts;      // ... and the number of slots every CTA wrote
+    void* ws;            // caller-provided workspace for the above (may be null: stream-ordered allocation)
+    size_t ws_bytes;
     const int* seg_ptr;
     const int* src_idx;
     const int* phi_idx;
@@ -34,6 +36,7 @@ struct DphiArgs {
 // Fast paths (contract_fast.cu).  Return 1 when the shape is handled, 0 when the caller must
 // fall back to the generic kernel, <0 / cudaError on failure.
 int qc_contract_tc(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t st);
+size_t qc_contract_tc_ws_bytes(int Ndst, int Cx, int Cy, int HP, int B);   // dW variant; 0 when the shape is not served
 int qc_contract_fast(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t st);
 int qc_dphi_tc(const DphiArgs& a, int HP, int B, cudaStream_t st);
 int qc_dphi_fast(const DphiArgs& a, int HP, int B, cudaStream_t st);

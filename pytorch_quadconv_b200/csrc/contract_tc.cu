@@ -487,8 +487,9 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
         const int nslots = (max_commits - 1) / DW_FLUSH + 1;
         const int nctas = gx * nblk, per = nkc * 64 * 32;
         const size_t fbytes = (size_t)nctas * nslots * per * sizeof(float);
-        char* buf = nullptr;
-        QC_CUDA(cudaMallocAsync((void**)&buf, fbytes + (size_t)nctas * sizeof(int), st));
+        char* buf = reinterpret_cast<char*>(a.ws);
+        const bool own = buf == nullptr || a.ws_bytes < fbytes + (size_t)nctas * sizeof(int);
+        if (own) QC_CUDA(cudaMallocAsync((void**)&buf, fbytes + (size_t)nctas * sizeof(int), st));
         a2.dW_scratch = reinterpret_cast<float*>(buf);
         a2.dW_counts = reinterpret_cast<int*>(buf + fbytes);
         k_contract_tc<HP, KCH, LB, DW, NW><<<grid, NW * 32, smem, st>>>(a2, nkc, nslots);
@@ -498,7 +499,7 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
                                                                                  a.Cx, a.H, a.Cy, a.CyP, a.dW2);
             le = cudaGetLastError();
         }
-        cudaFreeAsync(buf, st);
+        if (own) cudaFreeAsync(buf, st);
         if (le != cudaSuccess) return (int)le;
         return 1;
     }
@@ -873,6 +874,22 @@ int launch_dtc(const DphiArgs& a, int B, cudaStream_t st)
 }
 
 }  // namespace
+
+size_t qc_contract_tc_ws_bytes(int Ndst, int Cx, int Cy, int HP, int B)
+{
+    // mirrors launch_tc<.., DW = true, NW = 8>: slots of partial dW2 accumulators + one counter per CTA
+    const int Bp = qc_bp(B), nblk = qc_nblk(B);
+    if (Cy > 32 || !(HP == 4 || HP == 8) || !(Bp == 8 || Bp == 32)) return 0;
+    const int nkc = qc_ceil_div(Cx, 64 / HP), ppw = 32 / Bp;
+    const int ntiles = qc_ceil_div(Ndst, 8 * ppw);
+    int gx = qc_ceil_div(qc_num_sms(), nblk);
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    const int max_commits = qc_ceil_div(ntiles, gx) * 2 * nkc;
+    const int nslots = (max_commits - 1) / DW_FLUSH + 1;
+    const size_t nctas = (size_t)gx * nblk;
+    return nctas * nslots * ((size_t)nkc * 64 * 32) * sizeof(float) + nctas * sizeof(int);
+}
 
 int qc_contract_tc(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t st)
 {

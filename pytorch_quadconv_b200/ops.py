@@ -264,7 +264,7 @@ def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor
     C.check(L.qc_repack_wlast(C.ptr(w_last), Ci, Co, H, HP, 0, C.ptr(W2), st), "qc_repack_wlast")
     yp = torch.empty(_packed_shape(B, Co, No), dtype=torch.float32, device=dev)
     C.check(L.qc_contract(C.ptr(xp), Ni, Ci, C.ptr(row_ptr), C.ptr(pair_col), None, C.ptr(phi), H, HP,
-                          C.ptr(W2), Co, C.ptr(order_out), No, B, C.ptr(yp), None, None, st), "qc_contract")
+                          C.ptr(W2), Co, C.ptr(order_out), No, B, C.ptr(yp), None, None, None, 0, st), "qc_contract")
     b2 = None
     if bias is not None:
         b2 = _f32c(bias, "bias").reshape(Co, No)
@@ -362,8 +362,11 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
     C.check(L.qc_repack_wlast(C.ptr(w_last), Ci, Co, H, HP, 1, C.ptr(W2t), st), "qc_repack_wlast")
     dW2 = torch.zeros((Co * H, CiP), **f32)
     dxp = torch.empty(_packed_shape(B, Ci, Ni), **f32)
+    ws_bytes = L.qc_contract_workspace_bytes(Co, H, HP, Ci, Ni, B)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
     C.check(L.qc_contract(C.ptr(gp), No, Co, C.ptr(csc_ptr), C.ptr(csc_row), C.ptr(csc_pair), C.ptr(phi), H, HP,
-                          C.ptr(W2t), Ci, C.ptr(order_in), Ni, B, C.ptr(dxp), C.ptr(xp), C.ptr(dW2), st),
+                          C.ptr(W2t), Ci, C.ptr(order_in), Ni, B, C.ptr(dxp), C.ptr(xp), C.ptr(dW2),
+                          C.ptr(ws), ws_bytes, st),
             "qc_contract (backward)")
     d_w_last = torch.zeros((Ci * Co, H), **f32)
     C.check(L.qc_unpack_dwlast(C.ptr(dW2), Ci, Co, H, C.ptr(d_w_last), st), "qc_unpack_dwlast")
