@@ -11,8 +11,8 @@
 // (the fourth GEMM of the path, dW = X * T', reduces over the ROW index of T' and stays on cuBLAS.)
 //
 // One CTA = 4 warps = a 128-row x BN-column tile with the accumulator in TMEM.  Per 32-wide K chunk
-// every thread fetches its A row piece (and B row piece) with 128-bit loads one chunk ahead, splits it
-// into tf32 hi / lo and writes it as 16-byte pieces into the canonical K-major no-swizzle operand tiles
+// the warps fetch the A (and B) rows with 128-bit loads one chunk ahead, split them
+// into tf32 hi / lo and write them as 16-byte pieces into the canonical K-major no-swizzle operand tiles
 // of a two-stage shared-memory ring; one thread issues the 12 MMAs of the chunk and commits them to the
 // stage's mbarrier, which the loaders wait on before they overwrite that stage.
 //
@@ -39,13 +39,12 @@ struct GemmArgs {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, BN == 64 ? 2 : 1)
 k_gemm_tf32x3(const GemmArgs g)
 {
     constexpr int A_TILE = 128 * GK;             // floats per A tile (hi or lo)
     constexpr int B_TILE = BN * GK;
     constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    constexpr int BROWS = (BN + 127) / 128;      // B rows per thread (BN <= 128 -> 1)
     static_assert(BN == 64 || BN == 128, "tile widths");
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bars[GSTAGES];
@@ -67,38 +66,42 @@ k_gemm_tf32x3(const GemmArgs g)
     tc::fence_after_sync();
     const uint32_t tmem = tmem_base_s;
 
-    const long long m = m0 + tid;
+    const long long m = m0 + tid;          // epilogue: this thread's output row (TMEM lane)
     const bool mvalid = m < g.M;
-    const float* arow = g.A + (mvalid ? m : 0) * (long long)g.K;
-    const int nrow = n0 + tid;                                  // this thread's B row (BN <= 128)
-    const bool nvalid = tid < BN && nrow < g.N;
-    const float* brow = g.B + (long long)(nvalid ? nrow : 0) * g.K;
     const int nk = (g.K + GK - 1) / GK;
+    const int lane = tid & 31;
 
+    // Loader mapping: a warp moves 32 rows x 128 bytes per chunk with 8 128-bit loads per lane.  In load j the
+    // lane handles row (j/2)*8 + lane%8 of the warp's 32 and the 16-byte piece q = (j%2)*4 + lane/8: eight
+    // lanes share a 64-byte run of one row (8 cache lines per instruction instead of 32 with one row per
+    // lane), and the eight lanes of a quarter-warp write one contiguous 128-byte core matrix (no bank conflicts).
     float4 ra[GK / 4], rb[GK / 4];
     auto fetch = [&](int kc) {
         const int k0 = kc * GK;
 #pragma unroll
-        for (int q = 0; q < GK / 4; ++q) {
-            ra[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            rb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < GK / 4; ++j) {
+            const int rl = warp * 32 + (j >> 1) * 8 + (lane & 7), q = (j & 1) * 4 + (lane >> 3);
+            ra[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k0 + 4 * q < g.K) {   // K is a multiple of 4 (checked by the host)
-                if (mvalid) ra[q] = __ldg(reinterpret_cast<const float4*>(arow + k0) + q);
-                if (nvalid) rb[q] = __ldg(reinterpret_cast<const float4*>(brow + k0) + q);
+                if (m0 + rl < g.M) ra[j] = __ldg(reinterpret_cast<const float4*>(g.A + (m0 + rl) * (long long)g.K + k0) + q);
+                if (rl < BN && n0 + rl < g.N)
+                    rb[j] = __ldg(reinterpret_cast<const float4*>(g.B + (long long)(n0 + rl) * g.K + k0) + q);
             }
         }
     };
-    auto split_store = [&](float* hi_t, float* lo_t, int row, const float4 (&r)[GK / 4]) {
+    auto split_store = [&](float* hi_t, float* lo_t, const float4 (&r)[GK / 4]) {
 #pragma unroll
-        for (int q = 0; q < GK / 4; ++q) {
-            const float v[4] = {r[q].x, r[q].y, r[q].z, r[q].w};
+        for (int j = 0; j < GK / 4; ++j) {
+            const int rl = warp * 32 + (j >> 1) * 8 + (lane & 7), q = (j & 1) * 4 + (lane >> 3);
+            const float v[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
             float h[4], l[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 h[e] = __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
                 l[e] = v[e] - h[e];
             }
-            const uint32_t off = tc::kmajor_off_bytes(row, 4 * q, GK) / 4;
+            const uint32_t off = tc::kmajor_off_bytes(rl, 4 * q, GK) / 4;
             *reinterpret_cast<float4*>(hi_t + off) = make_float4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<float4*>(lo_t + off) = make_float4(l[0], l[1], l[2], l[3]);
         }
@@ -134,8 +137,8 @@ k_gemm_tf32x3(const GemmArgs g)
             tc::mbar_wait(&bars[s], phase[s] & 1);
             ++phase[s];
         }
-        split_store(st, st + A_TILE, tid, ra);
-        if (tid < BN) split_store(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, tid, rb);
+        split_store(st, st + A_TILE, ra);
+        if (warp * 32 < BN) split_store(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, rb);
         if (kc + 1 < nk) fetch(kc + 1);     // in flight while this chunk is multiplied
         const int gi = kc / GROUP;
         if (kc % GROUP == GROUP / 2 && gi >= 1) {   // the previous group finished long ago: no stall
