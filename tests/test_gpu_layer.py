@@ -283,11 +283,12 @@ def test_linearity_and_batch_independence_full_size(cuda_lib):
     assert relerr(got.numpy(), yo[:, :, sel.cpu()].numpy()) < TOL
 
 
-def test_dw_last_accuracy_full_size(cuda_lib):
-    """d loss / d W_last at the C3 shape against the defining sum evaluated in float64 (torch on the GPU, pair
-    blocks).  The tcgen05 accumulators of this gradient run for the whole kernel; tcgen05.mma accumulates with
-    truncation, so without the periodic flush of csrc/contract_tc.cu the result drifts to 1.5e-4 at this size
-    while every small-mesh test still passes."""
+def test_gradients_full_size(cuda_lib):
+    """Every parameter gradient (and a spot check of the feature gradient) at the C3 shape against the defining sums evaluated in float64 (torch on the
+    GPU, pair blocks): d W_last, the hidden filter weights and the quadrature weights.  The tcgen05
+    accumulators of d W_last run for the whole kernel; tcgen05.mma accumulates with truncation, so without the
+    periodic flush of csrc/contract_tc.cu that gradient drifts to 1.5e-4 at this size while every small-mesh
+    test still passes."""
     import pytorch_quadconv_b200 as q
     torch.manual_seed(0)
     N, Ci, Co, B, H = 100_000, 32, 32, 32, 8
@@ -295,28 +296,53 @@ def test_dw_last_accuracy_full_size(cuda_lib):
     r = (150 / (4 * np.pi * N)) ** (1 / 3)
     layer = q.QuadConv(spatial_dim=3, in_points=N, out_points=N, in_channels=Ci, out_channels=Co,
                        filter_seq=[8, H], output_same=True, decay_param=r).cuda()
-    w = torch.rand(N).cuda() + 0.5
+    w = (torch.rand(N).cuda() + 0.5).requires_grad_()
     pc = pts.cuda()
     mesh = _StubMesh(pc, pc, w)
-    x = torch.randn(B, Ci, N, device="cuda")
+    x = torch.randn(B, Ci, N, device="cuda", requires_grad=True)
     y = layer(mesh, x)
     go = torch.randn_like(y)
     (y * go).sum().backward()
+    x_grad = x.grad
+    x = x.detach()
     lin = [m for m in layer.filter if isinstance(m, torch.nn.Linear)]
-    got = lin[-1].weight.grad.view(Ci, Co, H).double()
-    with torch.no_grad():
-        ev = layer.eval_indices
-        ref = torch.zeros(Ci, Co, H, dtype=torch.float64, device="cuda")
-        for s0 in range(0, ev.shape[0], 1 << 16):
-            io, ii = ev[s0:s0 + (1 << 16), 0], ev[s0:s0 + (1 << 16), 1]
-            h = (pc[io] - pc[ii]).double()                                   # quadconv.py:250-253 (fp32 subtract)
-            for m in lin[:-1]:
-                h = torch.sin(h @ m.weight.double().t())
-            phi = w.double()[ii].unsqueeze(1) * h                            # [c, H]
+    got_last = lin[-1].weight.grad.view(Ci, Co, H).double()
+    # float64 reference: per pair block, C[c,i,j] = sum_b x[b,i,in] go[b,j,out]; dW_last += C (x) phi;
+    # dphi = C : W_last, pushed back through the hidden layers and the quadrature weight by autograd
+    hid = [m.weight.detach().double().requires_grad_() for m in lin[:-1]]
+    w64 = w.detach().double().requires_grad_()
+    wl = lin[-1].weight.detach().double().view(Ci, Co, H)
+    ev = layer.eval_indices
+    ref_last = torch.zeros(Ci, Co, H, dtype=torch.float64, device="cuda")
+    for s0 in range(0, ev.shape[0], 1 << 16):
+        io, ii = ev[s0:s0 + (1 << 16), 0], ev[s0:s0 + (1 << 16), 1]
+        h = (pc[io] - pc[ii]).double()                                       # quadconv.py:250-253 (fp32 subtract)
+        for W in hid:
+            h = torch.sin(h @ W.t())
+        phi = w64[ii].unsqueeze(1) * h                                       # [c, H]
+        with torch.no_grad():
             cp = torch.einsum("bic,bjc->cij", x[:, :, ii].double(), go[:, :, io].double())
-            ref += torch.einsum("cij,ch->ijh", cp, phi)
-    err = float((got - ref).norm() / ref.norm())
-    assert err < TOL, err
+            ref_last += torch.einsum("cij,ch->ijh", cp, phi)
+            dphi = torch.einsum("cij,ijh->ch", cp, wl)
+        (phi * dphi).sum().backward()
+    assert float((got_last - ref_last).norm() / ref_last.norm()) < TOL
+    for m, W in zip(lin[:-1], hid):
+        assert float((m.weight.grad.double() - W.grad).norm() / W.grad.norm()) < TOL
+    assert float((w.grad.double() - w64.grad).norm() / w64.grad.norm()) < TOL
+    # d features at a few in-points: dX[b,i,n] = sum_{p: in(p)=n} sum_{j,h} phi[p][h] W_last[i,j,h] go[b,j,out(p)]
+    with torch.no_grad():
+        sel = torch.tensor([0, 12_345, N - 1], device="cuda")
+        for n in sel.tolist():
+            pm = ev[:, 1] == n
+            io = ev[pm, 0]
+            h = (pc[io] - pc[n]).double()
+            for W in hid:
+                h = torch.sin(h @ W.t())
+            phi = w64[n] * h
+            ref = torch.einsum("ch,ijh,bjc->bi", phi, wl, go[:, :, io].double())
+            assert ref.shape == (B, Ci)
+            sel_grad = x_grad[:, :, n].double()
+            assert float((sel_grad - ref).norm() / ref.norm()) < TOL
 
 
 @pytest.mark.parametrize("d,n", [(2, 700), (3, 500)])
