@@ -10,11 +10,12 @@
 //     dX = T' * W2t^T  (A = T'  [B*Ni x Co*H], B = W2t^T[Ci   x Co*H])      output transposed per batch
 // (the fourth GEMM of the path, dW = X * T', reduces over the ROW index of T' and stays on cuBLAS.)
 //
-// One CTA = 8 warps = a 128-row x BN-column tile with the accumulator in TMEM.  Per 32-wide K chunk
-// the warps fetch the A (and B) rows with 128-bit loads three chunks ahead (register ring), split them
-// into tf32 hi / lo and write them as 16-byte pieces into the canonical K-major no-swizzle operand tiles
-// of a two-stage shared-memory ring; one thread issues the 12 MMAs of the chunk and commits them to the
-// stage's mbarrier, which the loaders wait on before they overwrite that stage.
+// One CTA = 8 warps = a 128-row x BN-column tile with the accumulator in TMEM.  The 32-wide K chunks of
+// A and B arrive by cp.async (two chunks ahead; FIFO commit groups, because register prefetching is serialised
+// by ptxas' single-scoreboard allocation) straight into 128-byte-swizzled K-major operand tiles: the tensor core
+// reads only the upper 19 bits of an fp32 operand, so the raw tile IS the tf32 hi operand (verified: identical
+// results with and without masking); every thread then derives the lo tile (v - trunc(v)) from the pieces it
+// copied itself, one thread issues the 12 MMAs of the chunk and commits them to the stage's mbarrier.
 //
 // tcgen05.mma accumulates with truncation (~2e-8 relative per MMA, measured: 1.5e-5 after K = 2048), so the
 // TMEM accumulation only runs over groups of GROUP chunks (48 MMAs); two TMEM accumulators alternate, and
@@ -26,7 +27,6 @@
 namespace {
 
 constexpr int GK = 32;        // K chunk
-constexpr int GSTAGES = 2;
 constexpr int GROUP = 4;      // K chunks accumulated in TMEM before the partial sum moves to registers
 
 struct GemmArgs {
@@ -39,21 +39,25 @@ struct GemmArgs {
 };
 
 constexpr int GTHREADS = 256;
-constexpr int PD = 3;         // K chunks fetched ahead (register ring)
+constexpr int RAW = 4;        // stages of the raw (= hi) operand ring filled by cp.async
+constexpr int LOS = 2;        // stages of the lo operand tiles
+constexpr int AHEAD = 2;      // K chunks in flight ahead of the one being multiplied
 
 template <int BN>
 __global__ void __launch_bounds__(GTHREADS, 1)
 k_gemm_tf32x3(const GemmArgs g)
 {
-    constexpr int A_TILE = 128 * GK;             // floats per A tile (hi or lo)
+    constexpr int A_TILE = 128 * GK;             // floats per A tile
     constexpr int B_TILE = BN * GK;
-    constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+    constexpr int TILE = A_TILE + B_TILE;        // one stage: A tile then B tile
     constexpr int HN = BN / 2;                   // output columns per thread (two threads share a row)
     static_assert(BN == 64 || BN == 128, "tile widths");
     extern __shared__ __align__(1024) float smem_raw[];
-    // operand tiles use the 128-byte swizzle: 1 KB alignment
-    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bars[GSTAGES];
+    // operand tiles use the 128-byte swizzle: 1 KB alignment.  [RAW][TILE] raw fp32 (the tensor core reads the
+    // upper 19 bits, i.e. the raw tile IS the tf32 "hi" operand), then [LOS][TILE] lo = v - trunc(v)
+    float* raw_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* lo_s = raw_s + (size_t)RAW * TILE;
+    __shared__ __align__(8) uint64_t bars[RAW];    // MMAs of the chunk that used raw stage i have finished
     __shared__ __align__(8) uint64_t gbars[2];     // one per TMEM accumulator: its group of MMAs has finished
     __shared__ uint32_t tmem_base_s;
 
@@ -64,7 +68,7 @@ k_gemm_tf32x3(const GemmArgs g)
     const int n0 = blockIdx.y * BN;
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 2 * BN);
     if (tid == 0) {
-        for (int i = 0; i < GSTAGES; ++i) tc::mbar_init(&bars[i], 1);
+        for (int i = 0; i < RAW; ++i) tc::mbar_init(&bars[i], 1);
         tc::mbar_init(&gbars[0], 1);
         tc::mbar_init(&gbars[1], 1);
         tc::mbar_fence_init();
@@ -78,50 +82,57 @@ k_gemm_tf32x3(const GemmArgs g)
     const bool mvalid = m < g.M;
     const int nk = (g.K + GK - 1) / GK;
 
-    // Loader mapping: the 8 warps move 128 rows x 128 bytes per chunk with four 128-bit loads per lane.  Warp
-    // (wq, wh) covers rows wq*32.. and the K half wh; in load j the lane handles row j*8 + lane%8 of those 32 and
-    // the 16-byte piece q = wh*4 + lane/8: eight lanes share a 64-byte run of one row, and the eight lanes of a
-    // quarter-warp write one contiguous 128-byte core matrix (no bank conflicts).  PD chunks are in flight.
-    float4 ra[PD][4], rb[PD][4];
-    auto fetch = [&](float4 (&xa)[4], float4 (&xb)[4], int kc) {
+    // Copy mapping: the 8 warps move 128 rows x 128 bytes per chunk with four 16-byte cp.async per lane.  Warp
+    // (wq, wh) covers rows wq*32.. and the K half wh; in copy j the lane handles row j*8 + lane%8 of those 32 and
+    // the 16-byte piece q = wh*4 + lane/8 (eight lanes share a 64-byte run of one row).  Destination: K-major,
+    // SWIZZLE_128B -- a row is one 128-byte line (GK = 32 floats), 8 rows form a 1 KB atom, the piece index is
+    // XORed with the row index inside the atom.  Every thread later reads back exactly the pieces it copied.
+    const int q = wh * 4 + (lane >> 3);
+    uint32_t poff[4];                            // byte offsets of this thread's pieces inside an A or B tile
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int rl = wq * 32 + j * 8 + (lane & 7);
+        poff[j] = (uint32_t)((rl >> 3) * 1024 + (rl & 7) * 128 + ((q ^ (rl & 7)) * 16));
+    }
+    const bool has_b = wq * 32 < BN;
+    auto issue = [&](int kc) {
         const int k0 = kc * GK;
-        const int q = wh * 4 + (lane >> 3);
+        const bool kv = k0 + 4 * q < g.K;        // K is a multiple of 4 (checked by the host)
+        const uint32_t st = tc::smem_u32(raw_s + (size_t)(kc % RAW) * TILE);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int rl = wq * 32 + j * 8 + (lane & 7);
-            xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            xb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k0 + 4 * q < g.K) {   // K is a multiple of 4 (checked by the host)
-                if (m0 + rl < g.M) xa[j] = __ldg(reinterpret_cast<const float4*>(g.A + (m0 + rl) * (long long)g.K + k0) + q);
-                if (rl < BN && n0 + rl < g.N)
-                    xb[j] = __ldg(reinterpret_cast<const float4*>(g.B + (long long)(n0 + rl) * g.K + k0) + q);
+            const bool av = kv && m0 + rl < g.M;
+            tc::cp_async16_zfill(st + poff[j], g.A + (av ? (m0 + rl) * (long long)g.K + k0 + 4 * q : 0), av);
+            if (has_b) {
+                const bool bv = kv && n0 + rl < g.N;
+                tc::cp_async16_zfill(st + A_TILE * 4 + poff[j], g.B + (bv ? (long long)(n0 + rl) * g.K + k0 + 4 * q : 0), bv);
             }
         }
     };
-    auto split_store = [&](float* hi_t, float* lo_t, const float4 (&r)[4]) {
-        const int q = wh * 4 + (lane >> 3);
+    auto make_lo = [&](int kc) {
+        const float* rs = raw_s + (size_t)(kc % RAW) * TILE;
+        float* ls = lo_s + (size_t)(kc % LOS) * TILE;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int rl = wq * 32 + j * 8 + (lane & 7);
-            const float v[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
-            float h[4], l[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                h[e] = __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
-                l[e] = v[e] - h[e];
+            for (int t = 0; t < 2; ++t) {
+                if (t == 1 && !has_b) continue;
+                const uint32_t o = (t * A_TILE * 4 + poff[j]) / 4;
+                const float4 v = *reinterpret_cast<const float4*>(rs + o);
+                float4 l;
+                l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                *reinterpret_cast<float4*>(ls + o) = l;
             }
-            // K-major, SWIZZLE_128B: a row is one 128-byte line (GK = 32 floats), 8 rows form a 1 KB atom and
-            // the 16-byte piece index is XORed with the row index inside the atom (conflict-free operand fetch)
-            const uint32_t off = (uint32_t)((rl >> 3) * 1024 + (rl & 7) * 128 + ((q ^ (rl & 7)) * 16)) / 4;
-            *reinterpret_cast<float4*>(hi_t + off) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(lo_t + off) = make_float4(l[0], l[1], l[2], l[3]);
         }
     };
 
     const uint32_t idesc = tc::make_idesc_tf32(128, BN);
     constexpr uint32_t SBO = 1024;                      // between 8-row atoms
     constexpr uint64_t SW128 = (uint64_t)2 << 61;       // descriptor layout type SWIZZLE_128B
-    uint32_t phase0 = 0u, phase1 = 0u;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     const int ngroups = (nk + GROUP - 1) / GROUP;
     float acc[HN];
@@ -142,49 +153,43 @@ k_gemm_tf32x3(const GemmArgs g)
     };
 
 #pragma unroll
-    for (int u = 0; u < PD; ++u)
-        if (u < nk) fetch(ra[u], rb[u], u);
-    for (int kc0 = 0; kc0 < nk; kc0 += PD) {
+    for (int u = 0; u < AHEAD; ++u) {
+        if (u < nk) issue(u);
+        tc::cp_async_commit();
+    }
+    for (int kc = 0; kc < nk; ++kc) {
+        // chunk kc-2 used raw stage (kc+2) % RAW and lo stage kc % LOS: both are free once its MMAs are done
+        if (kc >= 2) tc::mbar_wait(&bars[(kc - 2) % RAW], ((kc - 2) / RAW) & 1);
+        if (kc + AHEAD < nk) issue(kc + AHEAD);
+        tc::cp_async_commit();
+        tc::cp_async_wait<AHEAD>();                  // this thread's copies of chunk kc have landed
+        make_lo(kc);
+        const int gi = kc / GROUP;
+        if (kc % GROUP == GROUP / 2 && gi >= 1) {    // the previous group finished long ago: no stall
+            take_group(gi - 1);
+            gread = gi;
+        }
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t ahi = tc::smem_u32(raw_s + (size_t)(kc % RAW) * TILE), bhi = ahi + A_TILE * 4;
+            const uint32_t alo = tc::smem_u32(lo_s + (size_t)(kc % LOS) * TILE), blo = alo + A_TILE * 4;
 #pragma unroll
-        for (int u = 0; u < PD; ++u) {
-            const int kc = kc0 + u;
-            if (kc >= nk) break;                 // block-uniform
-            const int s = kc % GSTAGES;
-            float* st = smem + (size_t)s * STAGE;
-            if (kc >= GSTAGES) {   // the MMAs that read this stage two chunks ago have finished
-                if (s == 0) { tc::mbar_wait(&bars[0], phase0 & 1); ++phase0; }
-                else        { tc::mbar_wait(&bars[1], phase1 & 1); ++phase1; }
+            for (int ks = 0; ks < GK / 8; ++ks) {
+                // one k-step = 8 tf32 = 32 bytes along the (unswizzled) row; LBO is not used by swizzled K-major tiles
+                const uint64_t dah = tc::make_smem_desc(ahi + ks * 32, 16, SBO) | SW128;
+                const uint64_t dal = tc::make_smem_desc(alo + ks * 32, 16, SBO) | SW128;
+                const uint64_t dbh = tc::make_smem_desc(bhi + ks * 32, 16, SBO) | SW128;
+                const uint64_t dbl = tc::make_smem_desc(blo + ks * 32, 16, SBO) | SW128;
+                const uint32_t d = tmem + (gi & 1) * BN;
+                tc::mma_tf32_ss(d, dah, dbh, idesc, !(kc % GROUP == 0 && ks == 0));
+                tc::mma_tf32_ss(d, dal, dbh, idesc, true);
+                tc::mma_tf32_ss(d, dah, dbl, idesc, true);
             }
-            split_store(st, st + A_TILE, ra[u]);
-            if (wq * 32 < BN) split_store(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, rb[u]);
-            if (kc + PD < nk) fetch(ra[u], rb[u], kc + PD);     // in flight while the next chunks are multiplied
-            const int gi = kc / GROUP;
-            if (kc % GROUP == GROUP / 2 && gi >= 1) {   // the previous group finished long ago: no stall
-                take_group(gi - 1);
-                gread = gi;
-            }
-            tc::fence_proxy_async();
-            tc::fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc::fence_after_sync();
-                const uint32_t ahi = tc::smem_u32(st), alo = ahi + A_TILE * 4;
-                const uint32_t bhi = ahi + 2 * A_TILE * 4, blo = bhi + B_TILE * 4;
-#pragma unroll
-                for (int ks = 0; ks < GK / 8; ++ks) {
-                    // one k-step = 8 tf32 = 32 bytes along the (unswizzled) row; LBO is not used by swizzled K-major tiles
-                    const uint64_t dah = tc::make_smem_desc(ahi + ks * 32, 16, SBO) | SW128;
-                    const uint64_t dal = tc::make_smem_desc(alo + ks * 32, 16, SBO) | SW128;
-                    const uint64_t dbh = tc::make_smem_desc(bhi + ks * 32, 16, SBO) | SW128;
-                    const uint64_t dbl = tc::make_smem_desc(blo + ks * 32, 16, SBO) | SW128;
-                    const uint32_t d = tmem + (gi & 1) * BN;
-                    tc::mma_tf32_ss(d, dah, dbh, idesc, !(kc % GROUP == 0 && ks == 0));
-                    tc::mma_tf32_ss(d, dal, dbh, idesc, true);
-                    tc::mma_tf32_ss(d, dah, dbl, idesc, true);
-                }
-                tc::mma_commit(&bars[s]);
-                if (kc % GROUP == GROUP - 1 || kc == nk - 1) tc::mma_commit(&gbars[gi & 1]);
-            }
+            tc::mma_commit(&bars[kc % RAW]);
+            if (kc % GROUP == GROUP - 1 || kc == nk - 1) tc::mma_commit(&gbars[gi & 1]);
         }
     }
     // the groups not yet taken (their commits also cover every stage's last MMAs)
@@ -202,13 +207,13 @@ k_gemm_tf32x3(const GemmArgs g)
         } else {
             float* dst = g.D + m * g.N + nb;
 #pragma unroll
-            for (int q = 0; q < HN / 4; ++q) {
-                if ((g.N & 3) == 0 && nb + 4 * q + 4 <= g.N) {
-                    reinterpret_cast<float4*>(dst)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            for (int q4 = 0; q4 < HN / 4; ++q4) {
+                if ((g.N & 3) == 0 && nb + 4 * q4 + 4 <= g.N) {
+                    reinterpret_cast<float4*>(dst)[q4] = make_float4(acc[4 * q4], acc[4 * q4 + 1], acc[4 * q4 + 2], acc[4 * q4 + 3]);
                 } else {
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
-                        if (nb + 4 * q + e < g.N) dst[4 * q + e] = acc[4 * q + e];
+                        if (nb + 4 * q4 + e < g.N) dst[4 * q4 + e] = acc[4 * q4 + e];
                 }
             }
         }
@@ -221,7 +226,7 @@ k_gemm_tf32x3(const GemmArgs g)
 template <int BN>
 int launch_gemm(const GemmArgs& g, cudaStream_t st)
 {
-    const size_t smem = (size_t)GSTAGES * (2 * 128 * GK + 2 * BN * GK) * 4 + 1024;
+    const size_t smem = (size_t)(RAW + LOS) * (128 * GK + BN * GK) * 4 + 1024;
     QC_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long mt = (g.M + 127) / 128;
     const int nt = (g.N + BN - 1) / BN;
