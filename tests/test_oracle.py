@@ -60,3 +60,32 @@ def test_pool_index_and_values_match_reference():
     assert torch.equal(y1, torch.from_numpy(g["y1"]))
     z1 = O.maxpool_adjoint(y1, torch.from_numpy(g["index_up1"]))
     assert torch.equal(z1, torch.from_numpy(g["z1"]))
+
+
+def test_bf16_operand_mode_of_the_oracle():
+    """The product's `filter_dtype=torch.bfloat16` mode is not in the reference; its oracle (filter_mlp with
+    operand_bf16=True) must be exactly 'every Linear sees bf16-rounded weights and inputs, accumulation in the
+    working precision', with unrounded (straight-through) gradients."""
+    from oracle import quadconv_oracle as O
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(50, 2, generator=g, dtype=torch.float64)
+    ws = [torch.randn(8, 2, generator=g, dtype=torch.float64), torch.randn(8, 8, generator=g, dtype=torch.float64),
+          torch.randn(6, 8, generator=g, dtype=torch.float64)]
+    rnd = lambda t: t.float().bfloat16().double()
+    h = z
+    for l, W in enumerate(ws):
+        h = rnd(h) @ rnd(W).t()
+        if l + 1 < len(ws):
+            h = torch.sin(h)
+    got = O.filter_mlp(ws, z, operand_bf16=True)
+    assert torch.equal(got, h)
+    assert not torch.equal(got, O.filter_mlp(ws, z))                 # the mode really rounds
+    # straight-through: the gradient w.r.t. the last weight is the (rounded) last activation, not a bf16 value
+    wl = ws[-1].clone().requires_grad_()
+    O.filter_mlp(ws[:-1] + [wl], z, operand_bf16=True).sum().backward()
+    a_last = z
+    for W in ws[:-1]:
+        a_last = torch.sin(rnd(a_last) @ rnd(W).t())
+    expect = rnd(a_last).sum(0).expand(6, 8)
+    assert torch.allclose(wl.grad, expect, rtol=1e-12, atol=1e-12)
+    assert (wl.grad != rnd(wl.grad)).any()                           # not quantised to bf16
