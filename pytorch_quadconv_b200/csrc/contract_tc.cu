@@ -1,7 +1,9 @@
 // contract_tc.cu -- tensor-core (tcgen05) version of the fused gather-contract kernel.
 //
 // Stage B (segmented gather-accumulate over the pair list) is irregular, per-pair-unique work and
-// stays on the FP32 pipe exactly as in contract_fast.cu.  Stage C -- the last Linear of the
+// stays on the FP32 pipe: gathers by cp.async into a per-warp shared-memory ring (FIFO commit groups), the
+// staged pair n+1 moved to registers under the packed FMAs (fma.rn.f32x2) of pair n, all per-point control
+// flow warp-uniform.  Stage C -- the last Linear of the
 // reference's filter MLP (quadconv.py:143) folded into the contraction,
 //     Y[row][j] = sum_k T[row][k] * W2[k][j],      row = (point, batch lane), k = (channel, h)
 // -- is a dense GEMM with a shared weight, and runs on the 5th-generation tensor cores:
@@ -16,6 +18,9 @@
 //   * tcgen05.commit -> mbarrier tells the row block when A may be overwritten / D may be read;
 //     the epilogue reads D with tcgen05.ld and stores the packed output rows with 128-bit stores.
 // The MMAs are asynchronous: the FP32 pipe is already gathering the next chunk while they run.
+// tcgen05.mma accumulates with truncation (~2e-8 relative per MMA): D only accumulates the chunks of one tile
+// (96 MMAs at 32 channels), and the dW_last accumulators of the DW variant, which would otherwise run for the
+// whole kernel, are flushed every DW_FLUSH uses (see flush_dw / k_dw_reduce).
 #include <cstdlib>
 #include "contract_args.cuh"
 #include "tc_common.cuh"
