@@ -762,15 +762,26 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                                         }
                                 }
 #pragma unroll
-                                for (int k = 0; k < HP; ++k) acc0[k] += __shfl_xor_sync(0xffffffffu, acc1[k], 16);
+                                for (int k = 0; k < HP; k += 2) {   // adds in pairs (packed FP32 add)
+                                    const float r0 = __shfl_xor_sync(0xffffffffu, acc1[k], 16);
+                                    const float r1 = __shfl_xor_sync(0xffffffffu, acc1[k + 1], 16);
+                                    tc::add2(acc0[k], acc0[k + 1], r0, r1);
+                                }
 #pragma unroll
                                 for (int st = 0; st < LBr; ++st) {
                                     const int mask = 1 << (LBr - 1 - st);
                                     if (st < NH) {
                                         const int half = HP >> (st + 1);
+                                        if (half >= 2) {
 #pragma unroll
-                                        for (int k = 0; k < half; ++k)
-                                            acc0[k] += __shfl_xor_sync(0xffffffffu, acc0[k + half], mask);
+                                            for (int k = 0; k < half; k += 2) {
+                                                const float r0 = __shfl_xor_sync(0xffffffffu, acc0[k + half], mask);
+                                                const float r1 = __shfl_xor_sync(0xffffffffu, acc0[k + 1 + half], mask);
+                                                tc::add2(acc0[k], acc0[k + 1], r0, r1);
+                                            }
+                                        } else {
+                                            acc0[0] += __shfl_xor_sync(0xffffffffu, acc0[1], mask);
+                                        }
                                     } else {
                                         acc0[0] += __shfl_xor_sync(0xffffffffu, acc0[0], mask);
                                     }

@@ -140,6 +140,20 @@ __device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, f
         : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+// Packed FP32 add: (d0, d1) += (a0, a1), each half rounded like a scalar add.
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1)
+{
+    asm("{\n"
+        ".reg .b64 d, a;\n"
+        "mov.b64 d, {%0, %1};\n"
+        "mov.b64 a, {%2, %3};\n"
+        "add.rn.f32x2 d, d, a;\n"
+        "mov.b64 {%0, %1}, d;\n"
+        "}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a0), "f"(a1));
+}
+
 // Shared-memory load the compiler may not sink to its use (used to start a dependent address chain early).
 __device__ __forceinline__ uint32_t lds_u32_early(uint32_t saddr)
 {
