@@ -523,10 +523,11 @@ def main():
     if rank == 0:
         launches = 0
         if is_ae:
-            launches = 8 * 13 + 8 * 2      # 8 QuadConv layers x 13 kernels (fwd+bwd) + 8 pool layers x 2
+            launches = 8 * 14 + 8 * 2      # 8 QuadConv layers x 14 kernels (fwd+bwd) + 8 pool layers x 2
         if table:
-            # every timed C-ABI call launches exactly one of our kernels (csrc/*.cu); memsets are not counted
-            launches = calls_per_step
+            # every timed C-ABI call launches one of our kernels (csrc/*.cu); the dW variant of qc_contract adds
+            # k_dw_reduce, the fused weight map (MeshHandler.weights) three more per step; memsets are not counted
+            launches = calls_per_step + (1 if "qc_contract.bwd" in table else 0) + 3
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
