@@ -81,6 +81,10 @@ int qc_pairs_to_csr(const int64_t* eval_indices, int64_t P, int No, int Ni, int*
 int qc_csc_count(const int* pair_col, int64_t P, int Ni, int* csc_counts, void* stream);
 int qc_csc_fill(const int* pair_row, const int* pair_col, int64_t P, int Ni, const int* csc_ptr,
                 int* cursor, int* csc_pair, int* csc_row, void* stream);
+/* Reorder a processing order (NULL = identity) inside windows of 2048 consecutive entries by segment length
+ * (seg_ptr[p+1] - seg_ptr[p], ascending, ties by position) so that the warps that share a CTA work on segments
+ * of similar length; `out` must not alias `order`. */
+int qc_balance_order(const int* order, const int* seg_ptr, int n, int* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout conversion between the reference's [B,C,N] tensors (quadconv.py:238 docstring) and the

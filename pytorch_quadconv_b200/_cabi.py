@@ -38,6 +38,7 @@ _SIGNATURES = {
     "qc_csc_count": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "qc_csc_fill": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p]),
+    "qc_balance_order": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "qc_pack_features": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qc_unpack_features": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "qc_batch_sum": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -426,6 +426,35 @@ int bin_points(const float* pts, int N, int d, Ws& w, int* cell_of, float* sorte
     return 0;
 }
 
+
+// Reorder the processing order of points inside windows of BAL_W consecutive entries by segment length
+// (ascending, ties by position: deterministic).  The order stays spatially compact (a window of the
+// cell-sorted order), but the four warps of a row block and the CTAs of a wave now work on segments of similar
+// length -- measured at C3: step 11.59 -> 11.39 ms.  One block per window, O(W^2) rank sort in shared memory
+// (a one-time cost of the cached tables).
+constexpr int BAL_W = 2048;
+__global__ void __launch_bounds__(256)
+k_balance_order(const int* __restrict__ order, const int* __restrict__ seg_ptr, int n, int* __restrict__ out)
+{
+    __shared__ int len_s[BAL_W];
+    const int w0 = blockIdx.x * BAL_W;
+    const int cnt = min(BAL_W, n - w0);
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+        const int p = order ? order[w0 + i] : w0 + i;
+        len_s[i] = seg_ptr[p + 1] - seg_ptr[p];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+        const int li = len_s[i];
+        int rank = 0;
+        for (int j = 0; j < cnt; ++j) {
+            const int lj = len_s[j];
+            rank += (lj < li || (lj == li && j < i)) ? 1 : 0;
+        }
+        out[w0 + rank] = order ? order[w0 + i] : w0 + i;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -561,6 +590,14 @@ int qc_csc_fill(const int* pair_row, const int* pair_col, int64_t P, int Ni, con
         k_csc_scatter<<<min(qc_ceil_div(P, 256), qc_num_sms() * 8), 256, 0, st>>>(pair_col, P, csc_ptr, cursor, csc_pair);
         k_csc_sort<<<min(qc_ceil_div((int64_t)Ni * 32, 256), qc_num_sms() * 16), 256, 0, st>>>(csc_ptr, Ni, pair_row, csc_pair, csc_row);
     }
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+int qc_balance_order(const int* order, const int* seg_ptr, int n, int* out, void* stream)
+{
+    if (n <= 0) return 0;
+    k_balance_order<<<qc_ceil_div(n, BAL_W), 256, 0, (cudaStream_t)stream>>>(order, seg_ptr, n, out);
     QC_CHECK_LAUNCH();
     return 0;
 }

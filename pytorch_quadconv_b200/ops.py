@@ -111,6 +111,11 @@ def build_pairs(out_pts: Tensor, in_pts: Tensor, radius: float, same: bool) -> L
                 "qc_search_fill")
     pair_row, pair_col = pair_row[:P], pair_col[:P]
     csc_ptr, csc_pair, csc_row = _csc(pair_row, pair_col, Ni)
+    # within windows of the cell-sorted orders, process segments of similar length together
+    bal_out, bal_in = torch.empty_like(order_out), torch.empty_like(order_in)
+    C.check(L.qc_balance_order(C.ptr(order_out), C.ptr(row_ptr), No, C.ptr(bal_out), C.stream()), "qc_balance_order")
+    C.check(L.qc_balance_order(C.ptr(order_in), C.ptr(csc_ptr), Ni, C.ptr(bal_in), C.stream()), "qc_balance_order")
+    order_out, order_in = bal_out, bal_in
     return [ev, pair_row, pair_col, row_ptr, csc_ptr, csc_pair[:P], csc_row[:P], order_out, order_in]
 
 
