@@ -286,7 +286,7 @@ int launch_bwd(const float* out_pts, const float* in_pts, const float* quad_w, c
 {
     size_t smem = ((size_t)2 * m.n_hidden * WMAX * WMAX + 2 * 128 * WMAX) * 4;
     QC_CUDA(cudaFuncSetAttribute(k_pair_phi_bwd<WMAX, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 4);
+    int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 16);
     k_pair_phi_bwd<WMAX, LT><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w);
     QC_CHECK_LAUNCH();
     return 0;
