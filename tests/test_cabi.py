@@ -28,6 +28,24 @@ def test_header_symbols_exported():
     assert _cabi.lib().qc_search_workspace_bytes(1000, 1000, 4) == 0
 
 
+def test_host_side_shape_queries():
+    """Pure host helpers of the C ABI (no device needed): which shapes the wide path serves, how many d(phi)
+    slices the kernels write, and the workspace of the dW variant (without a GPU the SM count falls back to 148)."""
+    from pytorch_quadconv_b200 import _cabi
+    L = _cabi.lib()
+    assert L.qc_gather_supported(64, 32, 32, 8) == 1          # C4: 64 channels, H = 32, batch 8
+    assert L.qc_gather_supported(64, 32, 32, 32) == 1
+    assert L.qc_gather_supported(64, 32, 32, 2) == 0          # 2 batch lanes: general kernel
+    assert L.qc_gather_supported(64, 40, 32, 8) == 0          # H > HP
+    assert L.qc_gather_dot_num_slices(64, 32, 8) == 1 and L.qc_gather_dot_num_slices(64, 32, 70) == 3
+    assert L.qc_dphi_num_slices(100000, 32, 32, 8, 32) == 4   # C3: one slice per channel chunk
+    assert L.qc_dphi_num_slices(1000, 64, 128, 32, 8) == 1    # not served by the fused kernels
+    ws = L.qc_contract_workspace_bytes(32, 8, 8, 32, 100000, 32)
+    # C3 backward: 148 CTAs x 85 slots x 4 chunks x 64 x 32 floats + one counter per CTA
+    assert ws == 148 * 85 * 4 * 64 * 32 * 4 + 148 * 4
+    assert L.qc_contract_workspace_bytes(64, 32, 32, 128, 10000, 8) == 0   # wide shapes: no tcgen05 dW variant
+
+
 def test_no_cpu_fallback():
     import pytest
     import torch
