@@ -235,6 +235,9 @@ int qc_weight_map_bwd(const float* pts, const int* adj, int M, int E, int d, con
 int qc_tc_selftest(const float* A, const float* B, float* D, void* stream);
 /* Same product with BOTH operands in shared memory (SS mode). Used by tests only. */
 int qc_tc_selftest_ss(const float* A, const float* B, float* D, void* stream);
+/* probe of the operand major-ness for 16-bit operands (kind::f16, bf16): D[128x32] = A[128x32] * B[32x32]^T;
+ * mode bit 0: A MN-major, bit 1: B MN-major (K-major otherwise) */
+int qc_tc_probe_bf16(const float* A, const float* B, float* D, int mode, void* stream);
 
 #ifdef __cplusplus
 }

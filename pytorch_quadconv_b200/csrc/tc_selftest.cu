@@ -3,6 +3,7 @@
 // written to TMEM by the threads (tcgen05.st), B staged in shared memory in the canonical K-major
 // layout, the accumulator read back with tcgen05.ld.  tests/test_gpu_tc.py compares against fp32.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include "tc_common.cuh"
 
 namespace {
@@ -158,7 +159,85 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest_ss(const float* __restri
     if (warp == 0) tc::tmem_dealloc(tmem, 32);
 }
 
+// Probe (not used by the product path): does MN-major work for 16-bit operands?  D[128 x 32] = A[128 x 32] *
+// B[32 x 32]^T with bf16 operands, kind::f16, no swizzle.  mode bit 0: A MN-major, bit 1: B MN-major.
+// Canonical layouts in bytes, T = 8 elements per 16 bytes (cute UMMA INTERLEAVE):
+//   K-major : off(mn, k) = (mn % 8) * 16 + (k % 8) * 2 + (k / 8) * LBO + (mn / 8) * SBO
+//   MN-major: off(mn, k) = (mn % 8) * 2 + (k % 8) * 16 + (mn / 8) * SBO + (k / 8) * LBO
+__global__ void __launch_bounds__(128, 1) k_tc_probe_bf16(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                           float* __restrict__ D, int mode)
+{
+    extern __shared__ __align__(128) unsigned char dyn_b[];
+    __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(dyn_b);              // 128 x 32
+    __nv_bfloat16* Bs = As + 128 * 32;                                          // 32 x 32
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 32);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_fence_init();
+    }
+    constexpr int K = 32;
+    // strides: K-major: LBO = 128 (next 8 k), SBO = (K/8)*128 (next 8 rows); MN-major: SBO = 128 (next 8 mn), LBO = (MN/8)*128
+    auto off = [&](bool mnmaj, int MN, int mn, int k) -> uint32_t {
+        if (!mnmaj) return (uint32_t)((mn % 8) * 16 + (k % 8) * 2 + (k / 8) * 128 + (mn / 8) * ((K / 8) * 128));
+        return (uint32_t)((mn % 8) * 2 + (k % 8) * 16 + (mn / 8) * 128 + (k / 8) * ((MN / 8) * 128));
+    };
+    for (int idx = tid; idx < 128 * K; idx += 128) {
+        const int m = idx / K, k = idx % K;
+        As[off(mode & 1, 128, m, k) / 2] = __float2bfloat16_rn(A[idx]);
+    }
+    for (int idx = tid; idx < 32 * K; idx += 128) {
+        const int n = idx / K, k = idx % K;
+        Bs[off(mode & 2, 32, n, k) / 2] = __float2bfloat16_rn(Bm[idx]);
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        // kind::f16: D fp32 (1 << 4), A/B format bf16 (1 << 7, 1 << 10)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((mode & 1) ? (1u << 15) : 0u) | ((mode & 2) ? (1u << 16) : 0u) |
+                               ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int ks = 0; ks < K / 16; ++ks) {   // K = 16 per MMA = two 8-k groups
+            const uint32_t a0 = tc::smem_u32(As) + ((mode & 1) ? ks * 2 * (128 / 8) * 128 : ks * 256);
+            const uint32_t b0 = tc::smem_u32(Bs) + ((mode & 2) ? ks * 2 * (32 / 8) * 128 : ks * 256);
+            const uint64_t da = (mode & 1) ? tc::make_smem_desc(a0, (128 / 8) * 128, 128) : tc::make_smem_desc(a0, 128, (K / 8) * 128);
+            const uint64_t db = (mode & 2) ? tc::make_smem_desc(b0, (32 / 8) * 128, 128) : tc::make_smem_desc(b0, 128, (K / 8) * 128);
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(ks != 0)) : "memory");
+        }
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    uint32_t q0[16], q1[16];
+    const uint32_t lb = (uint32_t)(warp * 32) << 16;
+    tc::tmem_ld16(lb + tmem, q0);
+    tc::tmem_ld16(lb + tmem + 16, q1);
+    tc::wait_ld();
+    for (int j = 0; j < 16; ++j) {
+        D[(size_t)tid * 32 + j] = __uint_as_float(q0[j]);
+        D[(size_t)tid * 32 + 16 + j] = __uint_as_float(q1[j]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 32);
+}
+
 }  // namespace
+
+extern "C" int qc_tc_probe_bf16(const float* A, const float* B, float* D, int mode, void* stream)
+{
+    const int smem = (128 * 32 + 32 * 32) * 2;
+    k_tc_probe_bf16<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, mode);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int qc_tc_selftest_ss(const float* A, const float* B, float* D, void* stream)
 {

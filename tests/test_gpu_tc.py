@@ -47,3 +47,20 @@ def test_tcgen05_gemm_nt_3xtf32(cuda_lib, M, N, K, rpb):
         ref = ref.reshape(M // rpb, rpb, N).transpose(1, 2).contiguous()   # [M/R, N, R]
     err = float((D.double().reshape(ref.shape) - ref).norm() / ref.norm())
     assert err < 2e-6, err
+
+
+def test_tcgen05_bf16_operand_majorness(cuda_lib):
+    """Building block for a reduced-precision gather stage: with bf16 operands (kind::f16) the shared-memory
+    operands may be MN-major (contiguous along M / N -- the order in which gathered feature rows arrive) as well
+    as K-major; all four combinations give the exact bf16 product.  (The same descriptors with kind::tf32 return
+    zeros for every MN-major variant, see profiles/README.md.)"""
+    from pytorch_quadconv_b200 import _cabi as C
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(128, 32, generator=g).cuda()
+    B = torch.randn(32, 32, generator=g).cuda()
+    ref = A.bfloat16().double() @ B.bfloat16().double().T
+    for mode in range(4):
+        D = torch.full((128, 32), float("nan"), device="cuda")
+        C.check(cuda_lib.qc_tc_probe_bf16(C.ptr(A), C.ptr(B), C.ptr(D), mode, C.stream()), "qc_tc_probe_bf16")
+        torch.cuda.synchronize()
+        assert float((D.double() - ref).norm() / ref.norm()) < 1e-6, mode
