@@ -285,90 +285,60 @@ def time_kernels(w, mesh, layer, x, reps=5):
     return out, calls
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c3")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-cache", action="store_true",
-                    help="QuadConv(cache=False): the neighbour search runs inside every forward "
-                         "(the mode of the reference's py_scripts/quadconv_layer_profile.py:46)")
-    ap.add_argument("--filter-dtype", default="f32", choices=["f32", "bf16"],
-                    help="bf16: the filter MLP takes bf16 operands with fp32 accumulation (C4's definition in "
-                         "BASELINE.json); the rest of the layer stays fp32 (single-layer workloads)")
-    ap.add_argument("--graph", action="store_true",
-                    help="capture the step in a CUDA graph and replay it (small meshes are launch-latency bound)")
-    ap.add_argument("--kernel-table", default=None, help="write the per-kernel timing table (json) here")
-    args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
-        args.warmup = 3
-    w = workload(args.workload)
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        steps = max(1, min(args.steps, 3))
-        cb, t, P = run_cpu_reference(w, steps, 1)
-        print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "note": "CPU host cores; bounded sample, see cpu_baseline.sample"},
-            "cpu_baseline": cb,
-            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
-
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+def run_ours(args, w, rank, local_rank, world, dev, sub=False):
+    """One workload on this rank's GPU.  Returns the JSON line (rank 0) or None.  sub=True: a secondary record
+    riding on the default line (no CPU baseline, no per-kernel table)."""
     import torch.distributed as dist
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    from pytorch_quadconv_b200 import _cabi  # fails loudly if the .so is missing
-    _cabi.lib()
     from pytorch_quadconv_b200.distributed import FlatGradAllReduce, trainable_parameters
-
     is_ae = w.get("model") == "autoencoder"
+    # A step is three stream-ordered pieces: compute (zero grads, forward, backward, gradients gathered into the
+    # flat buffer), the ONE flat all-reduce (eager NCCL call; nothing when world == 1), and the update (Adam for
+    # the autoencoder, nothing for the single-layer workloads).  With --graph the first and the last are CUDA
+    # graphs replayed per rank, the collective stays between them.
     if is_ae:
         b_local = w["B"] // world if w.get("strong") else w["B"]
         mesh, layer, x_host = build_autoencoder(w, dev, b_local)
         x = x_host.to(dev)
         params = trainable_parameters([layer])      # the model owns the mesh (and its weight network)
-        reducer = FlatGradAllReduce(params) if world > 1 else None
+        reducer = FlatGradAllReduce(params)
         opt = torch.optim.Adam(params, lr=1e-3, capturable=args.graph)
 
-        def step(xin):
-            opt.zero_grad(set_to_none=True)
+        def compute(xin):
+            for p in params:
+                p.grad = None
             y = layer(xin)
             loss = torch.nn.functional.mse_loss(y, xin.detach())
             loss.backward()
-            if reducer is not None:
-                reducer()
-            opt.step()
+            reducer.pack()
             return loss
+
+        update = opt.step
     else:
         mesh, layer, x_host = build_problem(w, dev, cache=not args.no_cache,
                                             filter_dtype=torch.bfloat16 if args.filter_dtype == "bf16" else torch.float32)
         x = x_host.to(dev).requires_grad_()
         params = trainable_parameters([layer, mesh])
-        reducer = FlatGradAllReduce(params) if world > 1 else None
+        reducer = FlatGradAllReduce(params)
 
-        def step(xin):
+        def compute(xin):
             for p in params:
                 p.grad = None
             xin.grad = None
             y = layer(mesh, xin)
             loss = y.sum()
             loss.backward()
-            if reducer is not None:
-                reducer()
+            reducer.pack()
             return loss
+
+        update = None
+
+    def step(xin):
+        loss = compute(xin)
+        if world > 1:
+            reducer.reduce()
+        if update is not None:
+            update()
+        return loss
 
     def sync():
         if world > 1:
@@ -380,24 +350,31 @@ def main():
     P = layer.pairs() if is_ae else int(layer._tables[0].numel())
 
     if args.graph:
-        # whole step (forward, backward, optimiser / all-reduce excluded) as one CUDA graph on static buffers
-        assert world == 1, "--graph is a single-GPU option"
-        eager_step = step
         x_static = x.detach().clone().requires_grad_(x.requires_grad)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
-                eager_step(x_static)
+                step(x_static)
         torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            loss_static = eager_step(x_static)
+        torch.cuda.synchronize()
+        g_compute = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_compute):
+            loss_static = compute(x_static)
+        g_update = None
+        if update is not None:
+            g_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_update):
+                update()
 
         def step(xin):
             if xin is not x_static:
                 x_static.data.copy_(xin.detach(), non_blocking=True)
-            graph.replay()
+            g_compute.replay()
+            if world > 1:
+                reducer.reduce()
+            if g_update is not None:
+                g_update.replay()
             return loss_static
         x = x_static
 
@@ -415,7 +392,10 @@ def main():
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
-    value = P * world / (ms * 1e-3) / 1e6
+    # weak scaling: every rank walks the pair list for its own batch -> P * world pairs per step; strong scaling
+    # (C5): the ranks share ONE global batch, so a step is P pairs however many ranks split it
+    units = P * (1 if w.get("strong") else world)
+    value = units / (ms * 1e-3) / 1e6
 
     # ---- end to end: host (pinned) features -> device -> fwd+bwd -> loss + filter grads to host ----
     grads_host = [torch.empty(p.shape, dtype=p.dtype).pin_memory() for p in layer.parameters() if p.requires_grad]
@@ -474,7 +454,7 @@ def main():
         roof = {"bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
                 "note": "multi-layer training step: launch-latency dominated (SURVEY 8d); per-kernel roofline is "
                         "reported on the single-layer workloads (default c3)"}
-    if rank == 0 and not is_ae:
+    if rank == 0 and not is_ae and not sub:
         table, calls_per_step = time_kernels(w, mesh, layer, x)
         peaks = {}
         try:
@@ -535,17 +515,82 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["name"], "pairs_per_gpu": P,
                        "batch_per_gpu": (w["B"] // world if w.get("strong") else w["B"]),
-                       "parallelism": f"batch-sharded dp{world}, flat NCCL all-reduce of parameter grads",
+                       "global_batch": w["B"] if w.get("strong") else w["B"] * world,
+                       "parallelism": f"batch-sharded dp{world}, one flat NCCL all-reduce (AVG) of all parameter grads "
+                                      f"({reducer.numel} floats)",
                        "l2": "inputs larger than L2 (features+grads 1.6 GB/step > 126 MB)" if w["N"] >= 50000
                        else "working set fits in L2 (reference's own CPU-runnable case)",
                        "includes": "MeshHandler.weights() (fused weight-map kernels, mesh_handler.py:101-112) every step",
                        "cuda_graph": bool(args.graph), "cache": not args.no_cache, "filter_mlp_operands": args.filter_dtype},
             "clocks": clk.summary(),
-            "e2e": {"value": P * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+            "e2e": {"value": units / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches * args.steps,
             "roofline": roof, "cpu_baseline": cb, "kernels_ms": table,
         }
+        return line
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cache", action="store_true",
+                    help="QuadConv(cache=False): the neighbour search runs inside every forward "
+                         "(the mode of the reference's py_scripts/quadconv_layer_profile.py:46)")
+    ap.add_argument("--filter-dtype", default="f32", choices=["f32", "bf16"],
+                    help="bf16: the filter MLP takes bf16 operands with fp32 accumulation (C4's definition in "
+                         "BASELINE.json); the rest of the layer stays fp32 (single-layer workloads)")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture the step in a CUDA graph and replay it (small meshes are launch-latency bound)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 sub-record that rides on the default (c3) line")
+    ap.add_argument("--kernel-table", default=None, help="write the per-kernel timing table (json) here")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    w = workload(args.workload)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        cb, t, P = run_cpu_reference(w, steps, 1)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "note": "CPU host cores; bounded sample, see cpu_baseline.sample"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from pytorch_quadconv_b200 import _cabi  # fails loudly if the .so is missing
+    _cabi.lib()
+
+    line = run_ours(args, w, rank, local_rank, world, dev)
+    if args.workload == "c3" and not args.no_c5:
+        # north_star config 5: the batch-256 autoencoder training step, batch split over the
+        # ranks (STRONG scaling), step replayed from per-rank CUDA graphs with the flat NCCL all-reduce between them
+        sub_args = argparse.Namespace(**vars(args))
+        sub_args.graph, sub_args.steps, sub_args.warmup = True, max(5, args.steps // 2), 3
+        c5 = run_ours(sub_args, workload("c5"), rank, local_rank, world, dev, sub=True)
+        if line is not None:
+            line["c5"] = c5
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -149,6 +149,22 @@ def quadconv_forward(out_pts, in_pts, quad_weights, filt_weights, features, eval
 
 
 # ---------------------------------------------------------------------------------------------
+# learned quadrature weights
+# ---------------------------------------------------------------------------------------------
+
+def weight_map(points: torch.Tensor, adjacency: torch.Tensor, net_params, activation=torch.sigmoid) -> torch.Tensor:
+    """mesh_handler.py:101-112: per-simplex MLP  Linear(el*dim,8) s Linear(8,8) s Linear(8,8) s Linear(8,el) s
+    (mesh_handler.py:90-99, s = weight_activation) on the simplex's vertex coordinates, scatter_add of the
+    el outputs onto the vertices.  net_params = [W0,b0,W1,b1,W2,b2,W3,b3] in the dtype to evaluate in."""
+    el = adjacency.shape[1]
+    h = points[adjacency].reshape(-1, el * points.shape[1]).to(net_params[0].dtype)          # :104
+    for l in range(4):
+        h = activation(torch.nn.functional.linear(h, net_params[2 * l], net_params[2 * l + 1]))   # :106
+    w = torch.zeros(points.shape[0], dtype=h.dtype)                                          # :108
+    return w.scatter_add(0, adjacency.reshape(-1), h.reshape(-1))                            # :110
+
+
+# ---------------------------------------------------------------------------------------------
 # Mesh_MaxPool
 # ---------------------------------------------------------------------------------------------
 
@@ -179,7 +195,7 @@ def pool_adjoint_index(elim_map: dict, n_fine: int) -> np.ndarray:
 
 def maxpool_forward(x: torch.Tensor, group: torch.Tensor, n_out: int) -> torch.Tensor:
     """mesh_pool.py:88-89."""
-    out = torch.zeros(x.shape[0], x.shape[1], n_out)
+    out = torch.zeros(x.shape[0], x.shape[1], n_out, dtype=x.dtype)   # (fp32 in the reference; float64 when used as the exact checker)
     index = group.view(1, 1, -1).expand_as(x)
     return out.scatter_reduce(dim=2, index=index, src=x, reduce='amax', include_self=False)
 

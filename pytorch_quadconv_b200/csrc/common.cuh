@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include "../../include/quadconv_b200.h"
 
 #define QC_CHECK_LAUNCH()                                  \
@@ -34,16 +35,42 @@ static inline int qc_nblk(int B) { return (B + 31) / 32; }
 __host__ __device__ inline int qc_cp4(int C) { return (C + 3) & ~3; }
 __host__ __device__ inline int qc_off(int c, int b, int Bp) { return ((((c >> 2) * Bp) + b) << 2) + (c & 3); }
 
+// Per-process caches of launch-invariant host state (hoisted out of the per-launch path: a small-mesh layer
+// step is ~25 launches of a few microseconds each).  All keyed by the CURRENT device, so one process may
+// drive several GPUs.
+constexpr int QC_MAX_DEVICES = 64;
+static inline int qc_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev < 0 || dev >= QC_MAX_DEVICES) ? 0 : dev;
+}
+
 static inline int qc_num_sms()
 {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static int sms[QC_MAX_DEVICES] = {0};
+    const int dev = qc_device();
+    if (sms[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = v > 0 ? v : 148;
     }
-    return sms;
+    return sms[dev];
+}
+
+// Environment switches are read once per process.
+#define QC_ENV_SET(name) ([]() -> bool { static const bool v = getenv(name) != nullptr; return v; }())
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) and size increase.
+template <auto Kernel>
+static inline cudaError_t qc_set_max_smem(int bytes)
+{
+    static int cur[QC_MAX_DEVICES] = {0};
+    const int dev = qc_device();
+    if (bytes <= cur[dev]) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) cur[dev] = bytes;
+    return e;
 }
 
 __device__ __forceinline__ int qc_warp_max_i(int v)

@@ -353,7 +353,7 @@ inline int ilog2(int x)
 template <int HP, bool DW>
 int launch_contract(const ContractArgs& a, int nblk, size_t smem, cudaStream_t st)
 {
-    QC_CUDA(cudaFuncSetAttribute(k_contract<HP, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA((qc_set_max_smem<k_contract<HP, DW>>((int)smem)));
     const int WP = 8 >> a.LWK, PPW = 32 >> a.LB;
     const int ntiles = qc_ceil_div(a.Ndst, WP * PPW);
     int gx = qc_num_sms() * (DW ? 1 : 2);

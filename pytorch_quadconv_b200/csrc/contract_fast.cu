@@ -444,7 +444,7 @@ int launch_cf(const ContractArgs& a, int B, cudaStream_t st)
             smem += (size_t)nkc * 64 * 32 * 4;
         }
     }
-    QC_CUDA(cudaFuncSetAttribute(k_contract_fast<HP, LB, DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA((qc_set_max_smem<k_contract_fast<HP, LB, DW>>((int)smem)));
     const int ntiles = qc_ceil_div(a.Ndst, 8 * PPW);
     int gx = qc_num_sms();
     gx = (gx + nblk - 1) / nblk;
@@ -469,7 +469,7 @@ int launch_df(const DphiArgs& a, int B, cudaStream_t st)
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     dim3 grid(gx, nblk);
-    QC_CUDA(cudaFuncSetAttribute(k_dphi_fast<HP, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA((qc_set_max_smem<k_dphi_fast<HP, LB>>((int)smem)));
     k_dphi_fast<HP, LB><<<grid, 256, smem, st>>>(a, nkc, (size_t)a.P * HP);
     QC_CHECK_LAUNCH();
     return 1;
@@ -482,7 +482,7 @@ int qc_contract_fast(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t
     const int Bp = qc_bp(B);
     if (a.Cy > 32 || !(HP == 4 || HP == 8) || !(Bp == 8 || Bp == 32)) return 0;
     if ((size_t)a.Nsrc * qc_cp4(a.Cx) * Bp >= ((size_t)1 << 32)) return 0;   // 32-bit row offsets
-    if (nullptr != getenv("QC_NO_FAST")) return 0;
+    if (QC_ENV_SET("QC_NO_FAST")) return 0;
 #define QC_F(HPV, LBV) (dw ? launch_cf<HPV, LBV, true>(a, B, st) : launch_cf<HPV, LBV, false>(a, B, st))
     if (HP == 4) return Bp == 8 ? QC_F(4, 3) : QC_F(4, 5);
     return Bp == 8 ? QC_F(8, 3) : QC_F(8, 5);
@@ -494,7 +494,7 @@ bool qc_dphi_fast_ok(int Nsrc, int Cx, int Cg, int HP, int B)
     const int Bp = qc_bp(B);
     if (Cg > 32 || !(HP == 4 || HP == 8) || !(Bp == 8 || Bp == 32)) return false;
     if ((size_t)Nsrc * qc_cp4(Cx) * Bp >= ((size_t)1 << 32)) return false;
-    if (nullptr != getenv("QC_NO_FAST")) return false;
+    if (QC_ENV_SET("QC_NO_FAST")) return false;
     return true;
 }
 
@@ -503,7 +503,7 @@ int qc_dphi_fast(const DphiArgs& a, int HP, int B, cudaStream_t st)
     const int Bp = qc_bp(B);
     if (a.Cg > 32 || !(HP == 4 || HP == 8) || !(Bp == 8 || Bp == 32)) return 0;
     if ((size_t)a.Nsrc * qc_cp4(a.Cx) * Bp >= ((size_t)1 << 32)) return 0;
-    if (nullptr != getenv("QC_NO_FAST")) return 0;
+    if (QC_ENV_SET("QC_NO_FAST")) return 0;
     if (HP == 4) return Bp == 8 ? launch_df<4, 3>(a, B, st) : launch_df<4, 5>(a, B, st);
     return Bp == 8 ? launch_df<8, 3>(a, B, st) : launch_df<8, 5>(a, B, st);
 }

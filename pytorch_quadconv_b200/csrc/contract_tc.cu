@@ -477,7 +477,7 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
         if (smem > 113 * 1024) return 0;
     }
     if (smem > 227 * 1024) return 0;   // weight slices do not fit: use the FP32-pipe kernel
-    QC_CUDA(cudaFuncSetAttribute(k_contract_tc<HP, KCH, LB, DW, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA((qc_set_max_smem<k_contract_tc<HP, KCH, LB, DW, NW>>((int)smem)));
     const int ntiles = qc_ceil_div(a.Ndst, NW * PPW);
     int gx = qc_num_sms() * CTAS;
     gx = (gx + nblk - 1) / nblk;
@@ -877,7 +877,7 @@ int launch_dtc(const DphiArgs& a, int B, cudaStream_t st)
     constexpr int RING = dtc_ring_depth(CXC / 4) * (CXC / 4) * 512;
     const size_t smem = ((size_t)nkc * 2 * WSLICE + NW * PPW * PCH) * 4 + 64 + NW * RING;
     if (smem > 227 * 1024) return 0;
-    QC_CUDA(cudaFuncSetAttribute(k_dphi_tc<HP, LB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA((qc_set_max_smem<k_dphi_tc<HP, LB, NW>>((int)smem)));
     const int ntiles = qc_ceil_div(a.Ndst, NW * PPW);
     int gx = qc_num_sms();
     gx = (gx + nblk - 1) / nblk;
@@ -912,19 +912,19 @@ int qc_contract_tc(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t s
     const int Bp = qc_bp(B);
     if (a.Cy > 32 || !(HP == 4 || HP == 8) || !(Bp == 8 || Bp == 32)) return 0;
     if ((size_t)a.Nsrc * qc_cp4(a.Cx) * Bp >= ((size_t)1 << 32)) return 0;
-    if (nullptr != getenv("QC_NO_FAST") || nullptr != getenv("QC_NO_TC")) return 0;
+    if (QC_ENV_SET("QC_NO_FAST") || QC_ENV_SET("QC_NO_TC")) return 0;
     // Forward-type launches can also run with 32-wide chunks and two CTAs per SM (QC_TC_K32=1).
     // Measured on C3 (profiles/README.md): 16 instead of 8 warps/SM lift issue utilisation from 45 % to
     // 60 %, but the per-pair overhead is amortised over half the FMAs (+23 % instructions) and the two
     // CTAs halve the L1 hit rate, so the time is the same (4.0 ms); the one-CTA variant is the default.
-    if (!dw && nullptr != getenv("QC_TC_K32")) {
+    if (!dw && QC_ENV_SET("QC_TC_K32")) {
         int rc;
         if (HP == 4) rc = Bp == 8 ? launch_tc<4, 32, 3, false, 8>(a, B, st) : launch_tc<4, 32, 5, false, 8>(a, B, st);
         else rc = Bp == 8 ? launch_tc<8, 32, 3, false, 8>(a, B, st) : launch_tc<8, 32, 5, false, 8>(a, B, st);
         if (rc != 0) return rc;
     }
     // forward-type launches with H = 8: three 128-row blocks (12 warps) per CTA unless QC_TC_NW8=1
-    if (!dw && HP == 8 && nullptr == getenv("QC_TC_NW8")) {
+    if (!dw && HP == 8 && !QC_ENV_SET("QC_TC_NW8")) {
         const int rc = Bp == 8 ? launch_tc<8, 64, 3, false, 12>(a, B, st) : launch_tc<8, 64, 5, false, 12>(a, B, st);
         if (rc != 0) return rc;
     }
@@ -938,10 +938,10 @@ int qc_contract_tc(const ContractArgs& a, int HP, int B, bool dw, cudaStream_t s
 int qc_dphi_tc(const DphiArgs& a, int HP, int B, cudaStream_t st)
 {
     if (!qc_dphi_fast_ok(a.Nsrc, a.Cx, a.Cg, HP, B)) return 0;
-    if (nullptr != getenv("QC_NO_TC")) return 0;
+    if (QC_ENV_SET("QC_NO_TC")) return 0;
     const int Bp = qc_bp(B);
     if (HP == 4) return Bp == 8 ? launch_dtc<4, 3, 8>(a, B, st) : launch_dtc<4, 5, 8>(a, B, st);
-    if (nullptr == getenv("QC_TC_NW8")) {   // H = 8: four 128-row blocks (16 warps, 4 x 128 TMEM columns) per CTA
+    if (!QC_ENV_SET("QC_TC_NW8")) {   // H = 8: four 128-row blocks (16 warps, 4 x 128 TMEM columns) per CTA
         const int rc = Bp == 8 ? launch_dtc<8, 3, 16>(a, B, st) : launch_dtc<8, 5, 16>(a, B, st);
         if (rc != 0) return rc;
     }

@@ -410,7 +410,7 @@ template <int HC, int LB, int NW>
 int launch_acc(const WideArgs& a, cudaStream_t st)
 {
     const size_t smem = acc_smem<HC, LB>(NW);
-    QC_CUDA(cudaFuncSetAttribute(k_gather_acc<HC, LB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA((qc_set_max_smem<k_gather_acc<HC, LB, NW>>((int)smem)));
     const int nblk = qc_nblk(a.B);
     const int ntiles = qc_ceil_div(a.Ndst, NW);
     int gx = qc_ceil_div(qc_num_sms(), nblk);
@@ -425,7 +425,7 @@ template <int HC, int LB, int NW>
 int launch_dot(const WideArgs& a, cudaStream_t st)
 {
     const size_t smem = dot_smem<HC, LB>(NW);
-    QC_CUDA(cudaFuncSetAttribute(k_gather_dot<HC, LB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA((qc_set_max_smem<k_gather_dot<HC, LB, NW>>((int)smem)));
     const int nblk = qc_nblk(a.B);
     const int ntiles = qc_ceil_div(a.Ndst, NW);
     int gx = qc_ceil_div(qc_num_sms(), nblk);

@@ -227,7 +227,7 @@ template <int BN>
 int launch_gemm(const GemmArgs& g, cudaStream_t st)
 {
     const size_t smem = (size_t)(RAW + LOS) * (128 * GK + BN * GK) * 4 + 1024;
-    QC_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA((qc_set_max_smem<k_gemm_tf32x3<BN>>((int)smem)));
     const long long mt = (g.M + 127) / 128;
     const int nt = (g.N + BN - 1) / BN;
     if (mt > 2147483647LL || nt > 65535) return QC_EUNSUP;

@@ -272,7 +272,7 @@ int launch_fwd(const float* out_pts, const float* in_pts, const float* quad_w, c
                const int* pair_col, int64_t P, int d, const MlpDev& m, int HP, float* phi, cudaStream_t st)
 {
     size_t smem = (size_t)(m.n_hidden > 0 ? m.n_hidden : 1) * WMAX * WMAX * 4;
-    QC_CUDA(cudaFuncSetAttribute(k_pair_phi_fwd<WMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA((qc_set_max_smem<k_pair_phi_fwd<WMAX>>((int)smem)));
     int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 16);
     k_pair_phi_fwd<WMAX><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, phi);
     QC_CHECK_LAUNCH();
@@ -285,7 +285,7 @@ int launch_bwd(const float* out_pts, const float* in_pts, const float* quad_w, c
                int nslices, float* d_quad_w, cudaStream_t st)
 {
     size_t smem = ((size_t)2 * m.n_hidden * WMAX * WMAX + 2 * 128 * WMAX) * 4;
-    QC_CUDA(cudaFuncSetAttribute(k_pair_phi_bwd<WMAX, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QC_CUDA((qc_set_max_smem<k_pair_phi_bwd<WMAX, LT>>((int)smem)));
     int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 16);
     k_pair_phi_bwd<WMAX, LT><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w);
     QC_CHECK_LAUNCH();

@@ -19,8 +19,13 @@ __global__ void k_segmax_fwd(const float* __restrict__ x, const int* __restrict_
         const int beg = grp_ptr[g], end = grp_ptr[g + 1];
         float m = 0.f;  // empty group keeps the reference's zero initialisation
         if (end > beg) {
+            // NaN is sticky, like torch's amax (fmaxf would drop it and hide a diverged activation)
             m = -INFINITY;
-            for (int e = beg; e < end; ++e) m = fmaxf(m, __ldg(x + r * Nin + grp_mem[e]));
+            for (int e = beg; e < end; ++e) {
+                const float v = __ldg(x + r * Nin + grp_mem[e]);
+                m = (v != v || v > m) ? v : m;
+                if (m != m) break;
+            }
         }
         out[t] = m;
     }
@@ -38,7 +43,10 @@ __global__ void k_segmax_bwd(const float* __restrict__ x, const float* __restric
         const int g = group[k];
         const float m = out[r * Nout + g];
         float gx = 0.f;
-        if (x[t] == m) {
+        if (m != m) {
+            // torch: (src == result) is false for every member, grad / 0 ties, false * inf -> NaN for the whole group
+            gx = m;
+        } else if (x[t] == m) {
             // torch's amax backward counts `self == result` as one more tie even with
             // include_self=False, and self is the reference's zeros() tensor (mesh_pool.py:88):
             // a group whose maximum is exactly 0 spreads its gradient over ties+1.  Reproduced

@@ -242,7 +242,7 @@ extern "C" int qc_tc_probe_bf16(const float* A, const float* B, float* D, int mo
 extern "C" int qc_tc_selftest_ss(const float* A, const float* B, float* D, void* stream)
 {
     const int smem = (2 * 128 * 64 + 2 * 32 * 64) * 4;
-    QC_CUDA(cudaFuncSetAttribute(k_tc_selftest_ss, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    QC_CUDA((qc_set_max_smem<k_tc_selftest_ss>(smem)));
     k_tc_selftest_ss<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D);
     QC_CHECK_LAUNCH();
     return 0;

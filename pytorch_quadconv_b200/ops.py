@@ -12,6 +12,7 @@ FLOP of the path runs in libquadconv_b200.so.  Ops (namespace `quadconv_b200`):
 """
 from __future__ import annotations
 
+import functools
 import os
 
 from typing import List, Optional, Sequence, Tuple
@@ -22,6 +23,21 @@ import torch
 from . import _cabi as C
 
 Tensor = torch.Tensor
+
+
+def _on_device(fn):
+    """Run an op body with the CUDA device of its first tensor argument current: libquadconv launches on the
+    current device's current stream (C.stream()), so a model on cuda:1 must not launch on cuda:0."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if not a.is_cuda:
+                    raise RuntimeError("pytorch_quadconv_b200 kernels need CUDA tensors (there is no CPU path)")
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper
 
 
 def _hp(h: int) -> int:
@@ -79,6 +95,7 @@ def _csc(pair_row: Tensor, pair_col: Tensor, Ni: int) -> Tuple[Tensor, Tensor, T
 
 
 @torch.library.custom_op("quadconv_b200::build_pairs", mutates_args=())
+@_on_device
 def build_pairs(out_pts: Tensor, in_pts: Tensor, radius: float, same: bool) -> List[Tensor]:
     """Grid-binned neighbour search.  Returns
     [eval_indices int64 [P,2], pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in]."""
@@ -131,6 +148,7 @@ def _(out_pts, in_pts, radius, same):
 
 
 @torch.library.custom_op("quadconv_b200::pairs_to_tables", mutates_args=())
+@_on_device
 def pairs_to_tables(eval_indices: Tensor, n_out: int, n_in: int) -> List[Tensor]:
     """Tables for a pair list supplied by the caller (e.g. a loaded `eval_indices` Parameter).
     Returns [pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row]."""
@@ -223,6 +241,7 @@ class _fp32_matmul:
 
 
 @torch.library.custom_op("quadconv_b200::qc_forward", mutates_args=())
+@_on_device
 def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor,
                hidden_ws: Sequence[Tensor], w_last: Tensor, bias: Optional[Tensor],
                pair_row: Tensor, pair_col: Tensor, row_ptr: Tensor, order_out: Optional[Tensor],
@@ -288,6 +307,7 @@ def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair
 
 
 @torch.library.custom_op("quadconv_b200::qc_backward", mutates_args=())
+@_on_device
 def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor,
                 hidden_ws: Sequence[Tensor], w_last: Tensor, pair_row: Tensor, pair_col: Tensor,
                 row_ptr: Tensor, csc_ptr: Tensor, csc_pair: Tensor, csc_row: Tensor,
@@ -429,6 +449,7 @@ def _ptr_array(tensors):
 
 
 @torch.library.custom_op("quadconv_b200::weight_map", mutates_args=())
+@_on_device
 def weight_map(points: Tensor, adj32: Tensor, inc_ptr: Tensor, inc_idx: Tensor, params: Sequence[Tensor]) -> Tensor:
     """weights[N] = scatter_add of the per-simplex MLP outputs; params = [W0,b0,W1,b1,W2,b2,W3,b3]."""
     points = _f32c(points, "points")
@@ -449,6 +470,7 @@ def _(points, adj32, inc_ptr, inc_idx, params):
 
 
 @torch.library.custom_op("quadconv_b200::weight_map_bwd", mutates_args=())
+@_on_device
 def weight_map_bwd(grad_w: Tensor, points: Tensor, adj32: Tensor, params: Sequence[Tensor]) -> List[Tensor]:
     grad_w = _f32c(grad_w, "grad")
     points = _f32c(points, "points")
@@ -487,6 +509,7 @@ def weight_map_apply(points, adj32, inc_ptr, inc_idx, params):
 # ---------------------------------------------------------------------------------------------
 
 @torch.library.custom_op("quadconv_b200::segmax", mutates_args=())
+@_on_device
 def segmax(x: Tensor, group: Tensor, grp_ptr: Tensor, grp_mem: Tensor, n_out: int) -> Tensor:
     x = _f32c(x, "pool input")
     B, Cc, Nin = x.shape
@@ -502,6 +525,7 @@ def _(x, group, grp_ptr, grp_mem, n_out):
 
 
 @torch.library.custom_op("quadconv_b200::segmax_bwd", mutates_args=())
+@_on_device
 def segmax_bwd(x: Tensor, out: Tensor, grad_out: Tensor, group: Tensor, grp_ptr: Tensor, grp_mem: Tensor) -> Tensor:
     x, out, grad_out = _f32c(x, "x"), _f32c(out, "out"), _f32c(grad_out, "grad")
     B, Cc, Nin = x.shape
@@ -517,6 +541,7 @@ def _(x, out, grad_out, group, grp_ptr, grp_mem):
 
 
 @torch.library.custom_op("quadconv_b200::gather_pool", mutates_args=())
+@_on_device
 def gather_pool(x: Tensor, index: Tensor) -> Tensor:
     x = _f32c(x, "pool input")
     B, Cc, Nin = x.shape
@@ -532,6 +557,7 @@ def _(x, index):
 
 
 @torch.library.custom_op("quadconv_b200::gather_pool_bwd", mutates_args=())
+@_on_device
 def gather_pool_bwd(grad_out: Tensor, grp_ptr: Tensor, grp_mem: Tensor, n_coarse: int) -> Tensor:
     grad_out = _f32c(grad_out, "grad")
     B, Cc, Nf = grad_out.shape

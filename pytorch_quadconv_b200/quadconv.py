@@ -52,6 +52,13 @@ class QuadConv(nn.Module):
         self.filter_dtype = filter_dtype
 
         assert spatial_dim > 0                                   # quadconv.py:44
+        # limits of the sm_100a kernels, reported at construction instead of at the first forward (README "Limits")
+        if spatial_dim > 3:
+            raise NotImplementedError(f"spatial_dim={spatial_dim}: the grid-binned neighbour search is built for 1..3 dimensions")
+        if len(filter_seq) > 8:
+            raise NotImplementedError(f"filter_seq with {len(filter_seq)} hidden layers: the per-pair MLP kernels hold at most 8")
+        if len(filter_seq) > 0 and max(filter_seq) > 32:
+            raise NotImplementedError(f"filter_seq={list(filter_seq)}: hidden widths above 32 are not implemented by the per-pair MLP kernels")
 
         self.spatial_dim = spatial_dim
         self.in_points = in_points
@@ -125,11 +132,11 @@ class QuadConv(nn.Module):
                               bool(self.output_same))
         idx = res[0]
         self._tables = tuple(res[1:])
-        self._tables_key = (output_points.data_ptr(), input_points.data_ptr(), idx.data_ptr())
+        self._tables_key = None
 
         if self.cache:                                           # quadconv.py:186-188
             self.eval_indices = nn.Parameter(idx, requires_grad=False)
-            self._tables_key = (output_points.data_ptr(), input_points.data_ptr(), self.eval_indices.data_ptr())
+            self._tables_key = self._pairs_key()
             self.cached = True
 
         if self.verbose:                                         # quadconv.py:190-197 (same statistics)
@@ -141,10 +148,17 @@ class QuadConv(nn.Module):
 
         return idx
 
+    def _pairs_key(self):
+        """Identity of the pair list the CSR/CSC tables were derived from.  The reference reads `eval_indices`
+        on every forward (quadconv.py:247-253), so an in-place update (load_state_dict, `.data.copy_`) must
+        invalidate the tables: `_version` counts in-place writes, the pointer/shape catch re-assignment."""
+        ev = self.eval_indices
+        return (ev.data_ptr(), ev._version, tuple(ev.shape), str(ev.device))
+
     def _tables_for_cached(self, output_points, input_points):
         """Tables for an `eval_indices` that did not come from this module's own search (a loaded
         state_dict, or the two lines of quadconv.py:187-188 run by the caller)."""
-        key = (output_points.data_ptr(), input_points.data_ptr(), self.eval_indices.data_ptr())
+        key = self._pairs_key()
         if self._tables is None or self._tables_key != key:
             t = ops.pairs_to_tables(self.eval_indices.data, self.out_points, self.in_points)
             self._tables = tuple(t) + (None, None)

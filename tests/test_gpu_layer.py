@@ -48,10 +48,32 @@ def test_layer_matches_reference_golden(cuda_lib, name, d, fs, bias):
         assert relerr(got, L[f"dW{l}"]) < TOL, f"dW{l}"
     if bias:
         assert relerr(layer.bias.grad.cpu().numpy(), L["dbias"]) < TOL
-    # d/d quadrature weights flows on into MeshHandler._weight_network through torch autograd
+    # d/d quadrature weights flows on into MeshHandler._weight_network.  Against the live reference's fp32
+    # values these are only good to ~3e-5: the reference's own CPU fp32 bmm/scatter_add wander that far from
+    # the exact value (see below), so this comparison keeps a LOOSE bound ...
     for k, p in mesh.named_parameters():
         if p.requires_grad:
             assert relerr(p.grad.cpu().numpy(), L["meshgrad/" + k]) < 5e-5, k
+    # ... and the 1e-5 bound of north_star is asserted against the same formulas evaluated in float64 on the
+    # same fp32 inputs (oracle, reference association order), for the output and EVERY gradient.
+    import ref64
+    from oracle import quadconv_oracle as O
+    pts = torch.from_numpy(L["pts"])
+    mp = ref64.mesh_params64({k[5:]: L[k] for k in L.files if k.startswith("mesh/")})
+    qw64 = O.weight_map(pts, torch.from_numpy(L["mesh/_adjacency.0"]), mp)
+    x64 = torch.from_numpy(L["x"]).double().requires_grad_()
+    y64, ws64, b64 = ref64.layer64(pts, pts, qw64, [L[f"W{l}"] for l in range(len(fs) + 1)], x64,
+                                   torch.from_numpy(L["pairs"]), int(L["ci"]), int(L["co"]), L["bias"] if bias else None)
+    (y64 * torch.from_numpy(L["grad_out"]).double()).sum().backward()
+    assert relerr(y.detach().cpu().numpy(), y64.detach().numpy()) < TOL
+    assert relerr(x.grad.cpu().numpy(), x64.grad.numpy()) < TOL
+    for l in range(len(fs) + 1):
+        assert relerr(layer.filter[2 * l].weight.grad.cpu().numpy(), ws64[l].grad.numpy()) < TOL, f"dW{l} vs float64"
+    if bias:
+        assert relerr(layer.bias.grad.cpu().numpy(), b64.grad.numpy()) < TOL
+    named = dict(mesh.named_parameters())
+    for k, p64 in zip(ref64.mesh_param_names(), mp):
+        assert relerr(named[k].grad.cpu().numpy(), p64.grad.numpy()) < TOL, k + " vs float64"
 
 
 def test_dquadw_direct(cuda_lib):

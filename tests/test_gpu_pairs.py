@@ -93,3 +93,22 @@ def test_pairs_to_tables_roundtrip(cuda_lib):
     bad = ev.flip(0).contiguous()
     with pytest.raises(RuntimeError):
         ops.pairs_to_tables(bad, No, Ni)
+
+
+def test_pairs_c3_full_size_bit_exact(cuda_lib):
+    """The 100 000-point 3-D pair list of BASELINE config 3 (4.8 M pairs) is bit-exact in set AND order: its
+    SHA-256 equals the one tests/golden/make_pairs_c3_hash.py computed from the reference's own ATen ops
+    (2048-row blocks) and from the C oracle (they agreed before the hash was written)."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, "pairs_c3_sha256.json")))
+    torch.manual_seed(ref["seed"])
+    pts = torch.rand(ref["N"], ref["d"])
+    r = (150 / (4 * np.pi * ref["N"])) ** (1 / 3)
+    assert r == ref["radius"]
+    res = _search(pts.numpy(), pts.numpy(), r, True)
+    assert res[0].shape == (ref["P"], 2)
+    assert hashlib.sha256(np.ascontiguousarray(res[0]).tobytes()).hexdigest() == ref["sha256"]
+    _check_tables(res, ref["N"], ref["N"])

@@ -89,3 +89,62 @@ def test_bf16_operand_mode_of_the_oracle():
     expect = rnd(a_last).sum(0).expand(6, 8)
     assert torch.allclose(wl.grad, expect, rtol=1e-12, atol=1e-12)
     assert (wl.grad != rnd(wl.grad)).any()                           # not quantised to bf16
+
+
+def test_float64_composition_agrees_with_live_reference_golden():
+    """tests/ref64.py (the float64 checker the GPU tests hold the 1e-5 bound against) reproduces the live
+    reference's fp32 autoencoder slice -- output, loss and every gradient -- to the reference's own fp32 noise."""
+    import torch
+    import ref64
+    from oracle import quadconv_oracle as O
+    A = load_golden("autoencoder")
+    mp = ref64.mesh_params64({k[5:]: A[k] for k in A.files if k.startswith("mesh/")})
+    pts = [torch.from_numpy(A[f"mesh/_points.{l}"]) for l in range(2)]
+    adj = [torch.from_numpy(A[f"mesh/_adjacency.{l}"]) for l in range(2)]
+    qw = [O.weight_map(pts[l], adj[l], mp) for l in range(2)]
+    elim = elim_map_from(A, "elim0")
+    n0, n1 = pts[0].shape[0], pts[1].shape[0]
+    grp = torch.from_numpy(O.pool_group_index(elim, n0))
+    upi = torch.from_numpy(O.pool_adjoint_index(elim, n0))
+    x64 = torch.from_numpy(A["x"]).double().requires_grad_()
+    P64 = {}
+
+    def conv64(nm, lvl, h, ci, co):
+        ws = [A[f"{nm}/filter.{2 * l}.weight"] for l in range(3)]
+        y_, ws64, b64 = ref64.layer64(pts[lvl], pts[lvl], qw[lvl], ws, h, torch.from_numpy(A[f"{nm}/eval_indices"]),
+                                      ci, co, A[f"{nm}/bias"])
+        for l in range(3):
+            P64[f"{nm}grad/filter.{2 * l}.weight"] = ws64[l]
+        P64[f"{nm}grad/bias"] = b64
+        return y_
+
+    h = torch.sin(conv64("e0", 0, x64, 2, 4))
+    h = O.maxpool_forward(h, grp, n1)
+    h = torch.sin(conv64("e1", 1, h, 4, 4))
+    h = O.maxpool_adjoint(h, upi)
+    y = conv64("d0", 0, h, 4, 2)
+    loss = torch.nn.functional.mse_loss(y, x64.detach())
+    loss.backward()
+    assert relerr(y.detach().numpy(), A["y"]) < 1e-5
+    assert abs(float(loss) - float(A["loss"])) < 1e-5 * abs(float(A["loss"]))
+    assert relerr(x64.grad.numpy(), A["dx"]) < 5e-5
+    for k, p in P64.items():
+        assert relerr(p.grad.numpy(), A[k]) < 5e-5, k
+    for k, p in zip(ref64.mesh_param_names(), mp):
+        assert relerr(p.grad.numpy(), A["meshgrad/" + k]) < 2e-4, k
+
+
+def test_c_oracle_reproduces_c3_pair_hash():
+    """The committed SHA-256 of the 100k-point C3 pair list (tests/golden/pairs_c3_sha256.json, written after the
+    reference's blocked ATen ops and the C oracle agreed) is what the C oracle computes today (~16 s on 8 cores)."""
+    import hashlib
+    import json
+    import os
+    import torch
+    from conftest import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, "pairs_c3_sha256.json")))
+    torch.manual_seed(ref["seed"])
+    pts = torch.rand(ref["N"], ref["d"]).numpy()
+    p = O.eval_indices_c(pts, pts, ref["radius"])
+    assert p.shape == (ref["P"], 2)
+    assert hashlib.sha256(np.ascontiguousarray(p).tobytes()).hexdigest() == ref["sha256"]
