@@ -185,7 +185,7 @@ class ClockSampler:
 # our arm
 # --------------------------------------------------------------------------------------------
 
-def build_problem(w, dev, cache=True, filter_dtype=torch.float32):
+def build_problem(w, dev, cache=True, filter_dtype=torch.float32, compute_dtype=torch.float32):
     import pytorch_quadconv_b200 as q
     torch.manual_seed(0)
     pts = torch.rand(w["N"], w["d"])
@@ -193,7 +193,7 @@ def build_problem(w, dev, cache=True, filter_dtype=torch.float32):
     mesh = q.MeshHandler(pts).construct([w["N"]], quad_args={"point_args": {}, "weight_args": weight_args(w["d"])})
     layer = q.QuadConv(spatial_dim=w["d"], in_points=w["N"], out_points=w["N"], in_channels=w["ci"],
                        out_channels=w["co"], filter_seq=w["fs"], output_same=True, decay_param=w["r"], cache=cache,
-                       filter_dtype=filter_dtype)
+                       filter_dtype=filter_dtype, compute_dtype=compute_dtype)
     return mesh.to(dev), layer.to(dev), x_host
 
 
@@ -244,7 +244,7 @@ def time_kernels(w, mesh, layer, x, reps=5):
     from pytorch_quadconv_b200 import _cabi as C, ops
     L = C.lib()
     names = ["qc_pair_phi_fwd", "qc_pack_features", "qc_repack_wlast", "qc_contract", "qc_unpack_features",
-             "qc_batch_sum", "qc_dphi", "qc_pair_phi_bwd", "qc_unpack_dwlast", "qc_gather_accumulate", "qc_gather_dot"]
+             "qc_batch_sum", "qc_dphi", "qc_pair_phi_bwd", "qc_unpack_dwlast", "qc_gather_accumulate", "qc_gather_dot", "qc_contract_mma", "qc_pack_features_bf16"]
     acc = {}
     orig = {n: getattr(L, n) for n in names}
     phase = {"bwd": False}
@@ -315,7 +315,8 @@ def run_ours(args, w, rank, local_rank, world, dev, sub=False):
         update = opt.step
     else:
         mesh, layer, x_host = build_problem(w, dev, cache=not args.no_cache,
-                                            filter_dtype=torch.bfloat16 if args.filter_dtype == "bf16" else torch.float32)
+                                            filter_dtype=torch.bfloat16 if args.filter_dtype == "bf16" else torch.float32,
+                                            compute_dtype=torch.bfloat16 if args.compute_dtype == "bf16" else torch.float32)
         x = x_host.to(dev).requires_grad_()
         params = trainable_parameters([layer, mesh])
         reducer = FlatGradAllReduce(params)
@@ -512,7 +513,7 @@ def run_ours(args, w, rank, local_rank, world, dev, sub=False):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong" if w.get("strong") else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16" if args.compute_dtype == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": w["name"], "pairs_per_gpu": P,
                        "batch_per_gpu": (w["B"] // world if w.get("strong") else w["B"]),
                        "global_batch": w["B"] if w.get("strong") else w["B"] * world,
@@ -521,7 +522,8 @@ def run_ours(args, w, rank, local_rank, world, dev, sub=False):
                        "l2": "inputs larger than L2 (features+grads 1.6 GB/step > 126 MB)" if w["N"] >= 50000
                        else "working set fits in L2 (reference's own CPU-runnable case)",
                        "includes": "MeshHandler.weights() (fused weight-map kernels, mesh_handler.py:101-112) every step",
-                       "cuda_graph": bool(args.graph), "cache": not args.no_cache, "filter_mlp_operands": args.filter_dtype},
+                       "cuda_graph": bool(args.graph), "cache": not args.no_cache, "filter_mlp_operands": args.filter_dtype,
+                       "compute_dtype": args.compute_dtype},
             "clocks": clk.summary(),
             "e2e": {"value": units / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -546,6 +548,9 @@ def main():
     ap.add_argument("--filter-dtype", default="f32", choices=["f32", "bf16"],
                     help="bf16: the filter MLP takes bf16 operands with fp32 accumulation (C4's definition in "
                          "BASELINE.json); the rest of the layer stays fp32 (single-layer workloads)")
+    ap.add_argument("--compute-dtype", default="f32", choices=["f32", "bf16"],
+                    help="bf16: the reduced-precision tensor-core mode (both contraction stages on tcgen05 with bf16 "
+                         "operands, fp32 accumulation; stated bound 1e-2 normwise).  f32 is the parity mode and the headline")
     ap.add_argument("--graph", action="store_true",
                     help="capture the step in a CUDA graph and replay it (small meshes are launch-latency bound)")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 sub-record that rides on the default (c3) line")

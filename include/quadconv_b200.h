@@ -229,6 +229,30 @@ int qc_vertex_sum(const float* el_w, const int* inc_ptr, const int* inc_idx, int
 int qc_weight_map_bwd(const float* pts, const int* adj, int M, int E, int d, const float* const* wb,
                       const float* gw, float* const* dwb, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Reduced-precision tensor-core path (bf16 operands, fp32 accumulation; QuadConv(compute_dtype=torch.bfloat16)).
+ * Replaces the same reference lines as qc_contract -- QuadConv._integrate and the last filter Linear,
+ * torch_quadconv/quadconv.py:213-227, :143 -- with BOTH stages of the factorised layer on tcgen05
+ * (csrc/contract_mma.cu).  Work unit: a tile of 16 destination points (consecutive entries of `order`) and the
+ * union of their source points:
+ *   tile_uptr[ntiles+1] : offsets into union_idx, every tile padded to a multiple of 16 entries (>= 16)
+ *   union_idx[]         : source point of every union slot, -1 = padding
+ *   pair_slot[P]        : union slot of every segment entry (segment order = seg_ptr order)
+ *   max_ku              : largest padded union (bounds the shared-memory operand; QC_EUNSUP when it does not fit)
+ * bf16 packed features  Xh[nblk][N][ceil(C/CC)][Bp][CC], CC = qc_mma_chunk_channels(C, B) in {4,8,16}.
+ * Output: fp32 packed rows (same layout as qc_contract, feed qc_unpack_features).
+ * transposed = 0: forward (sources = in points / in channels);  1: the d-features pass on the CSC view
+ * (sources = out points / out channels, phi rows through phi_idx).
+ * Numerics: features, phi, the stage-B result T and W_last are rounded to bf16 (nearest even); both
+ * accumulations are fp32.  Stated bound vs the fp32 layer: <= 1e-2 normwise (measured ~3e-3), tests/.
+ * ------------------------------------------------------------------------------------------ */
+int qc_mma_chunk_channels(int C, int B);          /* 0: batch lanes < 8, not served */
+int qc_pack_features_bf16(const float* x /*[B][C][N]*/, int B, int C, int N, int CC, void* xh, void* stream);
+int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const int* seg_ptr, const int* phi_idx, const int* pair_slot,
+                    const int* tile_uptr, const int* union_idx, int ntiles, int max_ku, const float* phi, int H,
+                    int HPphi, const float* w_last, int Cd, int transposed, const int* order, int Ndst, int B,
+                    float* Yp, void* stream);
+
 /* Known-answer self test of the tcgen05 building blocks (TMEM alloc, tcgen05.st/ld, kind::tf32 MMA with
  * A in TMEM and B through a K-major shared-memory descriptor, 3xTF32 split):
  * D[128][32] = A[128][64] * B[32][64]^T.  Used by tests only. */

@@ -148,6 +148,38 @@ def quadconv_forward(out_pts, in_pts, quad_weights, filt_weights, features, eval
     return integral
 
 
+def quadconv_forward_bf16tc(out_pts, in_pts, quad_weights, filt_weights, features, eval_indices,
+                            in_channels, out_channels, bias=None, block_pairs: int = 2048):
+    """The product's reduced-precision mode (QuadConv(compute_dtype=torch.bfloat16), csrc/contract_mma.cu) restated
+    with the SAME operand roundings, everything else in float64: it is quadconv.py:238-265 in the factorised
+    association order
+        phi[p,h] = w[i(p)] * (last hidden activation of the filter MLP at y_o(p) - x_i(p))      fp32 -> bf16
+        T[o,b,i,h] = sum_{p in N(o)} phi[p,h] * bf16(f[b,i,i(p)])                                -> bf16
+        out[b,j,o] = sum_{i,h} T[o,b,i,h] * bf16(W_last[i*Co+j, h])   (+ bias)
+    Not in the reference (it has one precision); used to bound the mode's own arithmetic."""
+    def rb(t):
+        return t.to(torch.float32).to(torch.bfloat16).to(torch.float64)
+    B = features.shape[0]
+    No = out_pts.shape[0]
+    H = filt_weights[-1].shape[1]
+    fb = rb(features)
+    T = torch.zeros(No, B, in_channels, H, dtype=torch.float64)
+    P = eval_indices.shape[0]
+    for s in range(0, P, block_pairs):
+        idx = eval_indices[s:s + block_pairs]
+        h = (out_pts[idx[:, 0]] - in_pts[idx[:, 1]]).to(torch.float64)          # :250-253 (fp32 subtract)
+        for W in filt_weights[:-1]:
+            h = torch.sin(torch.nn.functional.linear(h, W.to(torch.float64)))     # :130-145 hidden layers
+        phi = rb(quad_weights[idx[:, 1]].to(torch.float64).unsqueeze(1) * h)      # :247 folded into phi
+        contrib = torch.einsum('ph,bip->pbih', phi, fb[:, :, idx[:, 1]])
+        T.index_add_(0, idx[:, 0], contrib)
+    Wb = rb(filt_weights[-1]).view(in_channels, out_channels, H)
+    out = torch.einsum('obih,ijh->bjo', rb(T), Wb)
+    if bias is not None:
+        out = out + bias.to(torch.float64)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # learned quadrature weights
 # ---------------------------------------------------------------------------------------------

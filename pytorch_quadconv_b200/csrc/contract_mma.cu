@@ -1,0 +1,451 @@
+// contract_mma.cu -- reduced-precision tensor-core path of the fused gather-contract kernel: BOTH stages of the
+// factorised layer on tcgen05 (bf16 operands, fp32 accumulation in TMEM).
+//
+// Reference: QuadConv._integrate + the last Linear of the filter MLP (torch_quadconv/quadconv.py:213-227, :143),
+// in the factorised form of DESIGN.md section 3:
+//     T[o; b,i,h] = sum_{p in N(o)} phi[p][h] * f[b,i,in(p)]          stage B  (gather stage)
+//     Y[o; b,j]   = sum_{i,h} T[o; b,i,h] * W_last[i*Co+j][h]          stage C  (dense stage)
+// The fp32 kernels (contract_tc.cu) run stage B on the FP32 pipe, one (point, batch) row per thread, and
+// re-gather every neighbour row for every destination point (19.7 GB of L2->SM traffic at C3).  Here a CTA
+// works on a TILE of 16 spatially adjacent destination points (cell-sorted order) and on the UNION U of their
+// neighbours (184 rows on average at C3 instead of 16 x 48 = 770: adjacent points share 3/4 of their support):
+//
+//   stage B  D[(o,h)][(b,i)] = sum_{u in U} Phi[(o,h)][u] * X[u][(b,i)]       one dense GEMM per tile
+//            M = 16 points x 8 filter components = 128, N = a chunk of (batch, channel) columns, K = |U|;
+//            Phi is the tile's zero-filled [128 x |U|] block of phi (a block of the block-sparse matrix whose
+//            pattern is eval_indices), X the gathered bf16 feature rows: both MN-major operands in shared memory;
+//   regroup  the fp32 accumulator [(o,h)][(b,i)] is read from TMEM, rounded to bf16 and stored as the K-major
+//            A operand [(o,b)][(h,i)] of stage C (h and b trade places between the two GEMMs);
+//   stage C  Y[(o,b)][j] += T[(o,b)][(h,i)] * W2[(h,i)][j], accumulated over the channel chunks in TMEM.
+//
+// Warp roles (288 threads, 1 CTA per SM, persistent over tiles):
+//   warps 0-3  regroup + output: TMEM -> registers -> shared / global (one TMEM lane per thread)
+//   warps 4-7  producers: build Phi for the tile, gather the union rows chunk by chunk into a ring of K-step
+//              stages with cp.async (16 bytes per lane straight into the operand layout)
+//   warp  8    one thread issues every tcgen05.mma and the tcgen05.commit that releases stages / buffers
+// All hand-offs are mbarriers; the MMAs of channel chunk c+1 run while chunk c is regrouped.
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TP = 16;                 // destination points per tile
+constexpr int NST = 8;                 // ring stages (one K step = 16 union rows each)
+constexpr int LAG = 4;                 // a stage is published once the copies of LAG later stages are issued
+constexpr int DCOLS = 128;             // TMEM columns per stage-B accumulator buffer
+constexpr uint32_t PHI_K8 = TP * 128;  // bytes between groups of 8 union rows in the Phi operand (16 points x 128 B)
+constexpr uint32_t AC_K8 = 144;        // bytes between groups of 8 k in the stage-C A operand (16 B pad: bank spread)
+constexpr int NTHREADS = 288;
+
+struct MmaArgs {
+    const __nv_bfloat16* X;     // packed source features [nblk][Nsrc][nch][Bp][CC]
+    float* Y;                   // packed destination rows, fp32 [nblk][Ndst][CP4/4][Bp][4] (common.cuh)
+    const int* order;           // processing order of the destination points (tile t = entries 16t .. 16t+15); may be null
+    const int* seg_ptr;         // [Ndst+1] pair segments of the destination points
+    const int* phi_idx;         // [P] phi row of each segment entry (CSC view) or null (identity)
+    const int* pair_slot;       // [P] position of each segment entry's source point in its tile's union list
+    const int* tile_uptr;       // [ntiles+1] offsets into union_idx (multiples of 16, at least 16 per tile)
+    const int* union_idx;       // union lists, -1 = padding
+    const float* phi;           // [P][HPphi] fp32
+    const float* w_last;        // [Ci*Co][H] fp32 (filter.{2L}.weight)
+    int Nsrc, Ndst, Cs, Cd, H, HPphi, Bp, nch, transposed, ntiles, nblk, max_ku;   // HPphi = floats per phi row (4 or 8)
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// byte step between groups of 8 rows of the stage-C A operand: 2 chunk halves x CC k-groups, padded so that the
+// regroup stores of a warp (4 points x 8 filter components at one batch lane) spread over all banks
+__host__ __device__ inline uint32_t ac_row8(int CC, int Bp)
+{
+    const uint32_t base = 2u * CC * AC_K8;
+    return base + (Bp >= 32 ? 16u : (Bp == 16 ? 32u : 64u));
+}
+
+template <int CC>
+__global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
+{
+    const int Bp = a.Bp, NC = Bp * CC, nch = a.nch;
+    const int rows = TP * Bp, MBC = rows >> 7;            // rows of the stage-C GEMM per tile, its 128-row blocks
+    const int CdP = max(16, (a.Cd + 15) & ~15);           // N of stage C
+    const uint32_t ACR = ac_row8(CC, Bp);
+    const uint32_t XK8 = (uint32_t)(NC >> 3) * 128;       // bytes between the two k-groups of a ring stage
+    const uint32_t STAGE = 2 * XK8;
+    const uint32_t W2CH = (uint32_t)CdP * 16 * CC;        // bytes of one chunk of the stage-C B operand
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* phi_s = smem;                                        // [max_ku/8][16 points][8 k][8 h] bf16
+    unsigned char* x_s = phi_s + (size_t)a.max_ku * 256;                 // [NST][2][NC/8][8 k][8 n] bf16
+    unsigned char* ac_s = x_s + NST * STAGE;                             // [rows/8][ACR]
+    unsigned char* w2_s = ac_s + (size_t)(rows >> 3) * ACR;              // [nch][CdP/8][CC][8 n][8 k] bf16
+    int* uidx_s = reinterpret_cast<int*>(w2_s + (size_t)nch * W2CH);     // [max_ku]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(uidx_s + a.max_ku);
+    uint64_t* x_full = bars;                 // [NST]  producers (4 warp arrivals) -> MMA
+    uint64_t* x_empty = x_full + NST;        // [NST]  MMA commit -> producers
+    uint64_t* d_full = x_empty + NST;        // [2]    MMA commit -> regroup
+    uint64_t* d_empty = d_full + 2;          // [2]    regroup (4) -> MMA
+    uint64_t* ac_full = d_empty + 2;         // [2]    regroup (4) -> MMA
+    uint64_t* ac_empty = ac_full + 2;        // [2]    MMA commit -> regroup
+    uint64_t* phi_full = ac_empty + 2;       // producers (4) -> MMA
+    uint64_t* phi_empty = phi_full + 1;      // MMA commit -> producers
+    uint64_t* y_full = phi_empty + 1;        // MMA commit -> output
+    uint64_t* y_empty = y_full + 1;          // output (4) -> MMA
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(y_empty + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    // ---- one-time setup ---------------------------------------------------------------------------------
+    if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
+    if (tid == 32) {
+        for (int i = 0; i < NST; ++i) tc::mbar_init(&x_full[i], 4), tc::mbar_init(&x_empty[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&d_full[i], 1), tc::mbar_init(&d_empty[i], 4);
+            tc::mbar_init(&ac_full[i], 4), tc::mbar_init(&ac_empty[i], 1);
+        }
+        tc::mbar_init(phi_full, 4), tc::mbar_init(phi_empty, 1);
+        tc::mbar_init(y_full, 1), tc::mbar_init(y_empty, 4);
+        tc::mbar_fence_init();
+    }
+    // stage-C weights, bf16, K-major [j][(h, channel in chunk)] per channel chunk
+    {
+        const int KC = 8 * CC;
+        const int total = nch * CdP * KC;
+        for (int idx = tid; idx < total; idx += NTHREADS) {
+            const int c = idx / (CdP * KC), r = idx % (CdP * KC);
+            const int n = r / KC, k = r % KC;
+            const int h = k / CC, cs = c * CC + k % CC;
+            float v = 0.f;
+            if (cs < a.Cs && n < a.Cd && h < a.H)
+                v = __ldg(a.w_last + (a.transposed ? ((size_t)n * a.Cs + cs) : ((size_t)cs * a.Cd + n)) * a.H + h);
+            const uint32_t off = (uint32_t)c * W2CH + tc::kmajor16_off(n, k, CC * 128, 128);
+            *reinterpret_cast<__nv_bfloat16*>(w2_s + off) = __float2bfloat16_rn(v);
+        }
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_base_s;
+    const uint32_t tmem_y = tmem + 2 * DCOLS;
+    const int nwork = a.ntiles * a.nblk;
+
+    if (warp >= 4 && warp < 8) {
+        // ===== producers ====================================================================================
+        const int pt = tid - 128, pw = warp - 4;
+        const uint32_t x_sa = tc::smem_u32(x_s);
+        uint32_t xit = 0, pub = 0, tt = 0;
+        for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
+            const int tile = wi % a.ntiles, blk = wi / a.ntiles;
+            const int u0 = a.tile_uptr[tile], ku = a.tile_uptr[tile + 1] - u0, nks = ku >> 4;
+            tc::named_bar_sync(2, 128);                       // every producer is done with the previous union list
+            tc::mbar_wait(phi_empty, (tt & 1) ^ 1);           // ... and the MMAs with the previous Phi
+            for (int i = pt; i < ku; i += 128) uidx_s[i] = a.union_idx[u0 + i];
+            for (int i = pt; i < ku * 16; i += 128) reinterpret_cast<uint4*>(phi_s)[i] = make_uint4(0, 0, 0, 0);
+            tc::named_bar_sync(2, 128);
+            for (int ol = pw; ol < TP; ol += 4) {
+                const int t = tile * TP + ol;
+                if (t < a.Ndst) {
+                    const int dstp = a.order ? a.order[t] : t;
+                    const int beg = a.seg_ptr[dstp], end = a.seg_ptr[dstp + 1];
+                    for (int e = beg + lane; e < end; e += 32) {
+                        const int pid = a.phi_idx ? a.phi_idx[e] : e;
+                        const int slot = a.pair_slot[e];
+                        const float4 p0 = __ldg(reinterpret_cast<const float4*>(a.phi + (size_t)pid * a.HPphi));
+                        float4 p1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (a.HPphi == 8) p1 = __ldg(reinterpret_cast<const float4*>(a.phi + (size_t)pid * 8 + 4));
+                        const uint4 v = make_uint4(pack_bf16(p0.x, p0.y), pack_bf16(p0.z, p0.w), pack_bf16(p1.x, p1.y),
+                                                   pack_bf16(p1.z, p1.w));
+                        *reinterpret_cast<uint4*>(phi_s + (size_t)(slot >> 3) * PHI_K8 + ol * 128 + (slot & 7) * 16) = v;
+                    }
+                }
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(phi_full);
+
+            // gather: per channel chunk, per K step: 16 union rows x NC columns, 16 bytes per lane.  Eight
+            // consecutive lanes copy the same 16-byte column piece of eight different rows = one 128-byte core
+            // matrix of the MN-major operand (no bank conflicts on the shared-memory side).
+            const size_t srow = (size_t)nch * NC;               // elements per source point
+            const __nv_bfloat16* Xb = a.X + (size_t)blk * a.Nsrc * srow;
+            const int npieces = 2 * NC;                          // 16 rows x NC/8 pieces
+            for (int c = 0; c < nch; ++c) {
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint32_t s = xit % NST, ph = (xit / NST) & 1;
+                    tc::mbar_wait(&x_empty[s], ph ^ 1);
+                    for (int pc = pt; pc < npieces; pc += 128) {
+                        const int k8 = pc & 7, q = (pc >> 3) % (NC >> 3), kg = (pc >> 3) / (NC >> 3);
+                        const int u = uidx_s[ks * 16 + kg * 8 + k8];
+                        const __nv_bfloat16* src = Xb + (u >= 0 ? ((size_t)u * srow + (size_t)c * NC + q * 8) : 0);
+                        tc::cp_async16_zfill(x_sa + s * STAGE + kg * XK8 + q * 128 + k8 * 16, src, u >= 0);
+                    }
+                    tc::cp_async_commit();
+                    ++xit;
+                    if (xit - pub > LAG) {                      // the copies of stage `pub` have landed
+                        tc::cp_async_wait<LAG>();
+                        tc::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&x_full[pub % NST]);
+                        ++pub;
+                    }
+                }
+            }
+            // publish the tail of this tile: the MMAs must finish the tile before its Phi can be replaced
+            tc::cp_async_wait<0>();
+            tc::fence_proxy_async();
+            __syncwarp();
+            for (; pub < xit; ++pub)
+                if (lane == 0) tc::mbar_arrive(&x_full[pub % NST]);
+        }
+    } else if (warp == 8) {
+        // ===== MMA issuer (one thread) =====================================================================
+        if (lane == 0) {
+            const uint32_t idB = tc::make_idesc_bf16(128, NC, true, true);
+            const uint32_t idC = tc::make_idesc_bf16(128, CdP, false, false);
+            const uint32_t phi_sa = tc::smem_u32(phi_s), x_sa = tc::smem_u32(x_s), ac_sa = tc::smem_u32(ac_s),
+                           w2_sa = tc::smem_u32(w2_s);
+            uint32_t xit = 0, cc = 0, tt = 0;
+            auto stage_c = [&](int c, uint32_t ccx) {
+                const uint32_t buf = ccx & 1, ph = (ccx >> 1) & 1;
+                if (c == 0) {
+                    tc::mbar_wait(y_empty, (tt & 1) ^ 1);       // the previous tile's output has left TMEM
+                    tc::fence_after_sync();
+                }
+                tc::mbar_wait(&ac_full[buf], ph);
+                tc::fence_after_sync();
+                for (int mb = 0; mb < MBC; ++mb)
+                    for (int k2 = 0; k2 < CC / 2; ++k2) {
+                        const uint64_t da = tc::make_smem_desc(ac_sa + mb * 16 * ACR + (buf * CC + k2 * 2) * AC_K8, AC_K8, ACR);
+                        const uint64_t db = tc::make_smem_desc(w2_sa + c * W2CH + k2 * 256, 128, CC * 128);
+                        tc::mma_bf16_ss(tmem_y + mb * CdP, da, db, idC, c > 0 || k2 > 0);
+                    }
+                tc::mma_commit(&ac_empty[buf]);
+            };
+            for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
+                const int tile = wi % a.ntiles;
+                const int nks = (a.tile_uptr[tile + 1] - a.tile_uptr[tile]) >> 4;
+                tc::mbar_wait(phi_full, tt & 1);
+                tc::fence_after_sync();
+                for (int c = 0; c < nch; ++c, ++cc) {
+                    const uint32_t buf = cc & 1, dph = (cc >> 1) & 1;
+                    tc::mbar_wait(&d_empty[buf], dph ^ 1);       // chunk cc-2 has been read out of this accumulator
+                    tc::fence_after_sync();
+                    for (int ks = 0; ks < nks; ++ks, ++xit) {
+                        const uint32_t s = xit % NST, ph = (xit / NST) & 1;
+                        tc::mbar_wait(&x_full[s], ph);
+                        tc::fence_after_sync();
+                        const uint64_t da = tc::make_smem_desc(phi_sa + ks * 2 * PHI_K8, PHI_K8, 128);
+                        const uint64_t db = tc::make_smem_desc(x_sa + s * STAGE, XK8, 128);
+                        tc::mma_bf16_ss(tmem + buf * DCOLS, da, db, idB, ks > 0);
+                        tc::mma_commit(&x_empty[s]);
+                    }
+                    tc::mma_commit(&d_full[buf]);
+                    if (c == nch - 1) tc::mma_commit(phi_empty);
+                    if (c >= 1) stage_c(c - 1, cc - 1);
+                }
+                stage_c(nch - 1, cc - 1);
+                tc::mma_commit(y_full);
+            }
+        }
+    } else if (warp < 4) {
+        // ===== regroup + output (thread = TMEM lane m = (point in tile, filter component)) ===================
+        const int m = tid;
+        const int ol = m >> 3, h = m & 7;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const size_t yrow = (size_t)qc_cp4(a.Cd) * Bp;
+        uint32_t cc = 0, tt = 0;
+        for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
+            const int tile = wi % a.ntiles, blk = wi / a.ntiles;
+            for (int c = 0; c < nch; ++c, ++cc) {
+                const uint32_t buf = cc & 1, ph = (cc >> 1) & 1;
+                tc::mbar_wait(&d_full[buf], ph);
+                tc::mbar_wait(&ac_empty[buf], ph ^ 1);           // stage C of chunk cc-2 has read this half
+                tc::fence_after_sync();
+                // element (row = ol*Bp + b, k = h*CC + il) of the K-major stage-C operand, chunk half `buf`
+                unsigned char* dst0 = ac_s + (size_t)buf * CC * AC_K8 + (size_t)((h * CC) >> 3) * AC_K8 + ((h * CC) & 7) * 2;
+                for (int g = 0; g < NC / 16; ++g) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(lane_base + tmem + buf * DCOLS + g * 16, r);
+                    tc::wait_ld();
+                    if (CC == 4) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int row = ol * Bp + g * 4 + q;
+                            const uint2 v = make_uint2(pack_bf16(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])),
+                                                       pack_bf16(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+                            *reinterpret_cast<uint2*>(dst0 + (size_t)(row >> 3) * ACR + (row & 7) * 16) = v;
+                        }
+                    } else if (CC == 8) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int row = ol * Bp + g * 2 + q;
+                            const uint4 v = make_uint4(pack_bf16(__uint_as_float(r[8 * q]), __uint_as_float(r[8 * q + 1])),
+                                                       pack_bf16(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3])),
+                                                       pack_bf16(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5])),
+                                                       pack_bf16(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
+                            *reinterpret_cast<uint4*>(dst0 + (size_t)(row >> 3) * ACR + (row & 7) * 16) = v;
+                        }
+                    } else {
+                        const int row = ol * Bp + g;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint4 v = make_uint4(pack_bf16(__uint_as_float(r[8 * q]), __uint_as_float(r[8 * q + 1])),
+                                                       pack_bf16(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3])),
+                                                       pack_bf16(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5])),
+                                                       pack_bf16(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
+                            *reinterpret_cast<uint4*>(dst0 + (size_t)(row >> 3) * ACR + q * AC_K8 + (row & 7) * 16) = v;
+                        }
+                    }
+                }
+                tc::fence_before_sync();
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tc::mbar_arrive(&d_empty[buf]);
+                    tc::mbar_arrive(&ac_full[buf]);
+                }
+            }
+            // output rows of this tile: TMEM lane = row % 128, row = (point in tile) * Bp + batch lane
+            tc::mbar_wait(y_full, tt & 1);
+            tc::fence_after_sync();
+            for (int mb = 0; mb < MBC; ++mb) {
+                const int row = mb * 128 + m;
+                const int o2 = row / Bp, b = row % Bp;
+                const int t = tile * TP + o2;
+                const int dstp = t < a.Ndst ? (a.order ? a.order[t] : t) : -1;
+                float* y = a.Y + ((size_t)blk * a.Ndst + (dstp >= 0 ? dstp : 0)) * yrow + b * 4;
+                for (int g = 0; g < CdP / 16; ++g) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(lane_base + tmem_y + mb * CdP + g * 16, r);
+                    tc::wait_ld();
+                    if (dstp >= 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (g * 16 + 4 * q < a.Cd)
+                                *reinterpret_cast<float4*>(y + (size_t)(g * 4 + q) * Bp * 4) =
+                                    make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(y_empty);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+template <int CC>
+int launch_mma(const MmaArgs& a, cudaStream_t st)
+{
+    const int NC = a.Bp * CC, rows = TP * a.Bp;
+    const int CdP = max(16, (a.Cd + 15) & ~15);
+    const size_t smem = (size_t)a.max_ku * 256 + (size_t)NST * 2 * (NC / 8) * 128 + (size_t)(rows / 8) * ac_row8(CC, a.Bp) +
+                        (size_t)a.nch * CdP * 16 * CC + (size_t)a.max_ku * 4 + 64 * 8;
+    if (smem > 227 * 1024) return 0;
+    QC_CUDA((qc_set_max_smem<k_contract_mma<CC>>((int)smem)));
+    int grid = min(qc_num_sms(), a.ntiles * a.nblk);
+    if (grid < 1) grid = 1;
+    k_contract_mma<CC><<<grid, NTHREADS, smem, st>>>(a);
+    QC_CHECK_LAUNCH();
+    return 1;
+}
+
+// fp32 [B][C][N] -> bf16 packed [nblk][N][nch][Bp][CC]: 64 points x (CC channels x Bp lanes) per block through a
+// padded shared-memory tile; 128-byte row pieces on the [B,C,N] side, CC*2-byte pieces, 2*NC contiguous bytes per
+// point, on the packed side.
+constexpr int PTB = 64, RSB = 65;
+__global__ void __launch_bounds__(256) k_pack_bf16(const float* __restrict__ x, int B, int C, int N, int Bp, int CC,
+                                                   __nv_bfloat16* __restrict__ xp)
+{
+    __shared__ float tile[128 * RSB];      // [(channel in chunk) * Bp + batch lane][point]
+    const int n0 = blockIdx.x * PTB, c = blockIdx.y, blk = blockIdx.z, nch = gridDim.y;
+    const int rows = CC * Bp;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = w; r < rows; r += 8) {
+        const int il = r / Bp, bl = r % Bp;
+        const int ch = c * CC + il, b = blk * 32 + bl;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int n = n0 + half * 32 + lane;
+            float v = 0.f;
+            if (ch < C && b < B && n < N) v = x[((size_t)b * C + ch) * N + n];
+            tile[r * RSB + half * 32 + lane] = v;
+        }
+    }
+    __syncthreads();
+    const int per_pt = rows / 2;           // bf16x2 words per point and chunk
+    for (int idx = threadIdx.x; idx < PTB * per_pt; idx += 256) {
+        const int nl = idx / per_pt, wd = idx % per_pt;
+        const int n = n0 + nl;
+        if (n < N) {
+            const int bl = (2 * wd) / CC, il = (2 * wd) % CC;
+            const uint32_t v = pack_bf16(tile[(il * Bp + bl) * RSB + nl], tile[((il + 1) * Bp + bl) * RSB + nl]);
+            reinterpret_cast<uint32_t*>(xp)[(((size_t)blk * N + n) * nch + c) * per_pt + wd] = v;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int qc_mma_chunk_channels(int Cs, int B)
+{
+    // channels per column chunk: NC = Bp * CC <= 128 columns, CC in {4, 8, 16}
+    const int Bp = qc_bp(B);
+    if (Bp < 8) return 0;
+    int cc = 128 / Bp;
+    while (cc > 4 && cc / 2 >= Cs) cc /= 2;
+    return cc;
+}
+
+int qc_pack_features_bf16(const float* x, int B, int C, int N, int CC, void* xp, void* stream)
+{
+    const int Bp = qc_bp(B);
+    if (B <= 0 || C <= 0 || N <= 0 || (CC != 4 && CC != 8 && CC != 16) || Bp * CC > 128) return QC_EINVAL;
+    dim3 grid(qc_ceil_div(N, PTB), qc_ceil_div(C, CC), qc_nblk(B));
+    k_pack_bf16<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, C, N, Bp, CC, reinterpret_cast<__nv_bfloat16*>(xp));
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const int* seg_ptr, const int* phi_idx, const int* pair_slot,
+                    const int* tile_uptr, const int* union_idx, int ntiles, int max_ku, const float* phi, int H,
+                    int HPphi, const float* w_last, int Cd, int transposed, const int* order, int Ndst, int B, float* Yp,
+                    void* stream)
+{
+    const int Bp = qc_bp(B);
+    const int CC = qc_mma_chunk_channels(Cs, B);
+    if (CC == 0 || H > 8 || H < 1 || (HPphi != 4 && HPphi != 8) || HPphi < H || Cd > 64 || max_ku < 16 || (max_ku & 15)) return QC_EUNSUP;
+    if ((TP * Bp / 128) * max(16, (Cd + 15) & ~15) > 256) return QC_EUNSUP;   // TMEM: stage-C accumulators
+    MmaArgs a;
+    a.X = reinterpret_cast<const __nv_bfloat16*>(Xh);
+    a.Y = Yp;
+    a.order = order;
+    a.seg_ptr = seg_ptr;
+    a.phi_idx = phi_idx;
+    a.pair_slot = pair_slot;
+    a.tile_uptr = tile_uptr;
+    a.union_idx = union_idx;
+    a.phi = phi;
+    a.w_last = w_last;
+    a.Nsrc = Nsrc, a.Ndst = Ndst, a.Cs = Cs, a.Cd = Cd, a.H = H, a.HPphi = HPphi, a.Bp = Bp, a.nch = qc_ceil_div(Cs, CC);
+    a.transposed = transposed, a.ntiles = ntiles, a.nblk = qc_nblk(B), a.max_ku = max_ku;
+    int rc;
+    if (CC == 4) rc = launch_mma<4>(a, (cudaStream_t)stream);
+    else if (CC == 8) rc = launch_mma<8>(a, (cudaStream_t)stream);
+    else rc = launch_mma<16>(a, (cudaStream_t)stream);
+    if (rc == 0) return QC_EUNSUP;
+    return rc == 1 ? 0 : rc;
+}
+
+}  // extern "C"

@@ -187,4 +187,44 @@ __host__ __device__ constexpr uint32_t kmajor_off_bytes(int n, int k, int k_tile
     return (uint32_t)((n >> 3) * (k_tile / 4) * 128 + (k >> 2) * 128 + (n & 7) * 16 + (k & 3) * 4);
 }
 
+// ---- kind::f16 (bf16 operands, fp32 accumulate), both operands from shared memory -------------------------
+// Instruction descriptor: [4,6) D format (1 = f32), [7,10) A format (1 = bf16), [10,13) B format (1 = bf16),
+// [15] A major (0 = K, 1 = MN), [16] B major, [17,23) N>>3, [24,29) M>>4.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major ? (1u << 15) : 0u) | (b_mn_major ? (1u << 16) : 0u) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+// plain arrive (count 1) on a CTA-local mbarrier
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Canonical no-swizzle ("interleave") operand tiles for 16-bit elements, in bytes.  A core matrix is 8 lines of
+// 16 bytes (8 elements); K-major: line = one row (M/N index), the 8 elements run along K;  MN-major: line = one
+// k, the 8 elements run along M/N.  `stride_mn8` = byte step between groups of 8 rows (M/N), `stride_k8` = byte
+// step between groups of 8 k.  Descriptor fields: K-major (LBO = stride_k8, SBO = stride_mn8); MN-major
+// (LBO = stride_k8, SBO = stride_mn8) as well -- the leading-dimension field always steps along K here.
+__host__ __device__ constexpr uint32_t kmajor16_off(int mn, int k, uint32_t stride_mn8, uint32_t stride_k8)
+{
+    return (uint32_t)(mn >> 3) * stride_mn8 + (uint32_t)(k >> 3) * stride_k8 + (uint32_t)(mn & 7) * 16 + (uint32_t)(k & 7) * 2;
+}
+__host__ __device__ constexpr uint32_t mnmajor16_off(int mn, int k, uint32_t stride_mn8, uint32_t stride_k8)
+{
+    return (uint32_t)(mn >> 3) * stride_mn8 + (uint32_t)(k >> 3) * stride_k8 + (uint32_t)(k & 7) * 16 + (uint32_t)(mn & 7) * 2;
+}
+
 }  // namespace tc

@@ -296,6 +296,118 @@ def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor
     return out, phi, xp
 
 
+# ---- reduced-precision tensor-core path (csrc/contract_mma.cu) ---------------------------------
+
+TC_TILE = 16            # destination points per tile (16 points x 8 filter components = the 128 rows of one MMA)
+_TC_MAX_SMEM = 227 * 1024
+
+
+def build_union_tables(seg_ptr: Tensor, src_idx: Tensor, order: Optional[Tensor], n_dst: int, n_src: int):
+    """Tile tables of the tensor-core path, built once per pair list (setup time, like the CSR/CSC tables):
+    destination points are taken 16 at a time in processing order; for every tile the sorted union of its
+    pairs' source points (padded with -1 to a multiple of 16 slots, at least 16) and, for every pair, the slot
+    of its source point in that union.  Returns (pair_slot [P], tile_uptr [ntiles+1], union_idx [total], max_ku)."""
+    dev = seg_ptr.device
+    ntiles = (n_dst + TC_TILE - 1) // TC_TILE
+    i32 = dict(dtype=torch.int32, device=dev)
+    P = int(src_idx.numel())
+    rank = torch.arange(n_dst, device=dev)
+    tile_of_dst = torch.empty(n_dst, dtype=torch.int64, device=dev)
+    if order is None:
+        tile_of_dst = rank // TC_TILE
+    else:
+        tile_of_dst[order.long()] = rank // TC_TILE
+    seg_len = (seg_ptr[1:] - seg_ptr[:-1]).long()
+    ptile = torch.repeat_interleave(tile_of_dst, seg_len, output_size=P)
+    key = ptile * n_src + src_idx.long()
+    uniq, inv = torch.unique(key, return_inverse=True)          # sorted: by tile, then by source index
+    utile = uniq // n_src
+    cnt = torch.bincount(utile, minlength=ntiles)
+    start = torch.cumsum(cnt, 0) - cnt
+    padded = torch.clamp((cnt + 15) // 16 * 16, min=16)
+    uptr = torch.zeros(ntiles + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(padded, 0, out=uptr[1:])
+    slot_u = torch.arange(uniq.numel(), device=dev) - start[utile]
+    total, max_ku = (int(v) for v in torch.stack([uptr[-1], padded.max()]).tolist())
+    union_idx = torch.full((total,), -1, **i32)
+    union_idx[uptr[utile] + slot_u] = (uniq % n_src).to(torch.int32)
+    pair_slot = slot_u[inv].to(torch.int32)
+    return pair_slot, uptr.to(torch.int32), union_idx, max_ku
+
+
+def tc_supported(Cs: int, Cd: int, H: int, B: int, max_ku: int) -> bool:
+    """Shapes served by qc_contract_mma: H <= 8, 8..32 batch lanes per block, destination channels <= 64 (TMEM),
+    operands within 227 KB of shared memory."""
+    L = C.lib()
+    CC = L.qc_mma_chunk_channels(Cs, B)
+    if CC == 0 or H > 8 or Cd > 64:
+        return False
+    Bp = _bp(B)
+    CdP = max(16, (Cd + 15) // 16 * 16)
+    if (TC_TILE * Bp // 128) * CdP > 256:
+        return False
+    nch = (Cs + CC - 1) // CC
+    ac_row8 = 2 * CC * 144 + (16 if Bp >= 32 else (32 if Bp == 16 else 64))
+    smem = max_ku * 256 + 8 * 2 * (Bp * CC // 8) * 128 + (TC_TILE * Bp // 8) * ac_row8 + nch * CdP * 16 * CC + max_ku * 4 + 512
+    return smem <= _TC_MAX_SMEM
+
+
+def _pack_bf16(x: Tensor) -> Tensor:
+    B, Cc, N = x.shape
+    CC = C.lib().qc_mma_chunk_channels(Cc, B)
+    xh = torch.empty((_nblk(B), N, (Cc + CC - 1) // CC, _bp(B), CC), dtype=torch.bfloat16, device=x.device)
+    C.check(C.lib().qc_pack_features_bf16(C.ptr(x), B, Cc, N, CC, C.ptr(xh), C.stream()), "qc_pack_features_bf16")
+    return xh
+
+
+@torch.library.custom_op("quadconv_b200::qc_forward_tc", mutates_args=())
+@_on_device
+def qc_forward_tc(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor,
+                  hidden_ws: Sequence[Tensor], w_last: Tensor, bias: Optional[Tensor],
+                  pair_row: Tensor, pair_col: Tensor, row_ptr: Tensor, order_out: Optional[Tensor],
+                  pair_slot: Tensor, tile_uptr: Tensor, union_idx: Tensor, max_ku: int,
+                  in_channels: int, out_channels: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Forward of the reduced-precision mode: per-pair hidden layers in fp32 (qc_pair_phi_fwd), then both
+    contraction stages on the tensor cores with bf16 operands (qc_contract_mma).  Returns (out, phi, bf16
+    packed features)."""
+    features = _f32c(features, "features")
+    out_pts, in_pts, quad_w = _f32c(out_pts, "points"), _f32c(in_pts, "points"), _f32c(quad_w, "weights")
+    hidden_ws = [_f32c(w, "filter weight") for w in hidden_ws]
+    w_last = _f32c(w_last, "filter weight")
+    B, Ci, Ni = features.shape
+    No, d = out_pts.shape
+    Co = out_channels
+    H = w_last.shape[1]
+    HP = _hp(H)
+    P = pair_row.numel()
+    L = C.lib()
+    st = C.stream()
+    mlp = C.make_mlp(d, hidden_ws, False)
+    phi = torch.empty((max(P, 1), HP), dtype=torch.float32, device=features.device)
+    C.check(L.qc_pair_phi_fwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row), C.ptr(pair_col),
+                              P, d, mlp, HP, C.ptr(phi), st), "qc_pair_phi_fwd")
+    xh = _pack_bf16(features)
+    yp = torch.empty(_packed_shape(B, Co, No), dtype=torch.float32, device=features.device)
+    C.check(L.qc_contract_mma(C.ptr(xh), Ni, Ci, C.ptr(row_ptr), None, C.ptr(pair_slot), C.ptr(tile_uptr),
+                              C.ptr(union_idx), tile_uptr.numel() - 1, max_ku, C.ptr(phi), H, HP, C.ptr(w_last), Co, 0,
+                              C.ptr(order_out), No, B, C.ptr(yp), st), "qc_contract_mma")
+    b2 = None
+    if bias is not None:
+        b2 = _f32c(bias, "bias").reshape(Co, No)
+    return _unpack(yp, B, Co, No, b2), phi, xh
+
+
+@qc_forward_tc.register_fake
+def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair_col, row_ptr, order_out,
+      pair_slot, tile_uptr, union_idx, max_ku, in_channels, out_channels):
+    B, Ci, Ni = features.shape
+    No = out_pts.shape[0]
+    HP = _hp(w_last.shape[1])
+    CC = 4
+    return (features.new_empty((B, out_channels, No)), features.new_empty((pair_row.shape[0], HP)),
+            features.new_empty((_nblk(B), Ni, (Ci + CC - 1) // CC, _bp(B), CC), dtype=torch.bfloat16))
+
+
 @qc_forward.register_fake
 def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair_col, row_ptr, order_out,
       in_channels, out_channels, mlp_bf16=False):
@@ -409,16 +521,24 @@ def _(grad_out, xp, phi, out_pts, in_pts, quad_w, hidden_ws, w_last, pair_row, p
 
 
 class _QuadConvFn(torch.autograd.Function):
-    """Autograd glue: forward/backward are the two custom ops above."""
+    """Autograd glue: forward/backward are the custom ops above."""
 
     @staticmethod
     def forward(ctx, features, quad_w, w_last, bias, tables, dims, *hidden_ws):
         out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = tables
-        Ci, Co, mlp_bf16 = dims
-        out, phi, xp = qc_forward(features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
-                                  pair_col, row_ptr, order_out, Ci, Co, mlp_bf16)
-        ctx.save_for_backward(xp, phi, quad_w, w_last, *hidden_ws)
+        Ci, Co, mlp_bf16, tc = dims
+        if tc is not None:
+            pair_slot, tile_uptr, union_idx, max_ku = tc["fwd"]
+            out, phi, xh = qc_forward_tc(features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
+                                         pair_col, row_ptr, order_out, pair_slot, tile_uptr, union_idx, max_ku, Ci, Co)
+            # (the backward of this mode still runs the fp32 kernels: it re-packs the fp32 features)
+            ctx.save_for_backward(features, phi, quad_w, w_last, *hidden_ws)
+        else:
+            out, phi, xp = qc_forward(features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
+                                      pair_col, row_ptr, order_out, Ci, Co, mlp_bf16)
+            ctx.save_for_backward(xp, phi, quad_w, w_last, *hidden_ws)
         ctx.tables = tables
+        ctx.tc = tc
         ctx.dims = (features.shape[0], Ci, Co, bias is not None, mlp_bf16)
         return out
 
@@ -427,6 +547,9 @@ class _QuadConvFn(torch.autograd.Function):
         xp, phi, quad_w, w_last, *hidden_ws = ctx.saved_tensors
         out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = ctx.tables
         B, Ci, Co, has_bias, mlp_bf16 = ctx.dims
+        if ctx.tc is not None:
+            with torch.cuda.device(xp.device):
+                xp = _pack(_f32c(xp, "features"))
         res = qc_backward(grad_out, xp, phi, out_pts, in_pts, quad_w, list(hidden_ws), w_last, pair_row, pair_col,
                           row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in, B, Ci, Co, has_bias, mlp_bf16)
         d_features, d_quad_w, d_w_last, d_bias = res[:4]
@@ -434,9 +557,10 @@ class _QuadConvFn(torch.autograd.Function):
         return (d_features, d_quad_w, d_w_last, d_bias if has_bias else None, None, None, *d_hidden)
 
 
-def quadconv_apply(features, quad_w, hidden_ws, w_last, bias, tables, in_channels, out_channels, mlp_bf16=False):
-    return _QuadConvFn.apply(features, quad_w, w_last, bias, tables, (in_channels, out_channels, bool(mlp_bf16)),
-                             *hidden_ws)
+def quadconv_apply(features, quad_w, hidden_ws, w_last, bias, tables, in_channels, out_channels, mlp_bf16=False,
+                   tc=None):
+    return _QuadConvFn.apply(features, quad_w, w_last, bias, tables,
+                             (in_channels, out_channels, bool(mlp_bf16), tc), *hidden_ws)
 
 
 # ---------------------------------------------------------------------------------------------

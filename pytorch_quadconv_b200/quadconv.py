@@ -41,7 +41,8 @@ class QuadConv(nn.Module):
                  output_same=False,
                  cache=True,
                  verbose=False,
-                 filter_dtype=torch.float32):
+                 filter_dtype=torch.float32,
+                 compute_dtype=torch.float32):
         super().__init__()
 
         # extension over the reference's signature: torch.bfloat16 evaluates the filter MLP with bf16
@@ -50,6 +51,16 @@ class QuadConv(nn.Module):
         if filter_dtype not in (torch.float32, torch.bfloat16):
             raise ValueError(f"filter_dtype must be torch.float32 or torch.bfloat16 (got {filter_dtype})")
         self.filter_dtype = filter_dtype
+        # second extension: torch.bfloat16 runs BOTH contraction stages on the tensor cores with bf16 operands
+        # (features, phi, the stage-B result and W_last rounded to nearest even; fp32 accumulation) -- the
+        # reduced-precision mode of north_star.  Stated bound: <= 1e-2 normwise from the fp32 layer (tests).
+        # Shapes the tensor-core kernels do not serve (last hidden width > 8, batch < 5, > 64 channels) run the
+        # fp32 kernels instead.
+        if compute_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError(f"compute_dtype must be torch.float32 or torch.bfloat16 (got {compute_dtype})")
+        self.compute_dtype = compute_dtype
+        self._tc = None
+        self._tc_key = None
 
         assert spatial_dim > 0                                   # quadconv.py:44
         # limits of the sm_100a kernels, reported at construction instead of at the first forward (README "Limits")
@@ -188,5 +199,20 @@ class QuadConv(nn.Module):
 
         full = (output_points.detach(), input_points.detach(), pair_row, pair_col, row_ptr, csc_ptr, csc_pair,
                 csc_row, order_out, order_in)
+        tc = None
+        if self.compute_dtype == torch.bfloat16 and pair_row.numel() > 0:
+            tc = self._tc_tables(tables, features.shape[0], w_last.shape[1])
         return ops.quadconv_apply(features, weights, hidden_ws, w_last, self.bias, full,
-                                  self.in_channels, self.out_channels, self.filter_dtype == torch.bfloat16)
+                                  self.in_channels, self.out_channels, self.filter_dtype == torch.bfloat16, tc)
+
+    def _tc_tables(self, tables, B, H):
+        """Union-tile tables of the tensor-core path (ops.build_union_tables), cached with the pair tables."""
+        pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = tables
+        key = (id(pair_row), pair_row.data_ptr())
+        if self._tc is None or self._tc_key != key:
+            fwd = ops.build_union_tables(row_ptr, pair_col, order_out, self.out_points, self.in_points)
+            self._tc = {"fwd": fwd}
+            self._tc_key = key
+        if not ops.tc_supported(self.in_channels, self.out_channels, H, B, self._tc["fwd"][3]):
+            return None
+        return self._tc

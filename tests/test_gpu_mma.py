@@ -1,0 +1,103 @@
+"""GPU: the reduced-precision tensor-core mode, QuadConv(compute_dtype=torch.bfloat16) (csrc/contract_mma.cu:
+both contraction stages on tcgen05 with bf16 operands, fp32 accumulation).
+
+Stated bounds (north_star "with a stated bf16 bound"), normwise relative:
+  * vs the oracle doing the SAME operand roundings in float64 (quadconv_forward_bf16tc): <= 2e-4
+    (what is left is fp32 accumulation order and roundings that flip at bf16 boundaries);
+  * vs the exact fp32-mode layer (float64 oracle of the reference formulas):              <= 1e-2 (measured ~3e-3),
+    and > 1e-5, i.e. the mode really is a different arithmetic.
+fp32 mode stays the parity mode (tests/test_gpu_layer.py, 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+from test_gpu_layer import _StubMesh, _oracle_case
+
+pytestmark = pytest.mark.gpu
+TOL_SAME_ROUNDING = 2e-4
+TOL_VS_FP32 = 1e-2
+
+
+def _layer(c, d, n, ci, co, fs, r, bias, No, same):
+    import pytorch_quadconv_b200 as q
+    layer = q.QuadConv(spatial_dim=d, in_points=n, out_points=No, in_channels=ci, out_channels=co,
+                       filter_seq=fs, bias=bias, output_same=same, decay_param=r,
+                       compute_dtype=torch.bfloat16).cuda()
+    with torch.no_grad():
+        lin = [m for m in layer.filter if isinstance(m, torch.nn.Linear)]
+        for m, w in zip(lin, c["ws"]):
+            m.weight.copy_(w.detach())
+        if bias:
+            layer.bias.copy_(c["b"].detach())
+    return layer, lin
+
+
+def test_stage_b_exposed(cuda_lib):
+    """Diagnostic known-answer test: with 4 input channels (one column chunk) and W_last chosen so that output
+    channel j = h*4 + i picks T[o,b,i,h], the layer output IS the gather stage's result T (rounded to bf16)."""
+    from oracle import quadconv_oracle as O
+    d, n, ci, co, B, fs, r = 2, 600, 4, 32, 32, [8, 8], 0.1
+    c = _oracle_case(d, n, ci, co, B, fs, r, False, seed=77)
+    wl = torch.zeros(ci * co, 8)
+    for i in range(ci):
+        for h in range(8):
+            wl[i * co + (h * 4 + i), h] = 1.0
+    c["ws"][-1] = wl
+    layer, _ = _layer(c, d, n, ci, co, fs, r, False, n, True)
+    assert layer.compute_dtype == torch.bfloat16
+    mesh = _StubMesh(c["pts"].cuda(), c["out_pts"].cuda(), c["qw"].detach().cuda())
+    y = layer(mesh, c["x"].detach().cuda())
+    assert layer._tc is not None, "the tensor-core path did not run"
+    ref = O.quadconv_forward_bf16tc(c["out_pts"], c["pts"], c["qw"].detach(), [w.detach() for w in c["ws"]],
+                                    c["x"].detach(), c["pairs"], ci, co)
+    err = relerr(y.detach().cpu().numpy(), ref.numpy())
+    assert err < TOL_SAME_ROUNDING, err
+
+
+@pytest.mark.parametrize("d,n,ci,co,B,fs,r,bias,n_out", [
+    (3, 1500, 32, 32, 32, [8, 8], 0.16, True, None),    # C3-like: 8 column chunks of 4 channels, 4 row blocks
+    (2, 900, 16, 16, 8, [4, 4], 0.1, False, None),      # C1-like: batch 8 -> 16 channels per chunk, H = 4 (phi rows of 4)
+    (2, 1000, 4, 8, 8, [8, 8], 0.08, True, None),       # C2's first layer: 4 channels, 32-column chunks
+    (2, 800, 8, 12, 16, [8, 8], 0.09, True, 300),       # batch 16 -> 8 channels per chunk; cross-level (No != Ni)
+    (2, 700, 20, 24, 40, [8], 0.1, False, None),        # batch 40: two batch blocks; partial last chunk; one hidden layer
+    (2, 1200, 8, 8, 8, [8, 8], 0.012, True, 500),       # tiny radius: most out points have no pair, empty tiles
+    (2, 50, 8, 8, 32, [8, 8], 0.3, False, None),        # fewer points than four tiles
+    (3, 900, 32, 64, 32, [8, 5], 0.2, False, None),     # 64 output channels (TMEM full), H = 5
+    (2, 600, 6, 5, 9, [6], 0.25, True, None),           # odd channels, batch 9 -> 16 lanes, ~118 pairs/point
+])
+def test_tc_forward_matches_same_rounding_oracle(cuda_lib, d, n, ci, co, B, fs, r, bias, n_out):
+    from oracle import quadconv_oracle as O
+    c = _oracle_case(d, n, ci, co, B, fs, r, bias, seed=7000 + n + ci, n_out=n_out)
+    same = n_out is None
+    No = c["out_pts"].shape[0]
+    layer, lin = _layer(c, d, n, ci, co, fs, r, bias, No, same)
+    w_dev = c["qw"].detach().cuda().requires_grad_()
+    mesh = _StubMesh(c["pts"].cuda(), c["out_pts"].cuda(), w_dev)
+    x = c["x"].detach().cuda().requires_grad_()
+    y = layer(mesh, x)
+    assert layer._tc is not None and layer._tc["fwd"][3] % 16 == 0
+    assert torch.equal(layer.eval_indices.cpu(), c["pairs"])                # the pair list does not depend on the mode
+    ref = O.quadconv_forward_bf16tc(c["out_pts"], c["pts"], c["qw"].detach(), [w.detach() for w in c["ws"]],
+                                    c["x"].detach(), c["pairs"], ci, co, c["b"].detach() if bias else None)
+    e_same = relerr(y.detach().cpu().numpy(), ref.numpy())
+    e_fp32 = relerr(y.detach().cpu().numpy(), c["y"].numpy())
+    assert e_same < TOL_SAME_ROUNDING, (e_same, e_fp32)
+    assert 1e-5 < e_fp32 < TOL_VS_FP32, e_fp32
+    # backward of the mode (currently the fp32 kernels on the fp32 features): exact-gradient bound
+    (y * c["go"].cuda()).sum().backward()
+    assert relerr(x.grad.cpu().numpy(), c["x"].grad.numpy()) < TOL_VS_FP32
+    assert relerr(w_dev.grad.cpu().numpy(), c["qw"].grad.numpy()) < TOL_VS_FP32
+    for m, w in zip(lin, c["ws"]):
+        assert relerr(m.weight.grad.cpu().numpy(), w.grad.numpy()) < TOL_VS_FP32
+
+
+def test_tc_falls_back_outside_its_shapes(cuda_lib):
+    """H = 16 (wide filter) and batch 3 are not served by the tensor-core kernels: the layer runs the fp32 path."""
+    import pytorch_quadconv_b200 as q
+    for (ci, co, B, fs) in ((8, 8, 8, [16]), (8, 8, 3, [8, 8])):
+        c = _oracle_case(2, 400, ci, co, B, fs, 0.12, False, seed=5)
+        layer, _ = _layer(c, 2, 400, ci, co, fs, 0.12, False, 400, True)
+        mesh = _StubMesh(c["pts"].cuda(), c["out_pts"].cuda(), c["qw"].detach().cuda())
+        y = layer(mesh, c["x"].detach().cuda())
+        assert relerr(y.detach().cpu().numpy(), c["y"].numpy()) < 1e-5

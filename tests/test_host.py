@@ -95,3 +95,36 @@ def test_ctor_validation():
     layer = q.QuadConv(spatial_dim=2, in_points=16, out_points=16, in_channels=1, out_channels=1, filter_seq=[2])
     assert float(layer.decay_param) == 1.0 and layer.bias is None and layer.cached is False
     assert q.MeshMaxPool is q.Mesh_MaxPool
+
+
+def test_union_tile_tables_host_logic():
+    """ops.build_union_tables (tables of the tensor-core path) against a brute-force construction: every pair's
+    slot points at its own source point, unions are sorted, padded to multiples of 16 with -1, tiles follow
+    the processing order."""
+    import numpy as np
+    import torch
+    from pytorch_quadconv_b200 import ops
+    rng = np.random.default_rng(0)
+    n_dst, n_src = 70, 50
+    lens = rng.integers(0, 9, n_dst)
+    lens[5] = 0
+    seg = np.zeros(n_dst + 1, dtype=np.int32)
+    np.cumsum(lens, out=seg[1:])
+    src = np.concatenate([np.sort(rng.choice(n_src, l, replace=False)) for l in lens]).astype(np.int32)
+    order = rng.permutation(n_dst).astype(np.int32)
+    for od in (None, order):
+        slot, uptr, uidx, max_ku = ops.build_union_tables(torch.from_numpy(seg), torch.from_numpy(src),
+                                                          None if od is None else torch.from_numpy(od), n_dst, n_src)
+        slot, uptr, uidx = slot.numpy(), uptr.numpy(), uidx.numpy()
+        ntiles = (n_dst + 15) // 16
+        assert uptr.shape == (ntiles + 1,) and uptr[0] == 0 and np.all(np.diff(uptr) % 16 == 0) and np.all(np.diff(uptr) >= 16)
+        assert max_ku == np.diff(uptr).max()
+        proc = np.arange(n_dst) if od is None else od
+        for t in range(ntiles):
+            members = proc[t * 16:(t + 1) * 16]
+            want = np.unique(np.concatenate([src[seg[m]:seg[m + 1]] for m in members] + [np.zeros(0, np.int32)]))
+            got = uidx[uptr[t]:uptr[t + 1]]
+            assert np.array_equal(got[:len(want)], want) and np.all(got[len(want):] == -1)
+            for m in members:
+                for e in range(seg[m], seg[m + 1]):
+                    assert got[slot[e]] == src[e]
