@@ -235,23 +235,26 @@ int qc_weight_map_bwd(const float* pts, const int* adj, int M, int E, int d, con
  * torch_quadconv/quadconv.py:213-227, :143 -- with BOTH stages of the factorised layer on tcgen05
  * (csrc/contract_mma.cu).  Work unit: a tile of 16 destination points (consecutive entries of `order`) and the
  * union of their source points:
- *   tile_uptr[ntiles+1] : offsets into union_idx, every tile padded to a multiple of 16 entries (>= 16)
+ *   tile_uptr[ntiles+1] : offsets into union_idx, every tile padded to a multiple of 32 entries (>= 32)
  *   union_idx[]         : source point of every union slot, -1 = padding
- *   pair_slot[P]        : union slot of every segment entry (segment order = seg_ptr order)
- *   max_ku              : largest padded union (bounds the shared-memory operand; QC_EUNSUP when it does not fit)
+ *   tile_ent[P] (int2)  : the pairs grouped by tile: {phi row, (point in tile << 16) | union slot};
+ *   tile_pptr[ntiles+1] : offsets into tile_ent
+ *   max_ku              : largest padded union (bounds the shared-memory operand; QC_EUNSUP when it does not fit:
+ *                         qc_mma_smem_bytes(...) <= 227 KB)
  * bf16 packed features  Xh[nblk][N][ceil(C/CC)][Bp][CC], CC = qc_mma_chunk_channels(C, B) in {4,8,16}.
  * Output: fp32 packed rows (same layout as qc_contract, feed qc_unpack_features).
  * transposed = 0: forward (sources = in points / in channels);  1: the d-features pass on the CSC view
- * (sources = out points / out channels, phi rows through phi_idx).
+ * (sources = out points / out channels).
  * Numerics: features, phi, the stage-B result T and W_last are rounded to bf16 (nearest even); both
  * accumulations are fp32.  Stated bound vs the fp32 layer: <= 1e-2 normwise (measured ~3e-3), tests/.
  * ------------------------------------------------------------------------------------------ */
 int qc_mma_chunk_channels(int C, int B);          /* 0: batch lanes < 8, not served */
+int qc_mma_smem_bytes(int Cs, int Cd, int B, int max_ku);
 int qc_pack_features_bf16(const float* x /*[B][C][N]*/, int B, int C, int N, int CC, void* xh, void* stream);
-int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const int* seg_ptr, const int* phi_idx, const int* pair_slot,
-                    const int* tile_uptr, const int* union_idx, int ntiles, int max_ku, const float* phi, int H,
-                    int HPphi, const float* w_last, int Cd, int transposed, const int* order, int Ndst, int B,
-                    float* Yp, void* stream);
+int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const void* tile_ent, const int* tile_pptr, const int* tile_uptr,
+                    const int* union_idx, int ntiles, int max_ku, const float* phi, int H, int HPphi,
+                    const float* w_last, int Cd, int transposed, const int* order, int Ndst, int B, float* Yp,
+                    void* stream);
 
 /* Known-answer self test of the tcgen05 building blocks (TMEM alloc, tcgen05.st/ld, kind::tf32 MMA with
  * A in TMEM and B through a K-major shared-memory descriptor, 3xTF32 split):

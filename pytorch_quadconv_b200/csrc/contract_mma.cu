@@ -31,9 +31,11 @@
 namespace {
 
 constexpr int TP = 16;                 // destination points per tile
-constexpr int NST = 8;                 // ring stages (one K step = 16 union rows each)
-constexpr int LAG = 4;                 // a stage is published once the copies of LAG later stages are issued
+constexpr int KST = 32;                // union rows per ring stage (two K steps of 16)
+constexpr int NST = 8;                 // ring stages
+constexpr int LAG = 6;                 // a stage is published once the copies of LAG later stages are issued
 constexpr int DCOLS = 128;             // TMEM columns per stage-B accumulator buffer
+constexpr int ENT_R = 8;               // pair entries per producer thread held in registers (1024 pairs per tile)
 constexpr uint32_t PHI_K8 = TP * 128;  // bytes between groups of 8 union rows in the Phi operand (16 points x 128 B)
 constexpr uint32_t AC_K8 = 144;        // bytes between groups of 8 k in the stage-C A operand (16 B pad: bank spread)
 constexpr int NTHREADS = 288;
@@ -42,14 +44,13 @@ struct MmaArgs {
     const __nv_bfloat16* X;     // packed source features [nblk][Nsrc][nch][Bp][CC]
     float* Y;                   // packed destination rows, fp32 [nblk][Ndst][CP4/4][Bp][4] (common.cuh)
     const int* order;           // processing order of the destination points (tile t = entries 16t .. 16t+15); may be null
-    const int* seg_ptr;         // [Ndst+1] pair segments of the destination points
-    const int* phi_idx;         // [P] phi row of each segment entry (CSC view) or null (identity)
-    const int* pair_slot;       // [P] position of each segment entry's source point in its tile's union list
-    const int* tile_uptr;       // [ntiles+1] offsets into union_idx (multiples of 16, at least 16 per tile)
+    const int2* tile_ent;       // pair entries grouped by tile: {phi row, (point in tile << 16) | union slot}
+    const int* tile_pptr;       // [ntiles+1] offsets into tile_ent
+    const int* tile_uptr;       // [ntiles+1] offsets into union_idx (multiples of 32, at least 32 per tile)
     const int* union_idx;       // union lists, -1 = padding
     const float* phi;           // [P][HPphi] fp32
     const float* w_last;        // [Ci*Co][H] fp32 (filter.{2L}.weight)
-    int Nsrc, Ndst, Cs, Cd, H, HPphi, Bp, nch, transposed, ntiles, nblk, max_ku;   // HPphi = floats per phi row (4 or 8)
+    int Nsrc, Ndst, Cs, Cd, H, HPphi, nch, transposed, ntiles, nblk, max_ku;   // HPphi = floats per phi row (4 or 8)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
@@ -58,39 +59,45 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
     return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// byte step between groups of 8 rows of the stage-C A operand: 2 chunk halves x CC k-groups, padded so that the
-// regroup stores of a warp (4 points x 8 filter components at one batch lane) spread over all banks
-__host__ __device__ inline uint32_t ac_row8(int CC, int Bp)
+// byte step between groups of 8 rows of the stage-C A operand (CC k-groups of one channel chunk), padded so that
+// the regroup stores of a warp (4 points x 8 filter components at one batch lane) spread over all banks
+__host__ __device__ constexpr uint32_t ac_row8(int CC, int Bp)
 {
-    const uint32_t base = 2u * CC * AC_K8;
-    return base + (Bp >= 32 ? 16u : (Bp == 16 ? 32u : 64u));
+    return (uint32_t)CC * AC_K8 + (Bp >= 32 ? 16u : (Bp == 16 ? 32u : 64u));
 }
 
-template <int CC>
+__host__ __device__ constexpr size_t mma_smem_bytes(int CC, int Bp, int nch, int CdP, int max_ku)
+{
+    return (size_t)max_ku * 256 + (size_t)NST * KST * Bp * CC * 2 + (size_t)(TP * Bp / 8) * ac_row8(CC, Bp) +
+           (size_t)nch * CdP * 16 * CC + (size_t)max_ku * 4 + 64 * 8;
+}
+
+template <int CC, int LB>
 __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
 {
-    const int Bp = a.Bp, NC = Bp * CC, nch = a.nch;
-    const int rows = TP * Bp, MBC = rows >> 7;            // rows of the stage-C GEMM per tile, its 128-row blocks
+    constexpr int Bp = 1 << LB, NC = Bp * CC, QN = NC / 8;
+    constexpr int rows = TP * Bp, MBC = rows / 128;       // rows of the stage-C GEMM per tile, its 128-row blocks
+    constexpr uint32_t ACR = ac_row8(CC, Bp);
+    constexpr uint32_t XK8 = (uint32_t)QN * 128;          // bytes between k-groups (8 union rows) of a ring stage
+    constexpr uint32_t STAGE = (KST / 8) * XK8;
+    const int nch = a.nch;
     const int CdP = max(16, (a.Cd + 15) & ~15);           // N of stage C
-    const uint32_t ACR = ac_row8(CC, Bp);
-    const uint32_t XK8 = (uint32_t)(NC >> 3) * 128;       // bytes between the two k-groups of a ring stage
-    const uint32_t STAGE = 2 * XK8;
     const uint32_t W2CH = (uint32_t)CdP * 16 * CC;        // bytes of one chunk of the stage-C B operand
 
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* phi_s = smem;                                        // [max_ku/8][16 points][8 k][8 h] bf16
-    unsigned char* x_s = phi_s + (size_t)a.max_ku * 256;                 // [NST][2][NC/8][8 k][8 n] bf16
+    unsigned char* x_s = phi_s + (size_t)a.max_ku * 256;                 // [NST][4][QN][8 k][8 n] bf16
     unsigned char* ac_s = x_s + NST * STAGE;                             // [rows/8][ACR]
-    unsigned char* w2_s = ac_s + (size_t)(rows >> 3) * ACR;              // [nch][CdP/8][CC][8 n][8 k] bf16
+    unsigned char* w2_s = ac_s + (size_t)(rows / 8) * ACR;               // [nch][CdP/8][CC][8 n][8 k] bf16
     int* uidx_s = reinterpret_cast<int*>(w2_s + (size_t)nch * W2CH);     // [max_ku]
     uint64_t* bars = reinterpret_cast<uint64_t*>(uidx_s + a.max_ku);
     uint64_t* x_full = bars;                 // [NST]  producers (4 warp arrivals) -> MMA
     uint64_t* x_empty = x_full + NST;        // [NST]  MMA commit -> producers
     uint64_t* d_full = x_empty + NST;        // [2]    MMA commit -> regroup
     uint64_t* d_empty = d_full + 2;          // [2]    regroup (4) -> MMA
-    uint64_t* ac_full = d_empty + 2;         // [2]    regroup (4) -> MMA
-    uint64_t* ac_empty = ac_full + 2;        // [2]    MMA commit -> regroup
-    uint64_t* phi_full = ac_empty + 2;       // producers (4) -> MMA
+    uint64_t* ac_full = d_empty + 2;         // regroup (4) -> MMA
+    uint64_t* ac_empty = ac_full + 1;        // MMA commit -> regroup
+    uint64_t* phi_full = ac_empty + 1;       // producers (4) -> MMA
     uint64_t* phi_empty = phi_full + 1;      // MMA commit -> producers
     uint64_t* y_full = phi_empty + 1;        // MMA commit -> output
     uint64_t* y_empty = y_full + 1;          // output (4) -> MMA
@@ -103,17 +110,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
     if (tid == 32) {
         for (int i = 0; i < NST; ++i) tc::mbar_init(&x_full[i], 4), tc::mbar_init(&x_empty[i], 1);
-        for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&d_full[i], 1), tc::mbar_init(&d_empty[i], 4);
-            tc::mbar_init(&ac_full[i], 4), tc::mbar_init(&ac_empty[i], 1);
-        }
+        for (int i = 0; i < 2; ++i) tc::mbar_init(&d_full[i], 1), tc::mbar_init(&d_empty[i], 4);
+        tc::mbar_init(ac_full, 4), tc::mbar_init(ac_empty, 1);
         tc::mbar_init(phi_full, 4), tc::mbar_init(phi_empty, 1);
         tc::mbar_init(y_full, 1), tc::mbar_init(y_empty, 4);
         tc::mbar_fence_init();
     }
     // stage-C weights, bf16, K-major [j][(h, channel in chunk)] per channel chunk
     {
-        const int KC = 8 * CC;
+        constexpr int KC = 8 * CC;
         const int total = nch * CdP * KC;
         for (int idx = tid; idx < total; idx += NTHREADS) {
             const int c = idx / (CdP * KC), r = idx % (CdP * KC);
@@ -136,53 +141,78 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
 
     if (warp >= 4 && warp < 8) {
         // ===== producers ====================================================================================
-        const int pt = tid - 128, pw = warp - 4;
+        const int pt = tid - 128;
         const uint32_t x_sa = tc::smem_u32(x_s);
         uint32_t xit = 0, pub = 0, tt = 0;
+        // pair entries of a tile, ENT_R per thread in registers, fetched one tile ahead
+        int2 ent[ENT_R];
+        auto fetch_entries = [&](int wi2) {
+            if (wi2 < nwork) {
+                const int tile2 = wi2 % a.ntiles;
+                const int p0 = a.tile_pptr[tile2], np = a.tile_pptr[tile2 + 1] - p0;
+#pragma unroll
+                for (int r = 0; r < ENT_R; ++r) {
+                    const int i = pt + r * 128;
+                    ent[r] = i < np ? __ldg(a.tile_ent + p0 + i) : make_int2(-1, 0);
+                }
+            }
+        };
+        auto phi_row = [&](int pid) -> uint4 {
+            const float4 p0 = __ldg(reinterpret_cast<const float4*>(a.phi + (size_t)pid * a.HPphi));
+            float4 p1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.HPphi == 8) p1 = __ldg(reinterpret_cast<const float4*>(a.phi + (size_t)pid * 8 + 4));
+            return make_uint4(pack_bf16(p0.x, p0.y), pack_bf16(p0.z, p0.w), pack_bf16(p1.x, p1.y), pack_bf16(p1.z, p1.w));
+        };
+        auto phi_put = [&](int meta, const uint4& v) {
+            const int ol = meta >> 16, slot = meta & 0xffff;
+            *reinterpret_cast<uint4*>(phi_s + (size_t)(slot >> 3) * PHI_K8 + ol * 128 + (slot & 7) * 16) = v;
+        };
+        fetch_entries(blockIdx.x);
         for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
             const int tile = wi % a.ntiles, blk = wi / a.ntiles;
-            const int u0 = a.tile_uptr[tile], ku = a.tile_uptr[tile + 1] - u0, nks = ku >> 4;
+            const int u0 = a.tile_uptr[tile], ku = a.tile_uptr[tile + 1] - u0, nst = ku / KST;
+            const int p0 = a.tile_pptr[tile], np = a.tile_pptr[tile + 1] - p0;
+            // phi rows of this tile (the loads fly while the MMAs finish the previous tile)
+            uint4 pv[ENT_R];
+#pragma unroll
+            for (int r = 0; r < ENT_R; ++r)
+                if (ent[r].x >= 0) pv[r] = phi_row(ent[r].x);
             tc::named_bar_sync(2, 128);                       // every producer is done with the previous union list
             tc::mbar_wait(phi_empty, (tt & 1) ^ 1);           // ... and the MMAs with the previous Phi
-            for (int i = pt; i < ku; i += 128) uidx_s[i] = a.union_idx[u0 + i];
+            for (int i = pt; i < ku; i += 128) uidx_s[i] = __ldg(a.union_idx + u0 + i);
             for (int i = pt; i < ku * 16; i += 128) reinterpret_cast<uint4*>(phi_s)[i] = make_uint4(0, 0, 0, 0);
             tc::named_bar_sync(2, 128);
-            for (int ol = pw; ol < TP; ol += 4) {
-                const int t = tile * TP + ol;
-                if (t < a.Ndst) {
-                    const int dstp = a.order ? a.order[t] : t;
-                    const int beg = a.seg_ptr[dstp], end = a.seg_ptr[dstp + 1];
-                    for (int e = beg + lane; e < end; e += 32) {
-                        const int pid = a.phi_idx ? a.phi_idx[e] : e;
-                        const int slot = a.pair_slot[e];
-                        const float4 p0 = __ldg(reinterpret_cast<const float4*>(a.phi + (size_t)pid * a.HPphi));
-                        float4 p1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (a.HPphi == 8) p1 = __ldg(reinterpret_cast<const float4*>(a.phi + (size_t)pid * 8 + 4));
-                        const uint4 v = make_uint4(pack_bf16(p0.x, p0.y), pack_bf16(p0.z, p0.w), pack_bf16(p1.x, p1.y),
-                                                   pack_bf16(p1.z, p1.w));
-                        *reinterpret_cast<uint4*>(phi_s + (size_t)(slot >> 3) * PHI_K8 + ol * 128 + (slot & 7) * 16) = v;
-                    }
-                }
+#pragma unroll
+            for (int r = 0; r < ENT_R; ++r)
+                if (ent[r].x >= 0) phi_put(ent[r].y, pv[r]);
+            for (int i = pt + ENT_R * 128; i < np; i += 128) {   // tiles with more than 1024 pairs
+                const int2 e = __ldg(a.tile_ent + p0 + i);
+                phi_put(e.y, phi_row(e.x));
             }
             tc::fence_proxy_async();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(phi_full);
+            fetch_entries(wi + gridDim.x);
 
-            // gather: per channel chunk, per K step: 16 union rows x NC columns, 16 bytes per lane.  Eight
+            // gather: per channel chunk, per stage: 32 union rows x NC columns, 16 bytes per lane.  Eight
             // consecutive lanes copy the same 16-byte column piece of eight different rows = one 128-byte core
             // matrix of the MN-major operand (no bank conflicts on the shared-memory side).
+            constexpr size_t dummy = 0;
+            (void)dummy;
             const size_t srow = (size_t)nch * NC;               // elements per source point
             const __nv_bfloat16* Xb = a.X + (size_t)blk * a.Nsrc * srow;
-            const int npieces = 2 * NC;                          // 16 rows x NC/8 pieces
+            const int k8 = pt & 7, q = (pt >> 3) % QN, kg0 = (pt >> 3) / QN;
+            constexpr int KGSTEP = 16 / QN;
+            const uint32_t dst0 = x_sa + q * 128 + k8 * 16;
             for (int c = 0; c < nch; ++c) {
-                for (int ks = 0; ks < nks; ++ks) {
+                const __nv_bfloat16* Xc = Xb + (size_t)c * NC + q * 8;
+                for (int st = 0; st < nst; ++st) {
                     const uint32_t s = xit % NST, ph = (xit / NST) & 1;
                     tc::mbar_wait(&x_empty[s], ph ^ 1);
-                    for (int pc = pt; pc < npieces; pc += 128) {
-                        const int k8 = pc & 7, q = (pc >> 3) % (NC >> 3), kg = (pc >> 3) / (NC >> 3);
-                        const int u = uidx_s[ks * 16 + kg * 8 + k8];
-                        const __nv_bfloat16* src = Xb + (u >= 0 ? ((size_t)u * srow + (size_t)c * NC + q * 8) : 0);
-                        tc::cp_async16_zfill(x_sa + s * STAGE + kg * XK8 + q * 128 + k8 * 16, src, u >= 0);
+#pragma unroll
+                    for (int kg = kg0; kg < KST / 8; kg += KGSTEP) {
+                        const int u = uidx_s[st * KST + kg * 8 + k8];
+                        tc::cp_async16_zfill(dst0 + s * STAGE + kg * XK8, Xc + (u >= 0 ? (size_t)u * srow : 0), u >= 0);
                     }
                     tc::cp_async_commit();
                     ++xit;
@@ -211,37 +241,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
                            w2_sa = tc::smem_u32(w2_s);
             uint32_t xit = 0, cc = 0, tt = 0;
             auto stage_c = [&](int c, uint32_t ccx) {
-                const uint32_t buf = ccx & 1, ph = (ccx >> 1) & 1;
                 if (c == 0) {
                     tc::mbar_wait(y_empty, (tt & 1) ^ 1);       // the previous tile's output has left TMEM
                     tc::fence_after_sync();
                 }
-                tc::mbar_wait(&ac_full[buf], ph);
+                tc::mbar_wait(ac_full, ccx & 1);
                 tc::fence_after_sync();
                 for (int mb = 0; mb < MBC; ++mb)
+#pragma unroll
                     for (int k2 = 0; k2 < CC / 2; ++k2) {
-                        const uint64_t da = tc::make_smem_desc(ac_sa + mb * 16 * ACR + (buf * CC + k2 * 2) * AC_K8, AC_K8, ACR);
+                        const uint64_t da = tc::make_smem_desc(ac_sa + mb * 16 * ACR + k2 * 2 * AC_K8, AC_K8, ACR);
                         const uint64_t db = tc::make_smem_desc(w2_sa + c * W2CH + k2 * 256, 128, CC * 128);
                         tc::mma_bf16_ss(tmem_y + mb * CdP, da, db, idC, c > 0 || k2 > 0);
                     }
-                tc::mma_commit(&ac_empty[buf]);
+                tc::mma_commit(ac_empty);
             };
             for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
                 const int tile = wi % a.ntiles;
-                const int nks = (a.tile_uptr[tile + 1] - a.tile_uptr[tile]) >> 4;
+                const int nst = (a.tile_uptr[tile + 1] - a.tile_uptr[tile]) / KST;
                 tc::mbar_wait(phi_full, tt & 1);
                 tc::fence_after_sync();
                 for (int c = 0; c < nch; ++c, ++cc) {
                     const uint32_t buf = cc & 1, dph = (cc >> 1) & 1;
                     tc::mbar_wait(&d_empty[buf], dph ^ 1);       // chunk cc-2 has been read out of this accumulator
                     tc::fence_after_sync();
-                    for (int ks = 0; ks < nks; ++ks, ++xit) {
+                    for (int st = 0; st < nst; ++st, ++xit) {
                         const uint32_t s = xit % NST, ph = (xit / NST) & 1;
                         tc::mbar_wait(&x_full[s], ph);
                         tc::fence_after_sync();
-                        const uint64_t da = tc::make_smem_desc(phi_sa + ks * 2 * PHI_K8, PHI_K8, 128);
-                        const uint64_t db = tc::make_smem_desc(x_sa + s * STAGE, XK8, 128);
-                        tc::mma_bf16_ss(tmem + buf * DCOLS, da, db, idB, ks > 0);
+#pragma unroll
+                        for (int k2 = 0; k2 < KST / 16; ++k2) {
+                            const uint64_t da = tc::make_smem_desc(phi_sa + (st * (KST / 16) + k2) * 2 * PHI_K8, PHI_K8, 128);
+                            const uint64_t db = tc::make_smem_desc(x_sa + s * STAGE + k2 * 2 * XK8, XK8, 128);
+                            tc::mma_bf16_ss(tmem + buf * DCOLS, da, db, idB, st > 0 || k2 > 0);
+                        }
                         tc::mma_commit(&x_empty[s]);
                     }
                     tc::mma_commit(&d_full[buf]);
@@ -258,16 +291,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
         const int ol = m >> 3, h = m & 7;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
         const size_t yrow = (size_t)qc_cp4(a.Cd) * Bp;
+        // element (row = ol*Bp + b, k = h*CC + il) of the K-major stage-C operand
+        unsigned char* dst0 = ac_s + (size_t)((h * CC) >> 3) * AC_K8 + ((h * CC) & 7) * 2;
         uint32_t cc = 0, tt = 0;
         for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
             const int tile = wi % a.ntiles, blk = wi / a.ntiles;
             for (int c = 0; c < nch; ++c, ++cc) {
                 const uint32_t buf = cc & 1, ph = (cc >> 1) & 1;
                 tc::mbar_wait(&d_full[buf], ph);
-                tc::mbar_wait(&ac_empty[buf], ph ^ 1);           // stage C of chunk cc-2 has read this half
+                tc::mbar_wait(ac_empty, (cc & 1) ^ 1);           // stage C of the previous chunk has read the tile
                 tc::fence_after_sync();
-                // element (row = ol*Bp + b, k = h*CC + il) of the K-major stage-C operand, chunk half `buf`
-                unsigned char* dst0 = ac_s + (size_t)buf * CC * AC_K8 + (size_t)((h * CC) >> 3) * AC_K8 + ((h * CC) & 7) * 2;
+#pragma unroll 2
                 for (int g = 0; g < NC / 16; ++g) {
                     uint32_t r[16];
                     tc::tmem_ld16(lane_base + tmem + buf * DCOLS + g * 16, r);
@@ -307,7 +341,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
                 __syncwarp();
                 if (lane == 0) {
                     tc::mbar_arrive(&d_empty[buf]);
-                    tc::mbar_arrive(&ac_full[buf]);
+                    tc::mbar_arrive(ac_full);
                 }
             }
             // output rows of this tile: TMEM lane = row % 128, row = (point in tile) * Bp + batch lane
@@ -343,18 +377,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-template <int CC>
+template <int CC, int LB>
 int launch_mma(const MmaArgs& a, cudaStream_t st)
 {
-    const int NC = a.Bp * CC, rows = TP * a.Bp;
     const int CdP = max(16, (a.Cd + 15) & ~15);
-    const size_t smem = (size_t)a.max_ku * 256 + (size_t)NST * 2 * (NC / 8) * 128 + (size_t)(rows / 8) * ac_row8(CC, a.Bp) +
-                        (size_t)a.nch * CdP * 16 * CC + (size_t)a.max_ku * 4 + 64 * 8;
+    const size_t smem = mma_smem_bytes(CC, 1 << LB, a.nch, CdP, a.max_ku);
     if (smem > 227 * 1024) return 0;
-    QC_CUDA((qc_set_max_smem<k_contract_mma<CC>>((int)smem)));
+    QC_CUDA((qc_set_max_smem<k_contract_mma<CC, LB>>((int)smem)));
     int grid = min(qc_num_sms(), a.ntiles * a.nblk);
     if (grid < 1) grid = 1;
-    k_contract_mma<CC><<<grid, NTHREADS, smem, st>>>(a);
+    k_contract_mma<CC, LB><<<grid, NTHREADS, smem, st>>>(a);
     QC_CHECK_LAUNCH();
     return 1;
 }
@@ -418,32 +450,41 @@ int qc_pack_features_bf16(const float* x, int B, int C, int N, int CC, void* xp,
     return 0;
 }
 
-int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const int* seg_ptr, const int* phi_idx, const int* pair_slot,
-                    const int* tile_uptr, const int* union_idx, int ntiles, int max_ku, const float* phi, int H,
-                    int HPphi, const float* w_last, int Cd, int transposed, const int* order, int Ndst, int B, float* Yp,
+int qc_mma_smem_bytes(int Cs, int Cd, int B, int max_ku)
+{
+    const int CC = qc_mma_chunk_channels(Cs, B);
+    if (CC == 0) return 0;
+    return (int)mma_smem_bytes(CC, qc_bp(B), qc_ceil_div(Cs, CC), max(16, (Cd + 15) & ~15), max_ku);
+}
+
+int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const void* tile_ent, const int* tile_pptr, const int* tile_uptr,
+                    const int* union_idx, int ntiles, int max_ku, const float* phi, int H, int HPphi,
+                    const float* w_last, int Cd, int transposed, const int* order, int Ndst, int B, float* Yp,
                     void* stream)
 {
     const int Bp = qc_bp(B);
     const int CC = qc_mma_chunk_channels(Cs, B);
-    if (CC == 0 || H > 8 || H < 1 || (HPphi != 4 && HPphi != 8) || HPphi < H || Cd > 64 || max_ku < 16 || (max_ku & 15)) return QC_EUNSUP;
+    if (CC == 0 || H > 8 || H < 1 || (HPphi != 4 && HPphi != 8) || HPphi < H || Cd > 64 || max_ku < KST || (max_ku % KST) ||
+        max_ku > 0xffff)
+        return QC_EUNSUP;
     if ((TP * Bp / 128) * max(16, (Cd + 15) & ~15) > 256) return QC_EUNSUP;   // TMEM: stage-C accumulators
     MmaArgs a;
     a.X = reinterpret_cast<const __nv_bfloat16*>(Xh);
     a.Y = Yp;
     a.order = order;
-    a.seg_ptr = seg_ptr;
-    a.phi_idx = phi_idx;
-    a.pair_slot = pair_slot;
+    a.tile_ent = reinterpret_cast<const int2*>(tile_ent);
+    a.tile_pptr = tile_pptr;
     a.tile_uptr = tile_uptr;
     a.union_idx = union_idx;
     a.phi = phi;
     a.w_last = w_last;
-    a.Nsrc = Nsrc, a.Ndst = Ndst, a.Cs = Cs, a.Cd = Cd, a.H = H, a.HPphi = HPphi, a.Bp = Bp, a.nch = qc_ceil_div(Cs, CC);
+    a.Nsrc = Nsrc, a.Ndst = Ndst, a.Cs = Cs, a.Cd = Cd, a.H = H, a.HPphi = HPphi, a.nch = qc_ceil_div(Cs, CC);
     a.transposed = transposed, a.ntiles = ntiles, a.nblk = qc_nblk(B), a.max_ku = max_ku;
-    int rc;
-    if (CC == 4) rc = launch_mma<4>(a, (cudaStream_t)stream);
-    else if (CC == 8) rc = launch_mma<8>(a, (cudaStream_t)stream);
-    else rc = launch_mma<16>(a, (cudaStream_t)stream);
+    const cudaStream_t st = (cudaStream_t)stream;
+    int rc = 0;
+    if (Bp == 32) rc = launch_mma<4, 5>(a, st);
+    else if (Bp == 16) rc = CC == 8 ? launch_mma<8, 4>(a, st) : launch_mma<4, 4>(a, st);
+    else if (Bp == 8) rc = CC == 16 ? launch_mma<16, 3>(a, st) : (CC == 8 ? launch_mma<8, 3>(a, st) : launch_mma<4, 3>(a, st));
     if (rc == 0) return QC_EUNSUP;
     return rc == 1 ? 0 : rc;
 }

@@ -98,7 +98,10 @@ def _csc(pair_row: Tensor, pair_col: Tensor, Ni: int) -> Tuple[Tensor, Tensor, T
 @_on_device
 def build_pairs(out_pts: Tensor, in_pts: Tensor, radius: float, same: bool) -> List[Tensor]:
     """Grid-binned neighbour search.  Returns
-    [eval_indices int64 [P,2], pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in]."""
+    [eval_indices int64 [P,2], pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in,
+     cell_out, cell_in]: the last two are the plain cell-sorted orders (16 consecutive entries = spatial neighbours,
+    the tiles of the tensor-core path), order_out/in the same re-sorted by segment length inside 2048-point windows
+    (the processing order of the fp32 kernels)."""
     out_pts = _f32c(out_pts, "output points")
     in_pts = _f32c(in_pts, "input points")
     if same:
@@ -132,8 +135,7 @@ def build_pairs(out_pts: Tensor, in_pts: Tensor, radius: float, same: bool) -> L
     bal_out, bal_in = torch.empty_like(order_out), torch.empty_like(order_in)
     C.check(L.qc_balance_order(C.ptr(order_out), C.ptr(row_ptr), No, C.ptr(bal_out), C.stream()), "qc_balance_order")
     C.check(L.qc_balance_order(C.ptr(order_in), C.ptr(csc_ptr), Ni, C.ptr(bal_in), C.stream()), "qc_balance_order")
-    order_out, order_in = bal_out, bal_in
-    return [ev, pair_row, pair_col, row_ptr, csc_ptr, csc_pair[:P], csc_row[:P], order_out, order_in]
+    return [ev, pair_row, pair_col, row_ptr, csc_ptr, csc_pair[:P], csc_row[:P], bal_out, bal_in, order_out, order_in]
 
 
 @build_pairs.register_fake
@@ -144,7 +146,8 @@ def _(out_pts, in_pts, radius, same):
     i32 = dict(dtype=torch.int32, device=in_pts.device)
     return [in_pts.new_empty((P, 2), dtype=torch.int64), in_pts.new_empty(P, **i32), in_pts.new_empty(P, **i32),
             in_pts.new_empty(No + 1, **i32), in_pts.new_empty(Ni + 1, **i32), in_pts.new_empty(P, **i32),
-            in_pts.new_empty(P, **i32), in_pts.new_empty(No, **i32), in_pts.new_empty(Ni, **i32)]
+            in_pts.new_empty(P, **i32), in_pts.new_empty(No, **i32), in_pts.new_empty(Ni, **i32),
+            in_pts.new_empty(No, **i32), in_pts.new_empty(Ni, **i32)]
 
 
 @torch.library.custom_op("quadconv_b200::pairs_to_tables", mutates_args=())
@@ -302,54 +305,59 @@ TC_TILE = 16            # destination points per tile (16 points x 8 filter comp
 _TC_MAX_SMEM = 227 * 1024
 
 
-def build_union_tables(seg_ptr: Tensor, src_idx: Tensor, order: Optional[Tensor], n_dst: int, n_src: int):
+def build_union_tables(seg_ptr: Tensor, src_idx: Tensor, order: Optional[Tensor], n_dst: int, n_src: int,
+                       phi_idx: Optional[Tensor] = None):
     """Tile tables of the tensor-core path, built once per pair list (setup time, like the CSR/CSC tables):
     destination points are taken 16 at a time in processing order; for every tile the sorted union of its
-    pairs' source points (padded with -1 to a multiple of 16 slots, at least 16) and, for every pair, the slot
-    of its source point in that union.  Returns (pair_slot [P], tile_uptr [ntiles+1], union_idx [total], max_ku)."""
+    pairs' source points (padded with -1 to a multiple of 32 slots, at least 32) and the tile's pairs as
+    entries {phi row, (point in tile << 16) | union slot}.  `phi_idx` maps a segment entry to its phi row
+    (the CSC view; identity when None).
+    Returns (tile_ent int32 [P,2], tile_pptr [ntiles+1], tile_uptr [ntiles+1], union_idx [total], max_ku)."""
     dev = seg_ptr.device
     ntiles = (n_dst + TC_TILE - 1) // TC_TILE
     i32 = dict(dtype=torch.int32, device=dev)
     P = int(src_idx.numel())
     rank = torch.arange(n_dst, device=dev)
-    tile_of_dst = torch.empty(n_dst, dtype=torch.int64, device=dev)
+    rank_of_dst = torch.empty(n_dst, dtype=torch.int64, device=dev)
     if order is None:
-        tile_of_dst = rank // TC_TILE
+        rank_of_dst = rank
     else:
-        tile_of_dst[order.long()] = rank // TC_TILE
+        rank_of_dst[order.long()] = rank
     seg_len = (seg_ptr[1:] - seg_ptr[:-1]).long()
-    ptile = torch.repeat_interleave(tile_of_dst, seg_len, output_size=P)
+    prank = torch.repeat_interleave(rank_of_dst, seg_len, output_size=P)     # processing rank of every pair's destination
+    ptile = prank // TC_TILE
     key = ptile * n_src + src_idx.long()
     uniq, inv = torch.unique(key, return_inverse=True)          # sorted: by tile, then by source index
     utile = uniq // n_src
     cnt = torch.bincount(utile, minlength=ntiles)
     start = torch.cumsum(cnt, 0) - cnt
-    padded = torch.clamp((cnt + 15) // 16 * 16, min=16)
+    padded = torch.clamp((cnt + 31) // 32 * 32, min=32)
     uptr = torch.zeros(ntiles + 1, dtype=torch.int64, device=dev)
     torch.cumsum(padded, 0, out=uptr[1:])
     slot_u = torch.arange(uniq.numel(), device=dev) - start[utile]
     total, max_ku = (int(v) for v in torch.stack([uptr[-1], padded.max()]).tolist())
     union_idx = torch.full((total,), -1, **i32)
     union_idx[uptr[utile] + slot_u] = (uniq % n_src).to(torch.int32)
-    pair_slot = slot_u[inv].to(torch.int32)
-    return pair_slot, uptr.to(torch.int32), union_idx, max_ku
+    # the pairs grouped by tile (stable: destination rank, then segment order)
+    perm = torch.argsort(prank, stable=True)
+    phi_row = perm if phi_idx is None else phi_idx.long()[perm]
+    meta = ((prank[perm] % TC_TILE) << 16) | slot_u[inv][perm]
+    tile_ent = torch.stack([phi_row, meta], dim=1).to(torch.int32).contiguous()
+    pptr = torch.zeros(ntiles + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(torch.bincount(ptile, minlength=ntiles), 0, out=pptr[1:])
+    return tile_ent, pptr.to(torch.int32), uptr.to(torch.int32), union_idx, max_ku
 
 
 def tc_supported(Cs: int, Cd: int, H: int, B: int, max_ku: int) -> bool:
     """Shapes served by qc_contract_mma: H <= 8, 8..32 batch lanes per block, destination channels <= 64 (TMEM),
     operands within 227 KB of shared memory."""
     L = C.lib()
-    CC = L.qc_mma_chunk_channels(Cs, B)
-    if CC == 0 or H > 8 or Cd > 64:
+    if L.qc_mma_chunk_channels(Cs, B) == 0 or H > 8 or Cd > 64 or max_ku > 0xffff:
         return False
-    Bp = _bp(B)
     CdP = max(16, (Cd + 15) // 16 * 16)
-    if (TC_TILE * Bp // 128) * CdP > 256:
+    if (TC_TILE * _bp(B) // 128) * CdP > 256:
         return False
-    nch = (Cs + CC - 1) // CC
-    ac_row8 = 2 * CC * 144 + (16 if Bp >= 32 else (32 if Bp == 16 else 64))
-    smem = max_ku * 256 + 8 * 2 * (Bp * CC // 8) * 128 + (TC_TILE * Bp // 8) * ac_row8 + nch * CdP * 16 * CC + max_ku * 4 + 512
-    return smem <= _TC_MAX_SMEM
+    return 0 < L.qc_mma_smem_bytes(Cs, Cd, B, max_ku) <= _TC_MAX_SMEM
 
 
 def _pack_bf16(x: Tensor) -> Tensor:
@@ -364,8 +372,8 @@ def _pack_bf16(x: Tensor) -> Tensor:
 @_on_device
 def qc_forward_tc(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor,
                   hidden_ws: Sequence[Tensor], w_last: Tensor, bias: Optional[Tensor],
-                  pair_row: Tensor, pair_col: Tensor, row_ptr: Tensor, order_out: Optional[Tensor],
-                  pair_slot: Tensor, tile_uptr: Tensor, union_idx: Tensor, max_ku: int,
+                  pair_row: Tensor, pair_col: Tensor, order_out: Optional[Tensor],
+                  tile_ent: Tensor, tile_pptr: Tensor, tile_uptr: Tensor, union_idx: Tensor, max_ku: int,
                   in_channels: int, out_channels: int) -> Tuple[Tensor, Tensor, Tensor]:
     """Forward of the reduced-precision mode: per-pair hidden layers in fp32 (qc_pair_phi_fwd), then both
     contraction stages on the tensor cores with bf16 operands (qc_contract_mma).  Returns (out, phi, bf16
@@ -388,7 +396,7 @@ def qc_forward_tc(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Ten
                               P, d, mlp, HP, C.ptr(phi), st), "qc_pair_phi_fwd")
     xh = _pack_bf16(features)
     yp = torch.empty(_packed_shape(B, Co, No), dtype=torch.float32, device=features.device)
-    C.check(L.qc_contract_mma(C.ptr(xh), Ni, Ci, C.ptr(row_ptr), None, C.ptr(pair_slot), C.ptr(tile_uptr),
+    C.check(L.qc_contract_mma(C.ptr(xh), Ni, Ci, C.ptr(tile_ent), C.ptr(tile_pptr), C.ptr(tile_uptr),
                               C.ptr(union_idx), tile_uptr.numel() - 1, max_ku, C.ptr(phi), H, HP, C.ptr(w_last), Co, 0,
                               C.ptr(order_out), No, B, C.ptr(yp), st), "qc_contract_mma")
     b2 = None
@@ -398,8 +406,8 @@ def qc_forward_tc(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Ten
 
 
 @qc_forward_tc.register_fake
-def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair_col, row_ptr, order_out,
-      pair_slot, tile_uptr, union_idx, max_ku, in_channels, out_channels):
+def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair_col, order_out,
+      tile_ent, tile_pptr, tile_uptr, union_idx, max_ku, in_channels, out_channels):
     B, Ci, Ni = features.shape
     No = out_pts.shape[0]
     HP = _hp(w_last.shape[1])
@@ -525,12 +533,12 @@ class _QuadConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, features, quad_w, w_last, bias, tables, dims, *hidden_ws):
-        out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = tables
+        out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = tables[:10]
         Ci, Co, mlp_bf16, tc = dims
         if tc is not None:
-            pair_slot, tile_uptr, union_idx, max_ku = tc["fwd"]
+            tile_ent, tile_pptr, tile_uptr, union_idx, max_ku = tc["fwd"]
             out, phi, xh = qc_forward_tc(features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
-                                         pair_col, row_ptr, order_out, pair_slot, tile_uptr, union_idx, max_ku, Ci, Co)
+                                         pair_col, tc["order_out"], tile_ent, tile_pptr, tile_uptr, union_idx, max_ku, Ci, Co)
             # (the backward of this mode still runs the fp32 kernels: it re-packs the fp32 features)
             ctx.save_for_backward(features, phi, quad_w, w_last, *hidden_ws)
         else:
@@ -545,7 +553,7 @@ class _QuadConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         xp, phi, quad_w, w_last, *hidden_ws = ctx.saved_tensors
-        out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = ctx.tables
+        out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = ctx.tables[:10]
         B, Ci, Co, has_bias, mlp_bf16 = ctx.dims
         if ctx.tc is not None:
             with torch.cuda.device(xp.device):

@@ -61,6 +61,7 @@ class QuadConv(nn.Module):
         self.compute_dtype = compute_dtype
         self._tc = None
         self._tc_key = None
+        self.tc_active = False           # whether the last forward ran the tensor-core kernels
 
         assert spatial_dim > 0                                   # quadconv.py:44
         # limits of the sm_100a kernels, reported at construction instead of at the first forward (README "Limits")
@@ -172,7 +173,7 @@ class QuadConv(nn.Module):
         key = self._pairs_key()
         if self._tables is None or self._tables_key != key:
             t = ops.pairs_to_tables(self.eval_indices.data, self.out_points, self.in_points)
-            self._tables = tuple(t) + (None, None)
+            self._tables = tuple(t) + (None, None, None, None)
             self._tables_key = key
         return self._tables
 
@@ -192,7 +193,7 @@ class QuadConv(nn.Module):
         if not self.output_same:                                 # quadconv.py:253-254
             mesh.step()
 
-        pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = tables
+        pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = tables[:8]
         linears = [m for m in self.filter if isinstance(m, nn.Linear)]
         hidden_ws = [m.weight for m in linears[:-1]]
         w_last = linears[-1].weight
@@ -207,12 +208,12 @@ class QuadConv(nn.Module):
 
     def _tc_tables(self, tables, B, H):
         """Union-tile tables of the tensor-core path (ops.build_union_tables), cached with the pair tables."""
-        pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = tables
+        pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, _, _, cell_out, cell_in = tables
         key = (id(pair_row), pair_row.data_ptr())
         if self._tc is None or self._tc_key != key:
-            fwd = ops.build_union_tables(row_ptr, pair_col, order_out, self.out_points, self.in_points)
-            self._tc = {"fwd": fwd}
+            # tiles = 16 consecutive points of the plain cell-sorted order (spatial neighbours share their supports)
+            fwd = ops.build_union_tables(row_ptr, pair_col, cell_out, self.out_points, self.in_points)
+            self._tc = {"fwd": fwd, "order_out": cell_out, "order_in": cell_in}
             self._tc_key = key
-        if not ops.tc_supported(self.in_channels, self.out_channels, H, B, self._tc["fwd"][3]):
-            return None
-        return self._tc
+        self.tc_active = ops.tc_supported(self.in_channels, self.out_channels, H, B, self._tc["fwd"][4])
+        return self._tc if self.tc_active else None

@@ -48,7 +48,7 @@ def test_stage_b_exposed(cuda_lib):
     assert layer.compute_dtype == torch.bfloat16
     mesh = _StubMesh(c["pts"].cuda(), c["out_pts"].cuda(), c["qw"].detach().cuda())
     y = layer(mesh, c["x"].detach().cuda())
-    assert layer._tc is not None, "the tensor-core path did not run"
+    assert layer.tc_active, "the tensor-core path did not run"
     ref = O.quadconv_forward_bf16tc(c["out_pts"], c["pts"], c["qw"].detach(), [w.detach() for w in c["ws"]],
                                     c["x"].detach(), c["pairs"], ci, co)
     err = relerr(y.detach().cpu().numpy(), ref.numpy())
@@ -63,8 +63,8 @@ def test_stage_b_exposed(cuda_lib):
     (2, 700, 20, 24, 40, [8], 0.1, False, None),        # batch 40: two batch blocks; partial last chunk; one hidden layer
     (2, 1200, 8, 8, 8, [8, 8], 0.012, True, 500),       # tiny radius: most out points have no pair, empty tiles
     (2, 50, 8, 8, 32, [8, 8], 0.3, False, None),        # fewer points than four tiles
-    (3, 900, 32, 64, 32, [8, 5], 0.2, False, None),     # 64 output channels (TMEM full), H = 5
-    (2, 600, 6, 5, 9, [6], 0.25, True, None),           # odd channels, batch 9 -> 16 lanes, ~118 pairs/point
+    (3, 900, 32, 64, 32, [8, 5], 0.12, False, None),    # 64 output channels (TMEM full), H = 5
+    (2, 600, 6, 5, 9, [6], 0.15, True, None),           # odd channels, batch 9 -> 16 lanes
 ])
 def test_tc_forward_matches_same_rounding_oracle(cuda_lib, d, n, ci, co, B, fs, r, bias, n_out):
     from oracle import quadconv_oracle as O
@@ -76,7 +76,7 @@ def test_tc_forward_matches_same_rounding_oracle(cuda_lib, d, n, ci, co, B, fs, 
     mesh = _StubMesh(c["pts"].cuda(), c["out_pts"].cuda(), w_dev)
     x = c["x"].detach().cuda().requires_grad_()
     y = layer(mesh, x)
-    assert layer._tc is not None and layer._tc["fwd"][3] % 16 == 0
+    assert layer.tc_active and layer._tc["fwd"][4] % 32 == 0
     assert torch.equal(layer.eval_indices.cpu(), c["pairs"])                # the pair list does not depend on the mode
     ref = O.quadconv_forward_bf16tc(c["out_pts"], c["pts"], c["qw"].detach(), [w.detach() for w in c["ws"]],
                                     c["x"].detach(), c["pairs"], ci, co, c["b"].detach() if bias else None)
@@ -100,4 +100,5 @@ def test_tc_falls_back_outside_its_shapes(cuda_lib):
         layer, _ = _layer(c, 2, 400, ci, co, fs, 0.12, False, 400, True)
         mesh = _StubMesh(c["pts"].cuda(), c["out_pts"].cuda(), c["qw"].detach().cuda())
         y = layer(mesh, c["x"].detach().cuda())
+        assert not layer.tc_active
         assert relerr(y.detach().cpu().numpy(), c["y"].numpy()) < 1e-5

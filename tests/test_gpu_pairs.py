@@ -19,7 +19,7 @@ def _search(out_pts, in_pts, r, same):
 
 
 def _check_tables(res, No, Ni):
-    ev, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = res
+    ev, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in, cell_out, cell_in = res
     P = ev.shape[0]
     assert row_ptr[0] == 0 and row_ptr[-1] == P and csc_ptr[0] == 0 and csc_ptr[-1] == P
     assert np.array_equal(pair_row, ev[:, 0].astype(np.int32))
@@ -32,6 +32,7 @@ def _check_tables(res, No, Ni):
     assert np.array_equal(csc_row, ev[perm, 0].astype(np.int32))
     assert np.array_equal(np.sort(order_out), np.arange(No))
     assert np.array_equal(np.sort(order_in), np.arange(Ni))
+    assert np.array_equal(np.sort(cell_out), np.arange(No)) and np.array_equal(np.sort(cell_in), np.arange(Ni))
 
 
 def test_pairs_match_reference_golden(cuda_lib):

@@ -113,18 +113,24 @@ def test_union_tile_tables_host_logic():
     src = np.concatenate([np.sort(rng.choice(n_src, l, replace=False)) for l in lens]).astype(np.int32)
     order = rng.permutation(n_dst).astype(np.int32)
     for od in (None, order):
-        slot, uptr, uidx, max_ku = ops.build_union_tables(torch.from_numpy(seg), torch.from_numpy(src),
-                                                          None if od is None else torch.from_numpy(od), n_dst, n_src)
-        slot, uptr, uidx = slot.numpy(), uptr.numpy(), uidx.numpy()
+        ent, pptr, uptr, uidx, max_ku = ops.build_union_tables(torch.from_numpy(seg), torch.from_numpy(src),
+                                                               None if od is None else torch.from_numpy(od), n_dst, n_src)
+        ent, pptr, uptr, uidx = ent.numpy(), pptr.numpy(), uptr.numpy(), uidx.numpy()
         ntiles = (n_dst + 15) // 16
-        assert uptr.shape == (ntiles + 1,) and uptr[0] == 0 and np.all(np.diff(uptr) % 16 == 0) and np.all(np.diff(uptr) >= 16)
+        assert uptr.shape == (ntiles + 1,) and uptr[0] == 0 and np.all(np.diff(uptr) % 32 == 0) and np.all(np.diff(uptr) >= 32)
         assert max_ku == np.diff(uptr).max()
+        assert pptr[0] == 0 and pptr[-1] == len(src) and ent.shape == (len(src), 2)
         proc = np.arange(n_dst) if od is None else od
+        seen = np.zeros(len(src), dtype=bool)
         for t in range(ntiles):
             members = proc[t * 16:(t + 1) * 16]
             want = np.unique(np.concatenate([src[seg[m]:seg[m + 1]] for m in members] + [np.zeros(0, np.int32)]))
             got = uidx[uptr[t]:uptr[t + 1]]
             assert np.array_equal(got[:len(want)], want) and np.all(got[len(want):] == -1)
-            for m in members:
-                for e in range(seg[m], seg[m + 1]):
-                    assert got[slot[e]] == src[e]
+            assert pptr[t + 1] - pptr[t] == sum(seg[m + 1] - seg[m] for m in members)
+            for e, meta in ent[pptr[t]:pptr[t + 1]]:
+                ol, slot = meta >> 16, meta & 0xffff
+                m = members[ol]
+                assert seg[m] <= e < seg[m + 1] and got[slot] == src[e] and not seen[e]
+                seen[e] = True
+        assert seen.all()
