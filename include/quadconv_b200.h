@@ -265,6 +265,10 @@ int qc_tc_selftest_ss(const float* A, const float* B, float* D, void* stream);
 /* probe of the operand major-ness for 16-bit operands (kind::f16, bf16): D[128x32] = A[128x32] * B[32x32]^T;
  * mode bit 0: A MN-major, bit 1: B MN-major (K-major otherwise) */
 int qc_tc_probe_bf16(const float* A, const float* B, float* D, int mode, void* stream);
+/* diagnostic micro-benchmark: cycles for `iters` back-to-back kind::f16 MMAs (SS mode) with the given operand layouts
+ * (major-ness, LBO/SBO, K-step advance in bytes, descriptor layout type), per CTA into out[grid]. */
+int qc_tc_mma_bench(int M, int N, int a_mn, int b_mn, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int a_kstep,
+                    int b_kstep, int swz, int iters, int grid, long long* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,7 @@ _SIGNATURES = {
     "qc_tc_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "qc_tc_selftest_ss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "qc_tc_probe_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "qc_tc_mma_bench": (c_int, [c_int] * 13 + [c_void_p, c_void_p]),
     "qc_weight_map_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
     "qc_vertex_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "qc_weight_map_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p,

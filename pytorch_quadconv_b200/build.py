@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("QC_NVCC_EXTRA", "").split() + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
             procs.append((src, subprocess.Popen(cmd)))

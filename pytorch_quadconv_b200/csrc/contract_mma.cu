@@ -25,6 +25,7 @@
 //   warp  8    one thread issues every tcgen05.mma and the tcgen05.commit that releases stages / buffers
 // All hand-offs are mbarriers; the MMAs of channel chunk c+1 run while chunk c is regrouped.
 #include <cuda_bf16.h>
+#include <cstdio>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -35,10 +36,12 @@ constexpr int KST = 32;                // union rows per ring stage (two K steps
 constexpr int NST = 8;                 // ring stages
 constexpr int LAG = 6;                 // a stage is published once the copies of LAG later stages are issued
 constexpr int DCOLS = 128;             // TMEM columns per stage-B accumulator buffer
+constexpr int PF_CH = 0;               // L2 prefetch distance of the gather in channel chunks (0 = off: measured slower,
+                                       // the prefetches compete with the copies for the same LSU request slots)
 constexpr int ENT_R = 8;               // pair entries per producer thread held in registers (1024 pairs per tile)
 constexpr uint32_t PHI_K8 = TP * 128;  // bytes between groups of 8 union rows in the Phi operand (16 points x 128 B)
 constexpr uint32_t AC_K8 = 144;        // bytes between groups of 8 k in the stage-C A operand (16 B pad: bank spread)
-constexpr int NTHREADS = 288;
+constexpr int NTHREADS = 448;         // 4 regroup + 4 producer + 2 issuer + 4 regroup warps
 
 struct MmaArgs {
     const __nv_bfloat16* X;     // packed source features [nblk][Nsrc][nch][Bp][CC]
@@ -51,7 +54,18 @@ struct MmaArgs {
     const float* phi;           // [P][HPphi] fp32
     const float* w_last;        // [Ci*Co][H] fp32 (filter.{2L}.weight)
     int Nsrc, Ndst, Cs, Cd, H, HPphi, nch, transposed, ntiles, nblk, max_ku;   // HPphi = floats per phi row (4 or 8)
+    long long* dbg;             // QC_MMA_PROFILE builds: wait-cycle counters of CTA 0 (null otherwise)
 };
+
+#ifdef QC_MMA_PROFILE
+#define PROF_DECL(n) long long n = 0
+#define PROF_T0() const long long t0__ = clock64()
+#define PROF_ADD(n) n += clock64() - t0__
+#define PROF_WAIT(n, ...) do { const long long t0__ = clock64(); __VA_ARGS__; n += clock64() - t0__; } while (0)
+#else
+#define PROF_DECL(n)
+#define PROF_WAIT(n, ...) do { __VA_ARGS__; } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
 {
@@ -68,30 +82,39 @@ __host__ __device__ constexpr uint32_t ac_row8(int CC, int Bp)
 
 __host__ __device__ constexpr size_t mma_smem_bytes(int CC, int Bp, int nch, int CdP, int max_ku)
 {
-    return (size_t)max_ku * 256 + (size_t)NST * KST * Bp * CC * 2 + (size_t)(TP * Bp / 8) * ac_row8(CC, Bp) +
-           (size_t)nch * CdP * 16 * CC + (size_t)max_ku * 4 + 64 * 8;
+    return (size_t)max_ku * 256 + (size_t)NST * (KST / 8) * (Bp * CC / 8) * 144 + (size_t)(TP * Bp / 8) * ac_row8(CC, Bp) +
+           (size_t)nch * CdP * 16 * CC + (size_t)max_ku * 8 + 64 * 8;
 }
 
-template <int CC, int LB>
+// VAR (gather experiment): bit 0 = cp.async.cg (bypass L1), bit 1 = n-chunk stride 144 B so that a quarter warp copies
+// ONE row's 128 contiguous bytes (8 chunks) without bank conflicts instead of 16 bytes of 8 rows
+template <int CC, int LB, int VAR>
 __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
 {
     constexpr int Bp = 1 << LB, NC = Bp * CC, QN = NC / 8;
+    constexpr bool CG = (VAR & 1) != 0, ROWMAJ = (VAR & 2) != 0;
+    // bit 2: the gathered operand in the 128-byte-swizzle MN-major layout (rows of 64 columns = 128 contiguous bytes,
+    // 16-byte chunks XOR-ed with the row index inside 1 KB atoms): a 128-byte line from L2 lands as ONE shared-memory
+    // wavefront (the no-swizzle layouts scatter it into eight 16-byte pieces, 6x the LSU data-pipe traffic, ncu)
+    constexpr bool SW = (VAR & 4) != 0 && (NC % 64 == 0);
+    constexpr uint32_t XSB = ROWMAJ ? 144 : 128;          // bytes between 8-column chunks of the gathered operand
     constexpr int rows = TP * Bp, MBC = rows / 128;       // rows of the stage-C GEMM per tile, its 128-row blocks
     constexpr uint32_t ACR = ac_row8(CC, Bp);
-    constexpr uint32_t XK8 = (uint32_t)QN * 128;          // bytes between k-groups (8 union rows) of a ring stage
-    constexpr uint32_t STAGE = (KST / 8) * XK8;
+    constexpr uint32_t XK8 = (uint32_t)QN * XSB;          // bytes between k-groups (8 union rows) of a ring stage
+    constexpr uint32_t XBLK = KST * 128;                  // SW: bytes between 64-column blocks of a stage
+    constexpr uint32_t STAGE = SW ? (NC / 64) * XBLK : (KST / 8) * XK8;
     const int nch = a.nch;
     const int CdP = max(16, (a.Cd + 15) & ~15);           // N of stage C
     const uint32_t W2CH = (uint32_t)CdP * 16 * CC;        // bytes of one chunk of the stage-C B operand
 
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* phi_s = smem;                                        // [max_ku/8][16 points][8 k][8 h] bf16
     unsigned char* x_s = phi_s + (size_t)a.max_ku * 256;                 // [NST][4][QN][8 k][8 n] bf16
     unsigned char* ac_s = x_s + NST * STAGE;                             // [rows/8][ACR]
     unsigned char* w2_s = ac_s + (size_t)(rows / 8) * ACR;               // [nch][CdP/8][CC][8 n][8 k] bf16
-    int* uidx_s = reinterpret_cast<int*>(w2_s + (size_t)nch * W2CH);     // [max_ku]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(uidx_s + a.max_ku);
-    uint64_t* x_full = bars;                 // [NST]  producers (4 warp arrivals) -> MMA
+    int* uidx_s = reinterpret_cast<int*>(w2_s + (size_t)nch * W2CH);     // [2][max_ku]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(uidx_s + 2 * a.max_ku);
+    uint64_t* x_full = bars;                 // [NST]  producers (128 copy-completion arrivals) -> MMA
     uint64_t* x_empty = x_full + NST;        // [NST]  MMA commit -> producers
     uint64_t* d_full = x_empty + NST;        // [2]    MMA commit -> regroup
     uint64_t* d_empty = d_full + 2;          // [2]    regroup (4) -> MMA
@@ -109,11 +132,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     // ---- one-time setup ---------------------------------------------------------------------------------
     if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
     if (tid == 32) {
-        for (int i = 0; i < NST; ++i) tc::mbar_init(&x_full[i], 4), tc::mbar_init(&x_empty[i], 1);
-        for (int i = 0; i < 2; ++i) tc::mbar_init(&d_full[i], 1), tc::mbar_init(&d_empty[i], 4);
-        tc::mbar_init(ac_full, 4), tc::mbar_init(ac_empty, 1);
+        for (int i = 0; i < NST; ++i) tc::mbar_init(&x_full[i], 128), tc::mbar_init(&x_empty[i], 1);
+        for (int i = 0; i < 2; ++i) tc::mbar_init(&d_full[i], 1), tc::mbar_init(&d_empty[i], 8);
+        tc::mbar_init(ac_full, 8), tc::mbar_init(ac_empty, 1);
         tc::mbar_init(phi_full, 4), tc::mbar_init(phi_empty, 1);
-        tc::mbar_init(y_full, 1), tc::mbar_init(y_empty, 4);
+        tc::mbar_init(y_full, 1), tc::mbar_init(y_empty, 8);
         tc::mbar_fence_init();
     }
     // stage-C weights, bf16, K-major [j][(h, channel in chunk)] per channel chunk
@@ -143,7 +166,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
         // ===== producers ====================================================================================
         const int pt = tid - 128;
         const uint32_t x_sa = tc::smem_u32(x_s);
-        uint32_t xit = 0, pub = 0, tt = 0;
+        uint32_t xit = 0, tt = 0;
+        PROF_DECL(w_xempty); PROF_DECL(w_phiempty); PROF_DECL(w_cpwait); PROF_DECL(w_phibuild); PROF_DECL(w_total);
+#ifdef QC_MMA_PROFILE
+        const long long tstart = clock64();
+#endif
         // pair entries of a tile, ENT_R per thread in registers, fetched one tile ahead
         int2 ent[ENT_R];
         auto fetch_entries = [&](int wi2) {
@@ -177,9 +204,102 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
 #pragma unroll
             for (int r = 0; r < ENT_R; ++r)
                 if (ent[r].x >= 0) pv[r] = phi_row(ent[r].x);
-            tc::named_bar_sync(2, 128);                       // every producer is done with the previous union list
-            tc::mbar_wait(phi_empty, (tt & 1) ^ 1);           // ... and the MMAs with the previous Phi
-            for (int i = pt; i < ku; i += 128) uidx_s[i] = __ldg(a.union_idx + u0 + i);
+            // union lists: this tile's (loaded one tile ago) and the next tile's (for the L2 prefetch below); the buffer
+            // being refilled was last read two tiles ago, every producer is past it after the barrier
+            int* uix = uidx_s + (tt & 1) * a.max_ku;
+            int* uix_next = uidx_s + ((tt + 1) & 1) * a.max_ku;
+            const int wi2 = wi + gridDim.x;
+            const bool has_next = wi2 < nwork;
+            int nst_next = 0, blk_next = 0;
+            tc::named_bar_sync(2, 128);
+            if (tt == 0)
+                for (int i = pt; i < ku; i += 128) uix[i] = __ldg(a.union_idx + u0 + i);
+            if (has_next) {
+                const int tile2 = wi2 % a.ntiles;
+                const int v0 = a.tile_uptr[tile2], kv = a.tile_uptr[tile2 + 1] - v0;
+                nst_next = kv / KST, blk_next = wi2 / a.ntiles;
+                for (int i = pt; i < kv; i += 128) uix_next[i] = __ldg(a.union_idx + v0 + i);
+            }
+            tc::named_bar_sync(2, 128);
+
+            // gather: per channel chunk, per stage: 32 union rows x NC columns, 16 bytes per lane, straight into the
+            // MN-major operand layout.
+            const size_t srow = (size_t)nch * NC;               // elements per source point
+            const __nv_bfloat16* Xb = a.X + (size_t)blk * a.Nsrc * srow;
+            // lane -> (row in k-group, column chunk): default 8 rows x 4 chunks per warp; ROWMAJ: 8 chunks (128 B) of 4 rows
+            constexpr int QL = ROWMAJ ? (QN < 8 ? QN : 8) : 1;            // consecutive chunks handled by consecutive lanes
+            const int k8 = ROWMAJ ? (pt / QL) & 7 : pt & 7;
+            const int qq = ROWMAJ ? (pt % QL) + QL * (pt / (QL * 8)) : (pt >> 3);
+            const int q = qq % QN, kg0 = qq / QN;
+            constexpr int KGSTEP = 16 / QN;
+            const uint32_t dst0 = x_sa + q * XSB + k8 * 16;
+            const __nv_bfloat16* Xq = Xb + q * 8;
+            auto issue_stage = [&](int c, int st) {
+                const uint32_t s = xit % NST, ph = (xit / NST) & 1;
+                PROF_WAIT(w_xempty, tc::mbar_wait(&x_empty[s], ph ^ 1));
+                if (SW) {
+                    // 8 lanes = the 8 chunks of one 128-byte row piece; line = (block of 64 columns, union row)
+                    constexpr int NLINE = KST * (NC / 64);
+                    const int cidx = pt & 7, l0 = pt >> 3;
+                    // L2 prefetch PF_CH channel chunks ahead (wrapping into the next tile): a stage is consumed when ALL
+                    // its 64 lines have arrived, i.e. after the slowest HBM miss; with the rows already in L2 the 64 KB
+                    // ring covers the (L2-hit) latency.  One lane of every row piece issues the prefetch.
+                    if (PF_CH > 0 && cidx == 0) {
+                        int c2 = c + PF_CH;
+                        const int* ux = uix;
+                        const __nv_bfloat16* Xp = Xb;
+                        bool ok = true;
+                        if (c2 >= nch) {
+                            c2 -= nch, ux = uix_next, Xp = a.X + (size_t)blk_next * a.Nsrc * srow;
+                            ok = has_next && st < nst_next;
+                        }
+                        if (ok) {
+#pragma unroll
+                            for (int j = 0; j < NLINE / 16; ++j) {
+                                const int line = l0 + 16 * j, r = line % KST, xb = line / KST;
+                                const int u = ux[st * KST + r];
+                                if (u >= 0) tc::prefetch_l2(Xp + (size_t)u * srow + (size_t)c2 * NC + xb * 64);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NLINE / 16; ++j) {
+                        const int line = l0 + 16 * j, r = line % KST, xb = line / KST;
+                        const int u = uix[st * KST + r];
+                        const __nv_bfloat16* src = Xb + (size_t)c * NC + xb * 64 + cidx * 8 + (u >= 0 ? (size_t)u * srow : 0);
+                        const uint32_t dst = x_sa + s * STAGE + xb * XBLK + r * 128 + ((cidx ^ (r & 7)) << 4);
+                        if (CG) tc::cp_async16_cg_zfill(dst, src, u >= 0);
+                        else tc::cp_async16_zfill(dst, src, u >= 0);
+                    }
+                } else {
+#pragma unroll
+                for (int kg = kg0; kg < KST / 8; kg += KGSTEP) {
+                    const int u = uix[st * KST + kg * 8 + k8];
+                    const __nv_bfloat16* src = Xq + (size_t)c * NC + (u >= 0 ? (size_t)u * srow : 0);
+                    if (CG)
+                        tc::cp_async16_cg_zfill(dst0 + s * STAGE + kg * XK8, src, u >= 0);
+                    else
+                        tc::cp_async16_zfill(dst0 + s * STAGE + kg * XK8, src, u >= 0);
+                }
+                }
+                // the stage's mbarrier counts one arrival per producer thread, delivered by the copy unit when this
+                // thread's copies have landed: no wait on the issuing side, nothing held back
+                tc::cp_async_mbar_arrive_noinc(&x_full[s]);
+                ++xit;
+            };
+            // the first stages of this tile go out BEFORE its Phi is built: they only need ring slots, which free up
+            // as the MMAs finish the previous tile, so the gather stream never drains at a tile boundary
+            const int total = nch * nst;
+            const int pre = min(total, NST - 1);
+            int c = 0, st = 0;
+            for (int j = 0; j < pre; ++j) {
+                issue_stage(c, st);
+                if (++st == nst) st = 0, ++c;
+            }
+            PROF_WAIT(w_phiempty, tc::mbar_wait(phi_empty, (tt & 1) ^ 1));   // the MMAs are done with the previous Phi
+#ifdef QC_MMA_PROFILE
+            const long long tb0 = clock64();
+#endif
             for (int i = pt; i < ku * 16; i += 128) reinterpret_cast<uint4*>(phi_s)[i] = make_uint4(0, 0, 0, 0);
             tc::named_bar_sync(2, 128);
 #pragma unroll
@@ -192,117 +312,132 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             tc::fence_proxy_async();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(phi_full);
+#ifdef QC_MMA_PROFILE
+            w_phibuild += clock64() - tb0;
+#endif
             fetch_entries(wi + gridDim.x);
-
-            // gather: per channel chunk, per stage: 32 union rows x NC columns, 16 bytes per lane.  Eight
-            // consecutive lanes copy the same 16-byte column piece of eight different rows = one 128-byte core
-            // matrix of the MN-major operand (no bank conflicts on the shared-memory side).
-            constexpr size_t dummy = 0;
-            (void)dummy;
-            const size_t srow = (size_t)nch * NC;               // elements per source point
-            const __nv_bfloat16* Xb = a.X + (size_t)blk * a.Nsrc * srow;
-            const int k8 = pt & 7, q = (pt >> 3) % QN, kg0 = (pt >> 3) / QN;
-            constexpr int KGSTEP = 16 / QN;
-            const uint32_t dst0 = x_sa + q * 128 + k8 * 16;
-            for (int c = 0; c < nch; ++c) {
-                const __nv_bfloat16* Xc = Xb + (size_t)c * NC + q * 8;
-                for (int st = 0; st < nst; ++st) {
-                    const uint32_t s = xit % NST, ph = (xit / NST) & 1;
-                    tc::mbar_wait(&x_empty[s], ph ^ 1);
-#pragma unroll
-                    for (int kg = kg0; kg < KST / 8; kg += KGSTEP) {
-                        const int u = uidx_s[st * KST + kg * 8 + k8];
-                        tc::cp_async16_zfill(dst0 + s * STAGE + kg * XK8, Xc + (u >= 0 ? (size_t)u * srow : 0), u >= 0);
-                    }
-                    tc::cp_async_commit();
-                    ++xit;
-                    if (xit - pub > LAG) {                      // the copies of stage `pub` have landed
-                        tc::cp_async_wait<LAG>();
-                        tc::fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&x_full[pub % NST]);
-                        ++pub;
-                    }
-                }
+            for (int j = pre; j < total; ++j) {
+                issue_stage(c, st);
+                if (++st == nst) st = 0, ++c;
             }
-            // publish the tail of this tile: the MMAs must finish the tile before its Phi can be replaced
-            tc::cp_async_wait<0>();
-            tc::fence_proxy_async();
-            __syncwarp();
-            for (; pub < xit; ++pub)
-                if (lane == 0) tc::mbar_arrive(&x_full[pub % NST]);
         }
+#ifdef QC_MMA_PROFILE
+        if (a.dbg && blockIdx.x == 0 && pt == 0) {
+            a.dbg[0] = clock64() - tstart, a.dbg[1] = w_xempty, a.dbg[2] = w_phiempty, a.dbg[3] = w_cpwait, a.dbg[4] = w_phibuild;
+        }
+#endif
     } else if (warp == 8) {
-        // ===== MMA issuer (one thread) =====================================================================
-        if (lane == 0) {
+        // ===== stage-B issuer (one thread): Phi x gathered rows -> D ==========================================
+        // The issuing thread is on the critical path (an MMA of 128 columns takes 65 cycles): descriptors are
+        // advanced by integer adds, and the readiness of the next stage is tested while the current MMAs issue.
+        // (the whole warp runs the loop with warp-uniform values, one elected lane issues: the descriptors then live in
+        //  uniform registers and a tcgen05.mma costs a handful of instructions instead of a divergence-safe loop)
+        {
             const uint32_t idB = tc::make_idesc_bf16(128, NC, true, true);
-            const uint32_t idC = tc::make_idesc_bf16(128, CdP, false, false);
-            const uint32_t phi_sa = tc::smem_u32(phi_s), x_sa = tc::smem_u32(x_s), ac_sa = tc::smem_u32(ac_s),
-                           w2_sa = tc::smem_u32(w2_s);
+            const uint64_t da0 = tc::make_smem_desc(tc::smem_u32(phi_s), PHI_K8, 128);
+            const uint64_t db0 = SW ? (tc::make_smem_desc(tc::smem_u32(x_s), XBLK, 1024) | ((uint64_t)2 << 61))
+                                    : tc::make_smem_desc(tc::smem_u32(x_s), XK8, XSB);
+            constexpr uint32_t XKSTEP = SW ? 2048 : 2 * XK8;       // bytes per K step of 16 union rows
             uint32_t xit = 0, cc = 0, tt = 0;
-            auto stage_c = [&](int c, uint32_t ccx) {
-                if (c == 0) {
-                    tc::mbar_wait(y_empty, (tt & 1) ^ 1);       // the previous tile's output has left TMEM
-                    tc::fence_after_sync();
-                }
-                tc::mbar_wait(ac_full, ccx & 1);
-                tc::fence_after_sync();
-                for (int mb = 0; mb < MBC; ++mb)
-#pragma unroll
-                    for (int k2 = 0; k2 < CC / 2; ++k2) {
-                        const uint64_t da = tc::make_smem_desc(ac_sa + mb * 16 * ACR + k2 * 2 * AC_K8, AC_K8, ACR);
-                        const uint64_t db = tc::make_smem_desc(w2_sa + c * W2CH + k2 * 256, 128, CC * 128);
-                        tc::mma_bf16_ss(tmem_y + mb * CdP, da, db, idC, c > 0 || k2 > 0);
-                    }
-                tc::mma_commit(ac_empty);
-            };
+            PROF_DECL(m_xfull); PROF_DECL(m_dempty); PROF_DECL(m_phifull);
+#ifdef QC_MMA_PROFILE
+            const long long tstart = clock64();
+#endif
             for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
                 const int tile = wi % a.ntiles;
-                const int nst = (a.tile_uptr[tile + 1] - a.tile_uptr[tile]) / KST;
-                tc::mbar_wait(phi_full, tt & 1);
+                const int nst = (__ldg(a.tile_uptr + tile + 1) - __ldg(a.tile_uptr + tile)) / KST;
+                PROF_WAIT(m_phifull, tc::mbar_wait(phi_full, tt & 1));     // (the producers fenced their Phi stores)
                 tc::fence_after_sync();
                 for (int c = 0; c < nch; ++c, ++cc) {
                     const uint32_t buf = cc & 1, dph = (cc >> 1) & 1;
-                    tc::mbar_wait(&d_empty[buf], dph ^ 1);       // chunk cc-2 has been read out of this accumulator
+                    PROF_WAIT(m_dempty, tc::mbar_wait(&d_empty[buf], dph ^ 1));       // chunk cc-2 has been read out of this accumulator
                     tc::fence_after_sync();
+                    const uint32_t dcol = tmem + buf * DCOLS;
                     for (int st = 0; st < nst; ++st, ++xit) {
                         const uint32_t s = xit % NST, ph = (xit / NST) & 1;
-                        tc::mbar_wait(&x_full[s], ph);
+                        // (cp.async completion delivered through the mbarrier orders the copies before the MMAs that
+                        //  follow the wait; no proxy fence: it costs a MEMBAR per stage and drains the copies in flight)
+                        PROF_WAIT(m_xfull, tc::mbar_wait(&x_full[s], ph));
                         tc::fence_after_sync();
+                        if (tc::elect_one()) {
+                            const uint64_t da = da0 + (uint64_t)((st * (KST / 16) * 2 * PHI_K8) >> 4);
+                            const uint64_t db = db0 + (uint64_t)((s * STAGE) >> 4);
+                            tc::mma_bf16_ss(dcol, da, db, idB, st > 0);
 #pragma unroll
-                        for (int k2 = 0; k2 < KST / 16; ++k2) {
-                            const uint64_t da = tc::make_smem_desc(phi_sa + (st * (KST / 16) + k2) * 2 * PHI_K8, PHI_K8, 128);
-                            const uint64_t db = tc::make_smem_desc(x_sa + s * STAGE + k2 * 2 * XK8, XK8, 128);
-                            tc::mma_bf16_ss(tmem + buf * DCOLS, da, db, idB, st > 0 || k2 > 0);
+                            for (int k2 = 1; k2 < KST / 16; ++k2)
+                                tc::mma_bf16_ss(dcol, da + (uint64_t)((k2 * 2 * PHI_K8) >> 4), db + (uint64_t)((k2 * XKSTEP) >> 4), idB, true);
+                            tc::mma_commit(&x_empty[s]);
                         }
-                        tc::mma_commit(&x_empty[s]);
+                        __syncwarp();
                     }
-                    tc::mma_commit(&d_full[buf]);
-                    if (c == nch - 1) tc::mma_commit(phi_empty);
-                    if (c >= 1) stage_c(c - 1, cc - 1);
+                    if (tc::elect_one()) tc::mma_commit(&d_full[buf]);
+                    __syncwarp();
                 }
-                stage_c(nch - 1, cc - 1);
-                tc::mma_commit(y_full);
+                if (tc::elect_one()) tc::mma_commit(phi_empty);
+                __syncwarp();
             }
+#ifdef QC_MMA_PROFILE
+            if (a.dbg && blockIdx.x == 0 && lane == 0) a.dbg[8] = clock64() - tstart, a.dbg[9] = m_xfull, a.dbg[10] = m_dempty, a.dbg[12] = m_phifull;
+#endif
         }
-    } else if (warp < 4) {
-        // ===== regroup + output (thread = TMEM lane m = (point in tile, filter component)) ===================
-        const int m = tid;
+    } else if (warp == 9) {
+        // ===== stage-C issuer (one thread): regrouped T x W2 -> Y ===========================================
+        {
+            const uint32_t idC = tc::make_idesc_bf16(128, CdP, false, false);
+            const uint64_t da0 = tc::make_smem_desc(tc::smem_u32(ac_s), AC_K8, ACR);
+            const uint64_t db0 = tc::make_smem_desc(tc::smem_u32(w2_s), 128, CC * 128);
+            uint32_t cc = 0, tt = 0;
+            PROF_DECL(m_acfull); PROF_DECL(m_yempty);
+            for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
+                PROF_WAIT(m_yempty, tc::mbar_wait(y_empty, (tt & 1) ^ 1));       // the previous tile's output has left TMEM
+                for (int c = 0; c < nch; ++c, ++cc) {
+                    PROF_WAIT(m_acfull, tc::mbar_wait(ac_full, cc & 1));
+                    tc::fence_after_sync();
+                    if (tc::elect_one()) {
+                        const uint64_t dbc = db0 + (uint64_t)((c * W2CH) >> 4);
+                        for (int mb = 0; mb < MBC; ++mb)
+#pragma unroll
+                            for (int k2 = 0; k2 < CC / 2; ++k2)
+                                tc::mma_bf16_ss(tmem_y + mb * CdP, da0 + (uint64_t)((mb * 16 * ACR + k2 * 2 * AC_K8) >> 4),
+                                                dbc + (uint64_t)((k2 * 256) >> 4), idC, c > 0 || k2 > 0);
+                        tc::mma_commit(ac_empty);
+                    }
+                    __syncwarp();
+                }
+                if (tc::elect_one()) tc::mma_commit(y_full);
+                __syncwarp();
+            }
+#ifdef QC_MMA_PROFILE
+            if (a.dbg && blockIdx.x == 0 && lane == 0) a.dbg[11] = m_acfull, a.dbg[13] = m_yempty;
+#endif
+        }
+    } else if (warp < 4 || warp >= 10) {
+        // ===== regroup + output, two groups of 4 warps (thread = TMEM lane m = (point in tile, filter component));
+        // group 0 (warps 0-3) takes the first half of a chunk's columns, group 1 (warps 10-13) the second =========
+        const int grp = warp >= 10 ? 1 : 0;
+        const int m = (warp & 3) * 32 + lane;
         const int ol = m >> 3, h = m & 7;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const size_t yrow = (size_t)qc_cp4(a.Cd) * Bp;
         // element (row = ol*Bp + b, k = h*CC + il) of the K-major stage-C operand
         unsigned char* dst0 = ac_s + (size_t)((h * CC) >> 3) * AC_K8 + ((h * CC) & 7) * 2;
         uint32_t cc = 0, tt = 0;
+        PROF_DECL(e_dfull); PROF_DECL(e_acempty); PROF_DECL(e_regroup); PROF_DECL(e_yfull); PROF_DECL(e_out);
+#ifdef QC_MMA_PROFILE
+        const long long tstart = clock64();
+#endif
         for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
             const int tile = wi % a.ntiles, blk = wi / a.ntiles;
             for (int c = 0; c < nch; ++c, ++cc) {
                 const uint32_t buf = cc & 1, ph = (cc >> 1) & 1;
-                tc::mbar_wait(&d_full[buf], ph);
-                tc::mbar_wait(ac_empty, (cc & 1) ^ 1);           // stage C of the previous chunk has read the tile
+                PROF_WAIT(e_dfull, tc::mbar_wait(&d_full[buf], ph));
+                PROF_WAIT(e_acempty, tc::mbar_wait(ac_empty, (cc & 1) ^ 1));           // stage C of the previous chunk has read the tile
                 tc::fence_after_sync();
+#ifdef QC_MMA_PROFILE
+                const long long tr0 = clock64();
+#endif
 #pragma unroll 2
-                for (int g = 0; g < NC / 16; ++g) {
+                for (int g = grp * (NC / 32); g < (grp + 1) * (NC / 32); ++g) {
                     uint32_t r[16];
                     tc::tmem_ld16(lane_base + tmem + buf * DCOLS + g * 16, r);
                     tc::wait_ld();
@@ -343,11 +478,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
                     tc::mbar_arrive(&d_empty[buf]);
                     tc::mbar_arrive(ac_full);
                 }
+#ifdef QC_MMA_PROFILE
+                e_regroup += clock64() - tr0;
+#endif
             }
             // output rows of this tile: TMEM lane = row % 128, row = (point in tile) * Bp + batch lane
-            tc::mbar_wait(y_full, tt & 1);
+            PROF_WAIT(e_yfull, tc::mbar_wait(y_full, tt & 1));
             tc::fence_after_sync();
-            for (int mb = 0; mb < MBC; ++mb) {
+#ifdef QC_MMA_PROFILE
+            const long long to0 = clock64();
+#endif
+            for (int mb = (MBC > 1 ? grp : 0); mb < MBC; mb += (MBC > 1 ? 2 : 1)) {
+                if (MBC == 1 && grp == 1) break;
                 const int row = mb * 128 + m;
                 const int o2 = row / Bp, b = row % Bp;
                 const int t = tile * TP + o2;
@@ -370,23 +512,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(y_empty);
+#ifdef QC_MMA_PROFILE
+            e_out += clock64() - to0;
+#endif
         }
+#ifdef QC_MMA_PROFILE
+        if (a.dbg && blockIdx.x == 0 && tid == 0) {
+            a.dbg[16] = clock64() - tstart, a.dbg[17] = e_dfull, a.dbg[18] = e_acempty, a.dbg[19] = e_regroup, a.dbg[20] = e_yfull,
+            a.dbg[21] = e_out;
+        }
+#endif
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-template <int CC, int LB>
+template <int CC, int LB, int VAR = 0>
 int launch_mma(const MmaArgs& a, cudaStream_t st)
 {
     const int CdP = max(16, (a.Cd + 15) & ~15);
     const size_t smem = mma_smem_bytes(CC, 1 << LB, a.nch, CdP, a.max_ku);
     if (smem > 227 * 1024) return 0;
-    QC_CUDA((qc_set_max_smem<k_contract_mma<CC, LB>>((int)smem)));
+    QC_CUDA((qc_set_max_smem<k_contract_mma<CC, LB, VAR>>((int)smem)));
     int grid = min(qc_num_sms(), a.ntiles * a.nblk);
     if (grid < 1) grid = 1;
-    k_contract_mma<CC, LB><<<grid, NTHREADS, smem, st>>>(a);
+    k_contract_mma<CC, LB, VAR><<<grid, NTHREADS, smem, st>>>(a);
     QC_CHECK_LAUNCH();
     return 1;
 }
@@ -480,11 +631,34 @@ int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const void* tile_ent, cons
     a.w_last = w_last;
     a.Nsrc = Nsrc, a.Ndst = Ndst, a.Cs = Cs, a.Cd = Cd, a.H = H, a.HPphi = HPphi, a.nch = qc_ceil_div(Cs, CC);
     a.transposed = transposed, a.ntiles = ntiles, a.nblk = qc_nblk(B), a.max_ku = max_ku;
+    a.dbg = nullptr;
     const cudaStream_t st = (cudaStream_t)stream;
+#ifdef QC_MMA_PROFILE
+    static long long* dbg = nullptr;
+    if (!dbg) cudaMalloc(&dbg, 32 * sizeof(long long));
+    cudaMemsetAsync(dbg, 0, 32 * sizeof(long long), st);
+    a.dbg = dbg;
+#endif
     int rc = 0;
-    if (Bp == 32) rc = launch_mma<4, 5>(a, st);
-    else if (Bp == 16) rc = CC == 8 ? launch_mma<8, 4>(a, st) : launch_mma<4, 4>(a, st);
-    else if (Bp == 8) rc = CC == 16 ? launch_mma<16, 3>(a, st) : (CC == 8 ? launch_mma<8, 3>(a, st) : launch_mma<4, 3>(a, st));
+    static const int var = getenv("QC_MMA_VAR") ? atoi(getenv("QC_MMA_VAR")) : 4;
+    if (Bp == 32) rc = var == 2 ? launch_mma<4, 5, 2>(a, st) : (var == 5 ? launch_mma<4, 5, 5>(a, st) : launch_mma<4, 5, 4>(a, st));
+    else if (Bp == 16) rc = CC == 8 ? launch_mma<8, 4, 4>(a, st) : launch_mma<4, 4, 4>(a, st);
+    else if (Bp == 8) rc = CC == 16 ? launch_mma<16, 3, 4>(a, st) : (CC == 8 ? launch_mma<8, 3, 4>(a, st) : launch_mma<4, 3, 2>(a, st));
+#ifdef QC_MMA_PROFILE
+    {
+        long long h[32];
+        cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        const char* names[32] = {"prod total", "prod wait x_empty", "prod wait phi_empty", "prod cp.async wait", "prod phi build", 0, 0, 0,
+                                 "mma total", "mma wait x_full", "mma wait d_empty", "mma wait ac_full", "mma wait phi_full",
+                                 "mma wait y_empty", "mma proxy fence", 0, "epi total", "epi wait d_full", "epi wait ac_empty",
+                                 "epi regroup", "epi wait y_full", "epi output"};
+        fprintf(stderr, "[qc_contract_mma profile, CTA 0, cycles]");
+        for (int i = 0; i < 32; ++i)
+            if (names[i]) fprintf(stderr, " %s=%lld;", names[i], h[i]);
+        fprintf(stderr, "\n");
+    }
+#endif
     if (rc == 0) return QC_EUNSUP;
     return rc == 1 ? 0 : rc;
 }

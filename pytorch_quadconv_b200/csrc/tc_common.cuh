@@ -122,6 +122,36 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 
+// true in exactly one lane of a fully converged warp (the lane that issues tcgen05.mma / commit); every lane must call it
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok));
+    return ok != 0;
+}
+
+// one non-blocking test of a phase (true: the phase with this parity has completed)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 // ---- asynchronous global->shared copies (LDGSTS): completion is tracked per commit group in FIFO
 // order, NOT through the 6 per-warp scoreboards -- ptxas puts every gather LDG of an unrolled loop on
 // one scoreboard, which collapses a register-prefetch pipeline to a depth of one (profiles/README.md).
@@ -170,6 +200,18 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc)
 __device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void* gsrc, bool valid)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// L2-only variant (bypasses L1): for streams that are read once per CTA
+__device__ __forceinline__ void cp_async16_cg_zfill(uint32_t smem_dst, const void* gsrc, bool valid)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
+}
+// the mbarrier receives one arrival (not counted in its pending count: .noinc) once all cp.async issued so far by
+// the executing thread have completed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

@@ -229,6 +229,86 @@ __global__ void __launch_bounds__(128, 1) k_tc_probe_bf16(const float* __restric
     if (warp == 0) tc::tmem_dealloc(tmem, 32);
 }
 
+
+// Micro-benchmark (diagnostic, not on the product path): issue rate of back-to-back tcgen05.mma kind::f16 with both
+// operands in shared memory, for the operand layouts / shapes used by csrc/contract_mma.cu.  One thread issues `iters`
+// MMAs (cycling over 8 K steps of a zeroed operand area), commits, waits; cycles per MMA are written per CTA.
+__global__ void __launch_bounds__(128, 1) k_tc_mma_bench(int M, int N, int a_mn, int b_mn, uint32_t a_lbo, uint32_t a_sbo,
+                                                          uint32_t b_lbo, uint32_t b_sbo, uint32_t a_kstep, uint32_t b_kstep,
+                                                          int swz, int iters, long long* __restrict__ out)
+{
+    extern __shared__ __align__(1024) unsigned char dyn_m[];
+    __shared__ __align__(8) uint64_t bar, bar2;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ volatile int done_flag;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) done_flag = 0;
+    for (int i = tid; i < 160 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(dyn_m)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_init(&bar2, 1 << 20);
+        tc::mbar_fence_init();
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    if (warp > 0 && ((swz >> 8) & 12)) {
+        // background traffic while warp 0 issues: mode bit 2 = shared-memory stores (16 B per lane, conflict free) into
+        // an unused area, bit 3 = tcgen05.ld of 16 columns in a loop
+        const int mode = swz >> 8;
+        uint4* area = reinterpret_cast<uint4*>(dyn_m + 144 * 1024) + (tid - 32);
+        uint32_t r[16];
+        uint32_t acc = 0;
+        while (done_flag == 0) {
+            if (mode & 4) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) area[(j & 3) * 96] = make_uint4(acc, j, 0, 0);
+            }
+            if (mode & 8) {
+                tc::tmem_ld16(((uint32_t)(warp * 32) << 16) + tmem + 384, r);
+                tc::wait_ld();
+                acc += r[0];
+            }
+        }
+        if (acc == 0x12345678u) out[0] = 1;
+    }
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_bf16(M, N, a_mn != 0, b_mn != 0);
+        const uint32_t a0 = tc::smem_u32(dyn_m), b0 = a0 + 80 * 1024;
+        const uint64_t lt = (uint64_t)(swz & 7) << 61;
+        const long long t0 = clock64();
+        uint64_t da[8], db[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            da[ks] = tc::make_smem_desc(a0 + ks * a_kstep, a_lbo, a_sbo) | lt;
+            db[ks] = tc::make_smem_desc(b0 + ks * b_kstep, b_lbo, b_sbo) | lt;
+        }
+        const int mode = swz >> 8;
+        for (int it = 0; it < iters; it += 8) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                if ((mode & 2) && (ks & 1) == 0) {
+                    tc::fence_proxy_async();
+                    tc::fence_after_sync();
+                }
+                asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(tmem + (ks & 1) * 256), "l"(da[ks]),
+                             "l"(db[ks]), "r"(idesc) : "memory");
+                if ((mode & 1) && (ks & 1)) tc::mma_commit(&bar2);
+            }
+        }
+        tc::mma_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+        out[blockIdx.x] = clock64() - t0;
+        done_flag = 1;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 
 extern "C" int qc_tc_probe_bf16(const float* A, const float* B, float* D, int mode, void* stream)
@@ -251,6 +331,17 @@ extern "C" int qc_tc_selftest_ss(const float* A, const float* B, float* D, void*
 extern "C" int qc_tc_selftest(const float* A, const float* B, float* D, void* stream)
 {
     k_tc_selftest<<<1, 128, 0, (cudaStream_t)stream>>>(A, B, D);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int qc_tc_mma_bench(int M, int N, int a_mn, int b_mn, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int a_kstep,
+                               int b_kstep, int swz, int iters, int grid, long long* out, void* stream)
+{
+    const int smem = 160 * 1024;
+    QC_CUDA((qc_set_max_smem<k_tc_mma_bench>(smem)));
+    k_tc_mma_bench<<<grid, 128, smem, (cudaStream_t)stream>>>(M, N, a_mn, b_mn, a_lbo, a_sbo, b_lbo, b_sbo, a_kstep, b_kstep,
+                                                             swz, iters, out);
     QC_CHECK_LAUNCH();
     return 0;
 }
