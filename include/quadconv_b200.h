@@ -256,6 +256,17 @@ int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const void* tile_ent, cons
                     const float* w_last, int Cd, int transposed, const int* order, int Ndst, int B, float* Yp,
                     void* stream);
 
+/* d(phi) of the reduced-precision mode (csrc/dphi_mma.cu): dphi[p][h] = sum_{b,i} f[b,i,in(p)] * dT[out(p); b,i,h],
+ * dT = grad_out x W_last, over the same tiles/unions as qc_contract_mma (forward view: destinations = out points,
+ * Xh = bf16 packed features of the in points, Gh = bf16 packed grad_out of the out points).  Autograd of
+ * torch_quadconv/quadconv.py:216-219 with respect to the filter output, folded through the last Linear (:143).
+ * dphi [P][HPphi] fp32, must be zero on entry when B > 32 (batch blocks accumulate).  QC_EUNSUP: batch lanes x chunk
+ * channels < 64, H > 8, more than 64 grad channels, max_ku > 384, operands beyond 227 KB of shared memory. */
+int qc_dphi_mma_smem_bytes(int Cs, int Cg, int B, int max_ku);
+int qc_dphi_mma(const void* Xh, int Nsrc, int Cs, const void* Gh, int Cg, const void* tile_ent, const int* tile_pptr,
+                const int* tile_uptr, const int* union_idx, int ntiles, int max_ku, const float* w_last, int H, int HPphi,
+                const int* order, int Ndst, int B, float* dphi, void* stream);
+
 /* Known-answer self test of the tcgen05 building blocks (TMEM alloc, tcgen05.st/ld, kind::tf32 MMA with
  * A in TMEM and B through a K-major shared-memory descriptor, 3xTF32 split):
  * D[128][32] = A[128][64] * B[32][64]^T.  Used by tests only. */

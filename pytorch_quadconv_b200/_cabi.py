@@ -74,6 +74,9 @@ _SIGNATURES = {
     "qc_contract_mma": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                 c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                                 c_void_p]),
+    "qc_dphi_mma_smem_bytes": (c_int, [c_int, c_int, c_int, c_int]),
+    "qc_dphi_mma": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                            c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "qc_tc_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "qc_tc_selftest_ss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "qc_tc_probe_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

@@ -201,6 +201,10 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void* 
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
 }
+__device__ __forceinline__ void cp_async8_zfill(uint32_t smem_dst, const void* gsrc, bool valid)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(valid ? 8 : 0) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // L2-only variant (bypasses L1): for streams that are read once per CTA
 __device__ __forceinline__ void cp_async16_cg_zfill(uint32_t smem_dst, const void* gsrc, bool valid)

@@ -102,3 +102,59 @@ def test_tc_falls_back_outside_its_shapes(cuda_lib):
         y = layer(mesh, c["x"].detach().cuda())
         assert not layer.tc_active
         assert relerr(y.detach().cpu().numpy(), c["y"].numpy()) < 1e-5
+
+
+def _rb(t):
+    return t.float().to(torch.bfloat16).double()
+
+
+@pytest.mark.parametrize("d,n,ci,co,B,H,r,n_out", [
+    (3, 1500, 32, 32, 32, 8, 0.16, None),     # C3-like
+    (2, 900, 16, 16, 8, 4, 0.1, None),        # C1-like: batch 8, 16 channels per chunk, phi rows of 4
+    (2, 800, 8, 12, 16, 8, 0.09, 300),        # batch 16, cross-level
+    (2, 700, 20, 24, 40, 8, 0.1, None),       # two batch blocks (atomic accumulation), partial last chunk
+    (2, 500, 8, 8, 8, 5, 0.1, None),          # batch 8 with 8 channels: 64-column chunks, H = 5
+])
+def test_dphi_mma_kernel(cuda_lib, d, n, ci, co, B, H, r, n_out):
+    """qc_dphi_mma through the C ABI against the same sums in float64 with the same operand roundings (features,
+    grad_out, W_last and dT rounded to bf16): <= 2e-3 (rounding flips of dT), and <= 1e-2 from the exact value."""
+    from pytorch_quadconv_b200 import _cabi as C, ops
+    g = torch.Generator().manual_seed(31 + n)
+    pts = torch.rand(n, d, generator=g)
+    out_pts = pts if n_out is None else pts[torch.randperm(n, generator=g)[:n_out]].contiguous()
+    No = out_pts.shape[0]
+    x = torch.randn(B, ci, n, generator=g)
+    go = torch.randn(B, co, No, generator=g)
+    wl = torch.randn(ci * co, H, generator=g) / np.sqrt(H)
+    res = ops.build_pairs(out_pts.cuda(), pts.cuda(), float(r), n_out is None)
+    ev, pair_row, pair_col, row_ptr = res[0], res[1], res[2], res[3]
+    cell_out = res[9]
+    ent, pptr, uptr, uidx, max_ku = ops.build_union_tables(row_ptr, pair_col, cell_out, No, n)
+    P = ev.shape[0]
+    HP = 4 if H <= 4 else 8
+    xh, gh = ops._pack_bf16(x.cuda()), ops._pack_bf16(go.cuda())
+    dphi = torch.zeros(P, HP, device="cuda")
+    L = C.lib()
+    assert 0 < L.qc_dphi_mma_smem_bytes(ci, co, B, max_ku) <= 227 * 1024
+    C.check(L.qc_dphi_mma(C.ptr(xh), n, ci, C.ptr(gh), co, C.ptr(ent), C.ptr(pptr), C.ptr(uptr), C.ptr(uidx),
+                          uptr.numel() - 1, max_ku, C.ptr(wl.cuda()), H, HP, C.ptr(cell_out), No, B, C.ptr(dphi),
+                          C.stream()), "qc_dphi_mma")
+    torch.cuda.synchronize()
+    io, ii = ev[:, 0].cpu(), ev[:, 1].cpu()
+    W = wl.view(ci, co, H)
+
+    def ref(rounded):
+        f = (lambda t: _rb(t)) if rounded else (lambda t: t.double())
+        dT = torch.einsum("bjo,ijh->obih", f(go), f(W))
+        if rounded:
+            dT = _rb(dT)
+        out = torch.empty(P, H, dtype=torch.float64)
+        xs = f(x)
+        for s in range(0, P, 4096):
+            out[s:s + 4096] = torch.einsum("bip,pbih->ph", xs[:, :, ii[s:s + 4096]], dT[io[s:s + 4096]])
+        return out
+    got = dphi[:, :H].cpu()
+    assert relerr(got.numpy(), ref(True).numpy()) < 2e-3
+    assert relerr(got.numpy(), ref(False).numpy()) < 1e-2
+    if HP > H:
+        assert float(dphi[:, H:].abs().max()) == 0.0
