@@ -256,6 +256,16 @@ int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const void* tile_ent, cons
                     const float* w_last, int Cd, int transposed, const int* order, int Ndst, int B, float* Yp,
                     void* stream);
 
+/* d W_last of the reduced-precision mode (csrc/contract_mma.cu, DW variant): d_w_last[(i*Cg + j)*H + h] =
+ * sum_{o,b} T[o;b,i,h] * g[b,j,o], T = the stage-B result of the forward recomputed from the same tiles (forward view:
+ * Xh = features of the in points, Gh = grad_out of the out points, both bf16 packed).  Written (not accumulated).
+ * ws: qc_dw_mma_workspace_bytes() bytes of scratch (per-CTA partial sums, reduced in CTA order: deterministic). */
+size_t qc_dw_mma_workspace_bytes(int Cs, int Cg, int B);
+int qc_dw_mma_smem_bytes(int Cs, int Cg, int B, int max_ku);
+int qc_dw_mma(const void* Xh, int Nsrc, int Cs, const void* Gh, int Cg, const void* tile_ent, const int* tile_pptr,
+              const int* tile_uptr, const int* union_idx, int ntiles, int max_ku, const float* phi, int H, int HPphi,
+              const int* order, int Ndst, int B, void* ws, size_t ws_bytes, float* d_w_last, void* stream);
+
 /* d(phi) of the reduced-precision mode (csrc/dphi_mma.cu): dphi[p][h] = sum_{b,i} f[b,i,in(p)] * dT[out(p); b,i,h],
  * dT = grad_out x W_last, over the same tiles/unions as qc_contract_mma (forward view: destinations = out points,
  * Xh = bf16 packed features of the in points, Gh = bf16 packed grad_out of the out points).  Autograd of

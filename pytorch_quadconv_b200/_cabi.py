@@ -74,6 +74,10 @@ _SIGNATURES = {
     "qc_contract_mma": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                 c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                                 c_void_p]),
+    "qc_dw_mma_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "qc_dw_mma_smem_bytes": (c_int, [c_int, c_int, c_int, c_int]),
+    "qc_dw_mma": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                          c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "qc_dphi_mma_smem_bytes": (c_int, [c_int, c_int, c_int, c_int]),
     "qc_dphi_mma": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                             c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),

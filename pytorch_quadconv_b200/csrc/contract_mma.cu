@@ -53,6 +53,10 @@ struct MmaArgs {
     const int* union_idx;       // union lists, -1 = padding
     const float* phi;           // [P][HPphi] fp32
     const float* w_last;        // [Ci*Co][H] fp32 (filter.{2L}.weight)
+    // DW mode (d W_last = sum over rows of T x grad rows instead of stage C):
+    const __nv_bfloat16* G;     // packed rows of the destination-side tensor [nblk][Ndst][nchg][Bp][CCg]
+    float* dw_part;             // per-CTA partial results [grid][groups][MDW][CgP]
+    int Cg, nchg, CCg;
     int Nsrc, Ndst, Cs, Cd, H, HPphi, nch, transposed, ntiles, nblk, max_ku;   // HPphi = floats per phi row (4 or 8)
     long long* dbg;             // QC_MMA_PROFILE builds: wait-cycle counters of CTA 0 (null otherwise)
 };
@@ -80,18 +84,26 @@ __host__ __device__ constexpr uint32_t ac_row8(int CC, int Bp)
     return (uint32_t)CC * AC_K8 + (Bp >= 32 ? 16u : (Bp == 16 ? 32u : 64u));
 }
 
-__host__ __device__ constexpr size_t mma_smem_bytes(int CC, int Bp, int nch, int CdP, int max_ku)
+__host__ __device__ constexpr size_t mma_smem_bytes(int CC, int Bp, int nch, int CdP, int max_ku, bool dw = false, int CgP = 0)
 {
-    return (size_t)max_ku * 256 + (size_t)NST * (KST / 8) * (Bp * CC / 8) * 144 + (size_t)(TP * Bp / 8) * ac_row8(CC, Bp) +
-           (size_t)nch * CdP * 16 * CC + (size_t)max_ku * 8 + 64 * 8;
+    const int cpp = dw ? (CC == 16 ? 128 : 64) / (8 * CC) : 1;
+    return (size_t)max_ku * 256 + (size_t)NST * (KST / 8) * (Bp * CC / 8) * 144 + (size_t)(TP * Bp / 8) * ac_row8(CC * cpp, Bp) +
+           (dw ? (size_t)TP * Bp * CgP * 2 : (size_t)nch * CdP * 16 * CC) + (size_t)max_ku * 8 + 64 * 8;
 }
 
 // VAR (gather experiment): bit 0 = cp.async.cg (bypass L1), bit 1 = n-chunk stride 144 B so that a quarter warp copies
 // ONE row's 128 contiguous bytes (8 chunks) without bank conflicts instead of 16 bytes of 8 rows
-template <int CC, int LB, int VAR>
+// DW = true: the dW_last pass.  Stage B and the regroup are unchanged; instead of stage C the regrouped tile T[(o,b)][(h,i)]
+// is the MN-major A operand of   D_dw[(h,i)][j] += sum_{(o,b)} T[(o,b)][(h,i)] * G[(o,b)][j]   (K = the tile's rows), G = the
+// tile's own rows of the destination-side tensor (grad_out in the forward view).  M = 64 or 128 k-values = CPP channel
+// chunks side by side in the regroup tile; the accumulators stay in TMEM for the whole kernel (one per chunk group) and
+// every CTA writes its partial sums once at the end.
+template <int CC, int LB, int VAR, bool DW>
 __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
 {
     constexpr int Bp = 1 << LB, NC = Bp * CC, QN = NC / 8;
+    constexpr int MDW = CC == 16 ? 128 : 64;              // M of the dW GEMM
+    constexpr int CPP = DW ? MDW / (8 * CC) : 1;          // channel chunks side by side in the regroup tile
     constexpr bool CG = (VAR & 1) != 0, ROWMAJ = (VAR & 2) != 0;
     // bit 2: the gathered operand in the 128-byte-swizzle MN-major layout (rows of 64 columns = 128 contiguous bytes,
     // 16-byte chunks XOR-ed with the row index inside 1 KB atoms): a 128-byte line from L2 lands as ONE shared-memory
@@ -99,20 +111,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     constexpr bool SW = (VAR & 4) != 0 && (NC % 64 == 0);
     constexpr uint32_t XSB = ROWMAJ ? 144 : 128;          // bytes between 8-column chunks of the gathered operand
     constexpr int rows = TP * Bp, MBC = rows / 128;       // rows of the stage-C GEMM per tile, its 128-row blocks
-    constexpr uint32_t ACR = ac_row8(CC, Bp);
+    constexpr uint32_t ACR = ac_row8(CC * CPP, Bp);
     constexpr uint32_t XK8 = (uint32_t)QN * XSB;          // bytes between k-groups (8 union rows) of a ring stage
     constexpr uint32_t XBLK = KST * 128;                  // SW: bytes between 64-column blocks of a stage
     constexpr uint32_t STAGE = SW ? (NC / 64) * XBLK : (KST / 8) * XK8;
     const int nch = a.nch;
-    const int CdP = max(16, (a.Cd + 15) & ~15);           // N of stage C
+    const int CdP = DW ? 0 : max(16, (a.Cd + 15) & ~15);  // N of stage C
     const uint32_t W2CH = (uint32_t)CdP * 16 * CC;        // bytes of one chunk of the stage-C B operand
+    const int CgP = DW ? ((a.Cg + 15) & ~15) : 0;         // N of the dW GEMM
+    constexpr uint32_t GMN8 = (rows / 8) * 128;           // DW: bytes between 8-channel groups of the G tile (MN-major B operand)
 
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* phi_s = smem;                                        // [max_ku/8][16 points][8 k][8 h] bf16
     unsigned char* x_s = phi_s + (size_t)a.max_ku * 256;                 // [NST][4][QN][8 k][8 n] bf16
     unsigned char* ac_s = x_s + NST * STAGE;                             // [rows/8][ACR]
-    unsigned char* w2_s = ac_s + (size_t)(rows / 8) * ACR;               // [nch][CdP/8][CC][8 n][8 k] bf16
-    int* uidx_s = reinterpret_cast<int*>(w2_s + (size_t)nch * W2CH);     // [2][max_ku]
+    unsigned char* w2_s = ac_s + (size_t)(rows / 8) * ACR;               // [nch][CdP/8][CC][8 n][8 k] bf16  (DW: the G tile)
+    unsigned char* g_s = w2_s;                                           // DW: [CgP/8][rows/8][8 rows][8 j] bf16
+    int* uidx_s = reinterpret_cast<int*>(w2_s + (DW ? (size_t)rows * CgP * 2 : (size_t)nch * W2CH));     // [2][max_ku]
     uint64_t* bars = reinterpret_cast<uint64_t*>(uidx_s + 2 * a.max_ku);
     uint64_t* x_full = bars;                 // [NST]  producers (128 copy-completion arrivals) -> MMA
     uint64_t* x_empty = x_full + NST;        // [NST]  MMA commit -> producers
@@ -124,7 +139,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     uint64_t* phi_empty = phi_full + 1;      // MMA commit -> producers
     uint64_t* y_full = phi_empty + 1;        // MMA commit -> output
     uint64_t* y_empty = y_full + 1;          // output (4) -> MMA
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(y_empty + 1);
+    uint64_t* g_full = y_empty + 1;          // DW: producers (128 copy completions) -> dW issuer
+    uint64_t* g_empty = g_full + 1;          // DW: dW commit -> producers
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(g_empty + 1);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -137,10 +154,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
         tc::mbar_init(ac_full, 8), tc::mbar_init(ac_empty, 1);
         tc::mbar_init(phi_full, 4), tc::mbar_init(phi_empty, 1);
         tc::mbar_init(y_full, 1), tc::mbar_init(y_empty, 8);
+        tc::mbar_init(g_full, 128), tc::mbar_init(g_empty, 1);
         tc::mbar_fence_init();
     }
     // stage-C weights, bf16, K-major [j][(h, channel in chunk)] per channel chunk
-    {
+    if (!DW) {
         constexpr int KC = 8 * CC;
         const int total = nch * CdP * KC;
         for (int idx = tid; idx < total; idx += NTHREADS) {
@@ -316,6 +334,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             w_phibuild += clock64() - tb0;
 #endif
             fetch_entries(wi + gridDim.x);
+            if (DW) {
+                // the tile's own rows of the destination-side tensor: MN-major B operand [j][(point, batch lane)],
+                // pieces of min(16, 2*CCg) bytes (one 16-byte line = 8 channels of one row)
+                tc::mbar_wait(g_empty, (tt & 1) ^ 1);
+                const size_t grow = (size_t)a.nchg * Bp * a.CCg;
+                const __nv_bfloat16* Gb = a.G + (size_t)blk * a.Ndst * grow;
+                const uint32_t g_sa = tc::smem_u32(g_s);
+                const int pb = a.CCg >= 8 ? 16 : 8;
+                const int ppr = CgP * 2 / pb;
+                for (int idx = pt; idx < rows * ppr; idx += 128) {
+                    const int row = idx % rows, pc = idx / rows;
+                    const int ol2 = row / Bp, b = row % Bp;
+                    const int j0 = pc * (pb / 2);
+                    const int t = tile * TP + ol2;
+                    const bool valid = t < a.Ndst && j0 < a.nchg * a.CCg;
+                    const int dstp = valid ? (a.order ? a.order[t] : t) : 0;
+                    const __nv_bfloat16* src = Gb + (size_t)dstp * grow + ((size_t)(j0 / a.CCg) * Bp + b) * a.CCg + j0 % a.CCg;
+                    const uint32_t dst = g_sa + tc::mnmajor16_off(j0, row, GMN8, 128);
+                    if (pb == 16) tc::cp_async16_zfill(dst, src, valid);
+                    else tc::cp_async8_zfill(dst, src, valid);
+                }
+                tc::cp_async_mbar_arrive_noinc(g_full);
+            }
             for (int j = pre; j < total; ++j) {
                 issue_stage(c, st);
                 if (++st == nst) st = 0, ++c;
@@ -380,8 +421,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             if (a.dbg && blockIdx.x == 0 && lane == 0) a.dbg[8] = clock64() - tstart, a.dbg[9] = m_xfull, a.dbg[10] = m_dempty, a.dbg[12] = m_phifull;
 #endif
         }
-    } else if (warp == 9) {
-        // ===== stage-C issuer (one thread): regrouped T x W2 -> Y ===========================================
+    } else if (warp == 9 && !DW) {
+        // ===== stage-C issuer (one elected lane): regrouped T x W2 -> Y ======================================
         {
             const uint32_t idC = tc::make_idesc_bf16(128, CdP, false, false);
             const uint64_t da0 = tc::make_smem_desc(tc::smem_u32(ac_s), AC_K8, ACR);
@@ -411,6 +452,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             if (a.dbg && blockIdx.x == 0 && lane == 0) a.dbg[11] = m_acfull, a.dbg[13] = m_yempty;
 #endif
         }
+    } else if (warp == 9 && DW) {
+        // ===== dW issuer: D_dw[group][(h,i)][j] += T^T x G over the tile's rows ==================================
+        {
+            const uint32_t idW = tc::make_idesc_bf16(MDW, CgP, true, true);
+            // A = the regroup tile read MN-major: 8 k-values (one 16-byte line) contiguous, k-groups AC_K8 apart, K = rows
+            const uint64_t da0 = tc::make_smem_desc(tc::smem_u32(ac_s), ACR, AC_K8);
+            const uint64_t db0 = tc::make_smem_desc(tc::smem_u32(g_s), 128, GMN8);
+            uint32_t cc = 0, tt = 0;
+            for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
+                tc::mbar_wait(g_full, tt & 1);
+                for (int c = 0; c < nch; ++c, ++cc) {
+                    tc::mbar_wait(ac_full, cc & 1);
+                    tc::fence_after_sync();
+                    if ((c % CPP) == CPP - 1 || c == nch - 1) {          // the chunk group is complete
+                        if (tc::elect_one()) {
+                            const uint32_t dcol = tmem_y + (c / CPP) * CgP;
+                            for (int ks = 0; ks < rows / 16; ++ks)
+                                tc::mma_bf16_ss(dcol, da0 + (uint64_t)((ks * 2 * ACR) >> 4), db0 + (uint64_t)((ks * 256) >> 4), idW,
+                                                tt > 0 || ks > 0);
+                            tc::mma_commit(ac_empty);
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (tc::elect_one()) tc::mma_commit(g_empty);
+                __syncwarp();
+            }
+            if (tc::elect_one()) tc::mma_commit(y_full);                 // every dW MMA of this CTA has retired
+            __syncwarp();
+        }
     } else if (warp < 4 || warp >= 10) {
         // ===== regroup + output, two groups of 4 warps (thread = TMEM lane m = (point in tile, filter component));
         // group 0 (warps 0-3) takes the first half of a chunk's columns, group 1 (warps 10-13) the second =========
@@ -420,8 +491,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const size_t yrow = (size_t)qc_cp4(a.Cd) * Bp;
         // element (row = ol*Bp + b, k = h*CC + il) of the K-major stage-C operand
-        unsigned char* dst0 = ac_s + (size_t)((h * CC) >> 3) * AC_K8 + ((h * CC) & 7) * 2;
-        uint32_t cc = 0, tt = 0;
+        unsigned char* dst00 = ac_s + (size_t)((h * CC) >> 3) * AC_K8 + ((h * CC) & 7) * 2;
+        uint32_t cc = 0, tt = 0, gc = 0;
         PROF_DECL(e_dfull); PROF_DECL(e_acempty); PROF_DECL(e_regroup); PROF_DECL(e_yfull); PROF_DECL(e_out);
 #ifdef QC_MMA_PROFILE
         const long long tstart = clock64();
@@ -431,8 +502,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             for (int c = 0; c < nch; ++c, ++cc) {
                 const uint32_t buf = cc & 1, ph = (cc >> 1) & 1;
                 PROF_WAIT(e_dfull, tc::mbar_wait(&d_full[buf], ph));
-                PROF_WAIT(e_acempty, tc::mbar_wait(ac_empty, (cc & 1) ^ 1));           // stage C of the previous chunk has read the tile
+                if (!DW) {
+                    PROF_WAIT(e_acempty, tc::mbar_wait(ac_empty, (cc & 1) ^ 1));       // stage C of the previous chunk has read the tile
+                } else if ((c % CPP) == 0) {
+                    tc::mbar_wait(ac_empty, (gc & 1) ^ 1);                             // ... the dW MMAs of the previous chunk group
+                    ++gc;
+                }
                 tc::fence_after_sync();
+                unsigned char* dst0 = dst00 + (DW ? (c % CPP) * CC * AC_K8 : 0);
 #ifdef QC_MMA_PROFILE
                 const long long tr0 = clock64();
 #endif
@@ -482,6 +559,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
                 e_regroup += clock64() - tr0;
 #endif
             }
+            if (DW) continue;
             // output rows of this tile: TMEM lane = row % 128, row = (point in tile) * Bp + batch lane
             PROF_WAIT(e_yfull, tc::mbar_wait(y_full, tt & 1));
             tc::fence_after_sync();
@@ -516,6 +594,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             e_out += clock64() - to0;
 #endif
         }
+        if (DW && grp == 0) {
+            // partial d W_last of this CTA: accumulator row m = (chunk in group, h, channel in chunk); an M = 64 accumulator
+            // keeps row m in TMEM lane (m % 16) + 32 * (m / 16)
+            tc::mbar_wait(y_full, 0);
+            tc::fence_after_sync();
+            const int ngrp = (nch + CPP - 1) / CPP;
+            const bool has_row = MDW == 128 || lane < 16;
+            const int mrow = MDW == 128 ? m : (warp & 3) * 16 + lane;
+            for (int g = 0; g < ngrp; ++g)
+                for (int q = 0; q < CgP / 16; ++q) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(lane_base + tmem_y + g * CgP + q * 16, r);
+                    tc::wait_ld();
+                    if (has_row) {
+                        float* out = a.dw_part + (((size_t)blockIdx.x * ngrp + g) * MDW + mrow) * CgP + q * 16;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(out + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    }
+                }
+        }
 #ifdef QC_MMA_PROFILE
         if (a.dbg && blockIdx.x == 0 && tid == 0) {
             a.dbg[16] = clock64() - tstart, a.dbg[17] = e_dfull, a.dbg[18] = e_acempty, a.dbg[19] = e_regroup, a.dbg[20] = e_yfull,
@@ -528,18 +628,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-template <int CC, int LB, int VAR = 0>
+inline int mma_grid(const MmaArgs& a)
+{
+    const int grid = min(qc_num_sms(), a.ntiles * a.nblk);
+    return grid < 1 ? 1 : grid;
+}
+
+template <int CC, int LB, int VAR = 0, bool DW = false>
 int launch_mma(const MmaArgs& a, cudaStream_t st)
 {
     const int CdP = max(16, (a.Cd + 15) & ~15);
-    const size_t smem = mma_smem_bytes(CC, 1 << LB, a.nch, CdP, a.max_ku);
+    const size_t smem = mma_smem_bytes(CC, 1 << LB, a.nch, CdP, a.max_ku, DW, (a.Cg + 15) & ~15);
     if (smem > 227 * 1024) return 0;
-    QC_CUDA((qc_set_max_smem<k_contract_mma<CC, LB, VAR>>((int)smem)));
-    int grid = min(qc_num_sms(), a.ntiles * a.nblk);
-    if (grid < 1) grid = 1;
-    k_contract_mma<CC, LB, VAR><<<grid, NTHREADS, smem, st>>>(a);
+    QC_CUDA((qc_set_max_smem<k_contract_mma<CC, LB, VAR, DW>>((int)smem)));
+    k_contract_mma<CC, LB, VAR, DW><<<mma_grid(a), NTHREADS, smem, st>>>(a);
     QC_CHECK_LAUNCH();
     return 1;
+}
+
+// d W_last[(i*Cg + j)*H + h] = sum over the CTAs' partial accumulators, in CTA order (deterministic)
+__global__ void k_dw_mma_reduce(const float* __restrict__ part, int ncta, int ngrp, int MDW, int CgP, int CC, int cpp, int Cs,
+                                int Cg, int H, float* __restrict__ dw)
+{
+    const int total = Cs * Cg * H;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int h = t % H, j = (t / H) % Cg, i = t / (H * Cg);
+        const int c = i / CC, il = i % CC;
+        const int g = c / cpp, m = (c % cpp) * 8 * CC + h * CC + il;
+        const float* p = part + ((size_t)g * MDW + m) * CgP + j;
+        const size_t stride = (size_t)ngrp * MDW * CgP;
+        float s0 = 0.f;
+        for (int k = 0; k < ncta; ++k) s0 += p[(size_t)k * stride];
+        dw[t] = s0;
+    }
 }
 
 // fp32 [B][C][N] -> bf16 packed [nblk][N][nch][Bp][CC]: 64 points x (CC channels x Bp lanes) per block through a
@@ -631,6 +752,7 @@ int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const void* tile_ent, cons
     a.w_last = w_last;
     a.Nsrc = Nsrc, a.Ndst = Ndst, a.Cs = Cs, a.Cd = Cd, a.H = H, a.HPphi = HPphi, a.nch = qc_ceil_div(Cs, CC);
     a.transposed = transposed, a.ntiles = ntiles, a.nblk = qc_nblk(B), a.max_ku = max_ku;
+    a.G = nullptr, a.dw_part = nullptr, a.Cg = 0, a.nchg = 0, a.CCg = 4;
     a.dbg = nullptr;
     const cudaStream_t st = (cudaStream_t)stream;
 #ifdef QC_MMA_PROFILE
@@ -661,6 +783,66 @@ int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const void* tile_ent, cons
 #endif
     if (rc == 0) return QC_EUNSUP;
     return rc == 1 ? 0 : rc;
+}
+
+// d W_last of the reduced-precision mode: same tiles and gather as the forward (sources = in points / features Xh), the
+// regrouped stage-B result T contracted with the tile's grad_out rows Gh over (point, batch).  ws: scratch of
+// qc_dw_mma_workspace_bytes(...) bytes (per-CTA partial accumulators, summed in CTA order).
+size_t qc_dw_mma_workspace_bytes(int Cs, int Cg, int B)
+{
+    const int CC = qc_mma_chunk_channels(Cs, B);
+    if (CC == 0) return 0;
+    const int mdw = CC == 16 ? 128 : 64, cpp = mdw / (8 * CC), nch = qc_ceil_div(Cs, CC);
+    return (size_t)qc_num_sms() * qc_ceil_div(nch, cpp) * mdw * ((Cg + 15) & ~15) * sizeof(float);
+}
+
+int qc_dw_mma_smem_bytes(int Cs, int Cg, int B, int max_ku)
+{
+    const int CC = qc_mma_chunk_channels(Cs, B);
+    if (CC == 0) return 0;
+    return (int)mma_smem_bytes(CC, qc_bp(B), qc_ceil_div(Cs, CC), 0, max_ku, true, (Cg + 15) & ~15);
+}
+
+int qc_dw_mma(const void* Xh, int Nsrc, int Cs, const void* Gh, int Cg, const void* tile_ent, const int* tile_pptr,
+              const int* tile_uptr, const int* union_idx, int ntiles, int max_ku, const float* phi, int H, int HPphi,
+              const int* order, int Ndst, int B, void* ws, size_t ws_bytes, float* d_w_last, void* stream)
+{
+    const int Bp = qc_bp(B);
+    const int CC = qc_mma_chunk_channels(Cs, B), CCg = qc_mma_chunk_channels(Cg, B);
+    if (CC == 0 || CCg == 0 || H > 8 || H < 1 || (HPphi != 4 && HPphi != 8) || HPphi < H || Cg > 64 || max_ku < KST ||
+        (max_ku % KST) || max_ku > 0xffff)
+        return QC_EUNSUP;
+    const int mdw = CC == 16 ? 128 : 64, cpp = mdw / (8 * CC), nch = qc_ceil_div(Cs, CC), ngrp = qc_ceil_div(nch, cpp);
+    const int CgP = (Cg + 15) & ~15;
+    if (ngrp * CgP > 256) return QC_EUNSUP;                                  // TMEM: one accumulator per chunk group
+    if (ws == nullptr || ws_bytes < qc_dw_mma_workspace_bytes(Cs, Cg, B)) return QC_EWORKSPACE;
+    MmaArgs a;
+    a.X = reinterpret_cast<const __nv_bfloat16*>(Xh);
+    a.Y = nullptr;
+    a.order = order;
+    a.tile_ent = reinterpret_cast<const int2*>(tile_ent);
+    a.tile_pptr = tile_pptr;
+    a.tile_uptr = tile_uptr;
+    a.union_idx = union_idx;
+    a.phi = phi;
+    a.w_last = nullptr;
+    a.G = reinterpret_cast<const __nv_bfloat16*>(Gh);
+    a.dw_part = reinterpret_cast<float*>(ws);
+    a.Cg = Cg, a.nchg = qc_ceil_div(Cg, CCg), a.CCg = CCg;
+    a.Nsrc = Nsrc, a.Ndst = Ndst, a.Cs = Cs, a.Cd = 0, a.H = H, a.HPphi = HPphi, a.nch = nch;
+    a.transposed = 0, a.ntiles = ntiles, a.nblk = qc_nblk(B), a.max_ku = max_ku;
+    a.dbg = nullptr;
+    const cudaStream_t st = (cudaStream_t)stream;
+    int rc = 0;
+    if (Bp == 32) rc = launch_mma<4, 5, 4, true>(a, st);
+    else if (Bp == 16) rc = CC == 8 ? launch_mma<8, 4, 4, true>(a, st) : launch_mma<4, 4, 4, true>(a, st);
+    else if (Bp == 8) rc = CC == 16 ? launch_mma<16, 3, 4, true>(a, st) : (CC == 8 ? launch_mma<8, 3, 4, true>(a, st) : launch_mma<4, 3, 2, true>(a, st));
+    if (rc == 0) return QC_EUNSUP;
+    if (rc != 1) return rc;
+    const int total = Cs * Cg * H;
+    k_dw_mma_reduce<<<qc_ceil_div(total, 256), 256, 0, st>>>(a.dw_part, mma_grid(a), ngrp, mdw, CgP, CC, cpp, Cs, Cg, H, d_w_last);
+    QC_CHECK_LAUNCH();
+    return 0;
 }
 
 }  // extern "C"

@@ -158,3 +158,53 @@ def test_dphi_mma_kernel(cuda_lib, d, n, ci, co, B, H, r, n_out):
     assert relerr(got.numpy(), ref(False).numpy()) < 1e-2
     if HP > H:
         assert float(dphi[:, H:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("d,n,ci,co,B,H,r,n_out", [
+    (3, 1500, 32, 32, 32, 8, 0.16, None),     # C3-like: chunk pairs (2 x 32 k-values = one M = 64 accumulator), 4 groups
+    (2, 900, 16, 16, 8, 4, 0.1, None),        # batch 8, 16 channels per chunk: one M = 128 accumulator
+    (2, 800, 8, 12, 16, 8, 0.09, 300),        # batch 16, 8 channels per chunk (M = 64 single chunk), cross-level
+    (2, 700, 20, 24, 40, 8, 0.1, None),       # two batch blocks, odd number of chunks (last group half empty)
+    (2, 1000, 4, 8, 8, 8, 0.08, None),        # 4 channels, 32-column chunks
+])
+def test_dw_mma_kernel(cuda_lib, d, n, ci, co, B, H, r, n_out):
+    """qc_dw_mma through the C ABI: d W_last = sum_{o,b} T[o;b,i,h] g[b,j,o] against float64 with the same operand
+    roundings (features, phi, T and grad_out rounded to bf16): <= 2e-3, and <= 1e-2 from the exact value."""
+    from pytorch_quadconv_b200 import _cabi as C, ops
+    g = torch.Generator().manual_seed(57 + n)
+    pts = torch.rand(n, d, generator=g)
+    out_pts = pts if n_out is None else pts[torch.randperm(n, generator=g)[:n_out]].contiguous()
+    No = out_pts.shape[0]
+    x = torch.randn(B, ci, n, generator=g)
+    go = torch.randn(B, co, No, generator=g)
+    res = ops.build_pairs(out_pts.cuda(), pts.cuda(), float(r), n_out is None)
+    ev, pair_row, pair_col, row_ptr, cell_out = res[0], res[1], res[2], res[3], res[9]
+    P = ev.shape[0]
+    HP = 4 if H <= 4 else 8
+    phi = torch.zeros(P, HP)
+    phi[:, :H] = torch.randn(P, H, generator=g)
+    ent, pptr, uptr, uidx, max_ku = ops.build_union_tables(row_ptr, pair_col, cell_out, No, n)
+    xh, gh = ops._pack_bf16(x.cuda()), ops._pack_bf16(go.cuda())
+    L = C.lib()
+    wsb = L.qc_dw_mma_workspace_bytes(ci, co, B)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    dw = torch.full((ci * co, H), float("nan"), device="cuda")
+    C.check(L.qc_dw_mma(C.ptr(xh), n, ci, C.ptr(gh), co, C.ptr(ent), C.ptr(pptr), C.ptr(uptr), C.ptr(uidx),
+                        uptr.numel() - 1, max_ku, C.ptr(phi.cuda()), H, HP, C.ptr(cell_out), No, B, C.ptr(ws), wsb,
+                        C.ptr(dw), C.stream()), "qc_dw_mma")
+    torch.cuda.synchronize()
+    io, ii = ev[:, 0].cpu(), ev[:, 1].cpu()
+
+    def ref(rounded):
+        f = (lambda t: _rb(t)) if rounded else (lambda t: t.double())
+        T = torch.zeros(No, B, ci, H, dtype=torch.float64)
+        xs, ph = f(x), f(phi[:, :H])
+        for s in range(0, P, 2048):
+            T.index_add_(0, io[s:s + 2048], torch.einsum("ph,bip->pbih", ph[s:s + 2048], xs[:, :, ii[s:s + 2048]]))
+        if rounded:
+            T = _rb(T)
+        return torch.einsum("obih,bjo->ijh", T, f(go)).reshape(ci * co, H)
+    got = dw.cpu()
+    assert torch.isfinite(got).all()
+    assert relerr(got.numpy(), ref(True).numpy()) < 2e-3
+    assert relerr(got.numpy(), ref(False).numpy()) < 1e-2
