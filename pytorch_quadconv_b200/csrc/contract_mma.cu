@@ -133,8 +133,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     uint64_t* x_empty = x_full + NST;        // [NST]  MMA commit -> producers
     uint64_t* d_full = x_empty + NST;        // [2]    MMA commit -> regroup
     uint64_t* d_empty = d_full + 2;          // [2]    regroup (4) -> MMA
-    uint64_t* ac_full = d_empty + 2;         // regroup (4) -> MMA
-    uint64_t* ac_empty = ac_full + 1;        // MMA commit -> regroup
+    uint64_t* ac_full = d_empty + 2;         // [2] regroup (8 warps) -> MMA; DW: one per chunk slot of the regroup tile, so that
+                                             // a barrier is never more than one phase ahead of its waiter
+    uint64_t* ac_empty = ac_full + 2;        // MMA commit -> regroup
     uint64_t* phi_full = ac_empty + 1;       // producers (4) -> MMA
     uint64_t* phi_empty = phi_full + 1;      // MMA commit -> producers
     uint64_t* y_full = phi_empty + 1;        // MMA commit -> output
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     if (tid == 32) {
         for (int i = 0; i < NST; ++i) tc::mbar_init(&x_full[i], 128), tc::mbar_init(&x_empty[i], 1);
         for (int i = 0; i < 2; ++i) tc::mbar_init(&d_full[i], 1), tc::mbar_init(&d_empty[i], 8);
-        tc::mbar_init(ac_full, 8), tc::mbar_init(ac_empty, 1);
+        tc::mbar_init(&ac_full[0], 8), tc::mbar_init(&ac_full[1], 8), tc::mbar_init(ac_empty, 1);
         tc::mbar_init(phi_full, 4), tc::mbar_init(phi_empty, 1);
         tc::mbar_init(y_full, 1), tc::mbar_init(y_empty, 8);
         tc::mbar_init(g_full, 128), tc::mbar_init(g_empty, 1);
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
                 PROF_WAIT(m_yempty, tc::mbar_wait(y_empty, (tt & 1) ^ 1));       // the previous tile's output has left TMEM
                 for (int c = 0; c < nch; ++c, ++cc) {
-                    PROF_WAIT(m_acfull, tc::mbar_wait(ac_full, cc & 1));
+                    PROF_WAIT(m_acfull, tc::mbar_wait(&ac_full[0], cc & 1));
                     tc::fence_after_sync();
                     if (tc::elect_one()) {
                         const uint64_t dbc = db0 + (uint64_t)((c * W2CH) >> 4);
@@ -455,15 +456,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     } else if (warp == 9 && DW) {
         // ===== dW issuer: D_dw[group][(h,i)][j] += T^T x G over the tile's rows ==================================
         {
-            const uint32_t idW = tc::make_idesc_bf16(MDW, CgP, true, true);
+            // (issued with M = 128: an M = 64 MMA never retired here; accumulator rows >= MDW read neighbouring
+            //  shared-memory bytes -- finite bf16 data -- and are never looked at)
+            const uint32_t idW = tc::make_idesc_bf16(128, CgP, true, true);
             // A = the regroup tile read MN-major: 8 k-values (one 16-byte line) contiguous, k-groups AC_K8 apart, K = rows
             const uint64_t da0 = tc::make_smem_desc(tc::smem_u32(ac_s), ACR, AC_K8);
             const uint64_t db0 = tc::make_smem_desc(tc::smem_u32(g_s), 128, GMN8);
-            uint32_t cc = 0, tt = 0;
+            uint32_t cc = 0, tt = 0, slot_uses[2] = {0, 0};
             for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x, ++tt) {
                 tc::mbar_wait(g_full, tt & 1);
                 for (int c = 0; c < nch; ++c, ++cc) {
-                    tc::mbar_wait(ac_full, cc & 1);
+                    const int hf = c % CPP;
+                    tc::mbar_wait(&ac_full[hf], slot_uses[hf] & 1);
+                    ++slot_uses[hf];
                     tc::fence_after_sync();
                     if ((c % CPP) == CPP - 1 || c == nch - 1) {          // the chunk group is complete
                         if (tc::elect_one()) {
@@ -553,7 +558,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
                 __syncwarp();
                 if (lane == 0) {
                     tc::mbar_arrive(&d_empty[buf]);
-                    tc::mbar_arrive(ac_full);
+                    tc::mbar_arrive(&ac_full[DW ? c % CPP : 0]);
                 }
 #ifdef QC_MMA_PROFILE
                 e_regroup += clock64() - tr0;
@@ -595,13 +600,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
 #endif
         }
         if (DW && grp == 0) {
-            // partial d W_last of this CTA: accumulator row m = (chunk in group, h, channel in chunk); an M = 64 accumulator
-            // keeps row m in TMEM lane (m % 16) + 32 * (m / 16)
+            // partial d W_last of this CTA: accumulator row (= TMEM lane) m = (chunk in group, h, channel in chunk), m < MDW
             tc::mbar_wait(y_full, 0);
             tc::fence_after_sync();
             const int ngrp = (nch + CPP - 1) / CPP;
-            const bool has_row = MDW == 128 || lane < 16;
-            const int mrow = MDW == 128 ? m : (warp & 3) * 16 + lane;
+            const bool has_row = m < MDW;
+            const int mrow = m;
             for (int g = 0; g < ngrp; ++g)
                 for (int q = 0; q < CgP / 16; ++q) {
                     uint32_t r[16];

@@ -4,6 +4,7 @@
 // Bit layouts follow the PTX ISA "tcgen05" matrix/instruction descriptor tables.
 #pragma once
 #include <stdint.h>
+#include <cstdio>
 
 namespace tc {
 
@@ -107,6 +108,31 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#ifdef QC_MBAR_WATCHDOG
+// debug builds: a wait that lasts longer than ~1 s reports the barrier (shared-memory address, parity, block, thread) and traps
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const long long t0 = clock64();
+    bool said = false;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        const long long dt = clock64() - t0;
+        if (dt > 2000000000LL && !said && (threadIdx.x & 31) == 0 && blockIdx.x == 0) {
+            printf("mbar_wait stuck: bar@%u parity %u block %d warp %d\n", smem_u32(bar), parity, (int)blockIdx.x, (int)(threadIdx.x >> 5));
+            said = true;
+        }
+        if (dt > 8000000000LL) __trap();
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     asm volatile(
@@ -121,6 +147,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+#endif
 
 // true in exactly one lane of a fully converged warp (the lane that issues tcgen05.mma / commit); every lane must call it
 __device__ __forceinline__ bool elect_one()

@@ -360,6 +360,25 @@ def tc_supported(Cs: int, Cd: int, H: int, B: int, max_ku: int) -> bool:
     return 0 < L.qc_mma_smem_bytes(Cs, Cd, B, max_ku) <= _TC_MAX_SMEM
 
 
+def tc_backward_supported(Ci: int, Co: int, H: int, B: int, max_ku_fwd: int, max_ku_bwd: int) -> bool:
+    """The three tensor-core backward kernels (d features = qc_contract_mma on the CSC view, qc_dphi_mma, qc_dw_mma)
+    all serve the shape; otherwise the backward runs the fp32 kernels."""
+    L = C.lib()
+    if not tc_supported(Co, Ci, H, B, max_ku_bwd):                       # d features: sources = out points / out channels
+        return False
+    CC = L.qc_mma_chunk_channels(Ci, B)
+    if CC == 0 or _bp(B) * CC < 64 or max_ku_fwd > 384 or Co > 64 or L.qc_mma_chunk_channels(Co, B) == 0:
+        return False
+    if not 0 < L.qc_dphi_mma_smem_bytes(Ci, Co, B, max_ku_fwd) <= _TC_MAX_SMEM:
+        return False
+    mdw = 128 if CC == 16 else 64
+    nch, cpp = (Ci + CC - 1) // CC, mdw // (8 * CC)
+    ngrp = (nch + cpp - 1) // cpp
+    if ngrp * ((Co + 15) // 16 * 16) > 256:
+        return False
+    return 0 < L.qc_dw_mma_smem_bytes(Ci, Co, B, max_ku_fwd) <= _TC_MAX_SMEM
+
+
 def _pack_bf16(x: Tensor) -> Tensor:
     B, Cc, N = x.shape
     CC = C.lib().qc_mma_chunk_channels(Cc, B)
@@ -414,6 +433,72 @@ def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair
     CC = 4
     return (features.new_empty((B, out_channels, No)), features.new_empty((pair_row.shape[0], HP)),
             features.new_empty((_nblk(B), Ni, (Ci + CC - 1) // CC, _bp(B), CC), dtype=torch.bfloat16))
+
+
+@torch.library.custom_op("quadconv_b200::qc_backward_tc", mutates_args=())
+@_on_device
+def qc_backward_tc(grad_out: Tensor, xh: Tensor, phi: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor,
+                   hidden_ws: Sequence[Tensor], w_last: Tensor, pair_row: Tensor, pair_col: Tensor,
+                   order_out: Optional[Tensor], order_in: Optional[Tensor],
+                   f_ent: Tensor, f_pptr: Tensor, f_uptr: Tensor, f_uidx: Tensor, f_max_ku: int,
+                   b_ent: Tensor, b_pptr: Tensor, b_uptr: Tensor, b_uidx: Tensor, b_max_ku: int,
+                   batch: int, in_channels: int, out_channels: int, has_bias: bool) -> List[Tensor]:
+    """Backward of the reduced-precision mode, all three contractions on the tensor cores (bf16 operands, fp32
+    accumulation): d(phi) (qc_dphi_mma), d W_last (qc_dw_mma), d features (qc_contract_mma on the CSC view); the
+    per-pair chain rule through the hidden layers stays fp32 (qc_pair_phi_bwd).
+    Returns [d_features, d_quad_w, d_w_last, d_bias (or empty), *d_hidden_ws]."""
+    import ctypes
+    grad_out = _f32c(grad_out, "grad_out")
+    hidden_ws = [_f32c(w, "filter weight") for w in hidden_ws]
+    w_last = _f32c(w_last, "filter weight")
+    B, Ci, Co = batch, in_channels, out_channels
+    Ni, No, d = in_pts.shape[0], out_pts.shape[0], out_pts.shape[1]
+    H = w_last.shape[1]
+    HP = _hp(H)
+    P = pair_row.numel()
+    dev = grad_out.device
+    L = C.lib()
+    st = C.stream()
+    f32 = dict(dtype=torch.float32, device=dev)
+    gh = _pack_bf16(grad_out)
+    d_bias = torch.empty(0, **f32)
+    if has_bias:
+        d_bias = torch.empty((1, Co, No), **f32)
+        C.check(L.qc_batch_sum(C.ptr(grad_out), B, Co, No, C.ptr(d_bias), st), "qc_batch_sum")
+    nft, nbt = f_uptr.numel() - 1, b_uptr.numel() - 1
+    # d phi (forward view: tiles of out points, gathered feature rows) and the per-pair chain rule
+    dphi = (torch.zeros if _nblk(B) > 1 else torch.empty)((1, max(P, 1), HP), **f32)
+    C.check(L.qc_dphi_mma(C.ptr(xh), Ni, Ci, C.ptr(gh), Co, C.ptr(f_ent), C.ptr(f_pptr), C.ptr(f_uptr), C.ptr(f_uidx), nft,
+                          f_max_ku, C.ptr(w_last), H, HP, C.ptr(order_out), No, B, C.ptr(dphi), st), "qc_dphi_mma")
+    d_hidden = [torch.zeros_like(w) for w in hidden_ws]
+    d_quad_w = torch.zeros(Ni, **f32)
+    mlp = C.make_mlp(d, hidden_ws, False)
+    dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
+    C.check(L.qc_pair_phi_bwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row), C.ptr(pair_col),
+                              P, d, mlp, HP, C.ptr(dphi), 1, dptrs, C.ptr(d_quad_w), st), "qc_pair_phi_bwd")
+    # d W_last (same tiles, the stage-B result recomputed and contracted with the grad rows)
+    d_w_last = torch.empty((Ci * Co, H), **f32)
+    wsb = L.qc_dw_mma_workspace_bytes(Ci, Co, B)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    C.check(L.qc_dw_mma(C.ptr(xh), Ni, Ci, C.ptr(gh), Co, C.ptr(f_ent), C.ptr(f_pptr), C.ptr(f_uptr), C.ptr(f_uidx), nft,
+                        f_max_ku, C.ptr(phi), H, HP, C.ptr(order_out), No, B, C.ptr(ws), wsb, C.ptr(d_w_last), st), "qc_dw_mma")
+    # d features (CSC view: tiles of in points, gathered grad rows, W_last transposed)
+    dxp = torch.empty(_packed_shape(B, Ci, Ni), **f32)
+    C.check(L.qc_contract_mma(C.ptr(gh), No, Co, C.ptr(b_ent), C.ptr(b_pptr), C.ptr(b_uptr), C.ptr(b_uidx), nbt, b_max_ku,
+                              C.ptr(phi), H, HP, C.ptr(w_last), Ci, 1, C.ptr(order_in), Ni, B, C.ptr(dxp), st),
+            "qc_contract_mma (d features)")
+    d_features = _unpack(dxp, B, Ci, Ni, None)
+    return [d_features, d_quad_w, d_w_last, d_bias] + d_hidden
+
+
+@qc_backward_tc.register_fake
+def _(grad_out, xh, phi, out_pts, in_pts, quad_w, hidden_ws, w_last, pair_row, pair_col, order_out, order_in,
+      f_ent, f_pptr, f_uptr, f_uidx, f_max_ku, b_ent, b_pptr, b_uptr, b_uidx, b_max_ku, batch, in_channels,
+      out_channels, has_bias):
+    Ni, No = in_pts.shape[0], out_pts.shape[0]
+    e = grad_out.new_empty
+    return [e((batch, in_channels, Ni)), e(Ni), e(w_last.shape),
+            e((1, out_channels, No)) if has_bias else e(0)] + [e(w.shape) for w in hidden_ws]
 
 
 @qc_forward.register_fake
@@ -539,8 +624,8 @@ class _QuadConvFn(torch.autograd.Function):
             tile_ent, tile_pptr, tile_uptr, union_idx, max_ku = tc["fwd"]
             out, phi, xh = qc_forward_tc(features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
                                          pair_col, tc["order_out"], tile_ent, tile_pptr, tile_uptr, union_idx, max_ku, Ci, Co)
-            # (the backward of this mode still runs the fp32 kernels: it re-packs the fp32 features)
-            ctx.save_for_backward(features, phi, quad_w, w_last, *hidden_ws)
+            # the tensor-core backward reads the bf16 packed features; shapes it does not serve re-pack the fp32 input
+            ctx.save_for_backward(xh if tc.get("bwd") is not None else features, phi, quad_w, w_last, *hidden_ws)
         else:
             out, phi, xp = qc_forward(features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
                                       pair_col, row_ptr, order_out, Ci, Co, mlp_bf16)
@@ -555,6 +640,11 @@ class _QuadConvFn(torch.autograd.Function):
         xp, phi, quad_w, w_last, *hidden_ws = ctx.saved_tensors
         out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = ctx.tables[:10]
         B, Ci, Co, has_bias, mlp_bf16 = ctx.dims
+        if ctx.tc is not None and ctx.tc.get("bwd") is not None:
+            tc = ctx.tc
+            res = qc_backward_tc(grad_out, xp, phi, out_pts, in_pts, quad_w, list(hidden_ws), w_last, pair_row, pair_col,
+                                 tc["order_out"], tc["order_in"], *tc["fwd"], *tc["bwd"], B, Ci, Co, has_bias)
+            return (res[0], res[1], res[2], res[3] if has_bias else None, None, None, *res[4:])
         if ctx.tc is not None:
             with torch.cuda.device(xp.device):
                 xp = _pack(_f32c(xp, "features"))

@@ -62,6 +62,7 @@ class QuadConv(nn.Module):
         self._tc = None
         self._tc_key = None
         self.tc_active = False           # whether the last forward ran the tensor-core kernels
+        self.tc_backward_active = False  # ... and whether its backward will
 
         assert spatial_dim > 0                                   # quadconv.py:44
         # limits of the sm_100a kernels, reported at construction instead of at the first forward (README "Limits")
@@ -211,9 +212,16 @@ class QuadConv(nn.Module):
         pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, _, _, cell_out, cell_in = tables
         key = (id(pair_row), pair_row.data_ptr())
         if self._tc is None or self._tc_key != key:
-            # tiles = 16 consecutive points of the plain cell-sorted order (spatial neighbours share their supports)
+            # tiles = 16 consecutive points of the plain cell-sorted order (spatial neighbours share their supports);
+            # forward view (out points gather in points) and CSC view (in points gather out points, phi rows via csc_pair)
             fwd = ops.build_union_tables(row_ptr, pair_col, cell_out, self.out_points, self.in_points)
-            self._tc = {"fwd": fwd, "order_out": cell_out, "order_in": cell_in}
+            bwd = ops.build_union_tables(csc_ptr, csc_row, cell_in, self.in_points, self.out_points, csc_pair)
+            self._tc = {"fwd": fwd, "bwd_tables": bwd, "order_out": cell_out, "order_in": cell_in}
             self._tc_key = key
-        self.tc_active = ops.tc_supported(self.in_channels, self.out_channels, H, B, self._tc["fwd"][4])
-        return self._tc if self.tc_active else None
+        tc = self._tc
+        self.tc_active = ops.tc_supported(self.in_channels, self.out_channels, H, B, tc["fwd"][4])
+        if not self.tc_active:
+            return None
+        bwd_ok = ops.tc_backward_supported(self.in_channels, self.out_channels, H, B, tc["fwd"][4], tc["bwd_tables"][4])
+        self.tc_backward_active = bwd_ok
+        return dict(tc, bwd=tc["bwd_tables"] if bwd_ok else None)
