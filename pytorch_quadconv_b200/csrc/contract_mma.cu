@@ -86,8 +86,9 @@ __host__ __device__ constexpr uint32_t ac_row8(int CC, int Bp)
 
 __host__ __device__ constexpr size_t mma_smem_bytes(int CC, int Bp, int nch, int CdP, int max_ku, bool dw = false, int CgP = 0)
 {
-    const int cpp = dw ? (CC == 16 ? 128 : 64) / (8 * CC) : 1;
-    return (size_t)max_ku * 256 + (size_t)NST * (KST / 8) * (Bp * CC / 8) * 144 + (size_t)(TP * Bp / 8) * ac_row8(CC * cpp, Bp) +
+    const int cpp = 1;
+    const size_t ring = (Bp * CC) % 64 == 0 ? (size_t)NST * KST * Bp * CC * 2 : (size_t)NST * (KST / 8) * (Bp * CC / 8) * 144;
+    return (size_t)max_ku * 256 + ring + (size_t)(TP * Bp / 8) * ac_row8(CC * cpp, Bp) +
            (dw ? (size_t)TP * Bp * CgP * 2 : (size_t)nch * CdP * 16 * CC) + (size_t)max_ku * 8 + 64 * 8;
 }
 
@@ -102,8 +103,10 @@ template <int CC, int LB, int VAR, bool DW>
 __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
 {
     constexpr int Bp = 1 << LB, NC = Bp * CC, QN = NC / 8;
-    constexpr int MDW = CC == 16 ? 128 : 64;              // M of the dW GEMM
-    constexpr int CPP = DW ? MDW / (8 * CC) : 1;          // channel chunks side by side in the regroup tile
+    // (one channel chunk per accumulator: pairing two 32-value chunks into one M = 64 operand would need both halves of
+    //  the regroup tile resident, 37 KB that the gather ring needs more)
+    constexpr int MDW = 8 * CC;                           // valid rows of the dW accumulator (the MMA is issued with M = 128)
+    constexpr int CPP = 1;                                // channel chunks side by side in the regroup tile
     constexpr bool CG = (VAR & 1) != 0, ROWMAJ = (VAR & 2) != 0;
     // bit 2: the gathered operand in the 128-byte-swizzle MN-major layout (rows of 64 columns = 128 contiguous bytes,
     // 16-byte chunks XOR-ed with the row index inside 1 KB atoms): a 128-byte line from L2 lands as ONE shared-memory
@@ -796,7 +799,7 @@ size_t qc_dw_mma_workspace_bytes(int Cs, int Cg, int B)
 {
     const int CC = qc_mma_chunk_channels(Cs, B);
     if (CC == 0) return 0;
-    const int mdw = CC == 16 ? 128 : 64, cpp = mdw / (8 * CC), nch = qc_ceil_div(Cs, CC);
+    const int mdw = 8 * CC, cpp = 1, nch = qc_ceil_div(Cs, CC);
     return (size_t)qc_num_sms() * qc_ceil_div(nch, cpp) * mdw * ((Cg + 15) & ~15) * sizeof(float);
 }
 
@@ -816,7 +819,7 @@ int qc_dw_mma(const void* Xh, int Nsrc, int Cs, const void* Gh, int Cg, const vo
     if (CC == 0 || CCg == 0 || H > 8 || H < 1 || (HPphi != 4 && HPphi != 8) || HPphi < H || Cg > 64 || max_ku < KST ||
         (max_ku % KST) || max_ku > 0xffff)
         return QC_EUNSUP;
-    const int mdw = CC == 16 ? 128 : 64, cpp = mdw / (8 * CC), nch = qc_ceil_div(Cs, CC), ngrp = qc_ceil_div(nch, cpp);
+    const int mdw = 8 * CC, cpp = 1, nch = qc_ceil_div(Cs, CC), ngrp = qc_ceil_div(nch, cpp);
     const int CgP = (Cg + 15) & ~15;
     if (ngrp * CgP > 256) return QC_EUNSUP;                                  // TMEM: one accumulator per chunk group
     if (ws == nullptr || ws_bytes < qc_dw_mma_workspace_bytes(Cs, Cg, B)) return QC_EWORKSPACE;

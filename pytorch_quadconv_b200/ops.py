@@ -371,10 +371,8 @@ def tc_backward_supported(Ci: int, Co: int, H: int, B: int, max_ku_fwd: int, max
         return False
     if not 0 < L.qc_dphi_mma_smem_bytes(Ci, Co, B, max_ku_fwd) <= _TC_MAX_SMEM:
         return False
-    mdw = 128 if CC == 16 else 64
-    nch, cpp = (Ci + CC - 1) // CC, mdw // (8 * CC)
-    ngrp = (nch + cpp - 1) // cpp
-    if ngrp * ((Co + 15) // 16 * 16) > 256:
+    nch = (Ci + CC - 1) // CC                                            # one TMEM accumulator per channel chunk
+    if nch * ((Co + 15) // 16 * 16) > 256:
         return False
     return 0 < L.qc_dw_mma_smem_bytes(Ci, Co, B, max_ku_fwd) <= _TC_MAX_SMEM
 
