@@ -234,13 +234,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             const bool has_next = wi2 < nwork;
             int nst_next = 0, blk_next = 0;
             tc::named_bar_sync(2, 128);
+            const uint32_t rowbytes = (uint32_t)(nch * NC * 2);
+            auto row_off = [&](int u) { return u >= 0 ? (int)((uint32_t)u * rowbytes) : -1; };   // (< 4 GB: checked by the host)
             if (tt == 0)
-                for (int i = pt; i < ku; i += 128) uix[i] = __ldg(a.union_idx + u0 + i);
+                for (int i = pt; i < ku; i += 128) uix[i] = row_off(__ldg(a.union_idx + u0 + i));
             if (has_next) {
                 const int tile2 = wi2 % a.ntiles;
                 const int v0 = a.tile_uptr[tile2], kv = a.tile_uptr[tile2 + 1] - v0;
                 nst_next = kv / KST, blk_next = wi2 / a.ntiles;
-                for (int i = pt; i < kv; i += 128) uix_next[i] = __ldg(a.union_idx + v0 + i);
+                for (int i = pt; i < kv; i += 128) uix_next[i] = row_off(__ldg(a.union_idx + v0 + i));
             }
             tc::named_bar_sync(2, 128);
 
@@ -256,53 +258,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             constexpr int KGSTEP = 16 / QN;
             const uint32_t dst0 = x_sa + q * XSB + k8 * 16;
             const __nv_bfloat16* Xq = Xb + q * 8;
+            // The union list holds BYTE offsets of the rows (0xffffffff = padding): the copy addresses of a stage are
+            // formed from 32-bit loads issued together BEFORE the wait on the ring slot, then the copies go out back to
+            // back (the index load -> 64-bit address arithmetic -> copy chain of one piece after the other made the
+            // producers latency bound at ~700 cycles per stage: the slowest role of the kernel).
+            const char* Xbytes = reinterpret_cast<const char*>(Xb);
             auto issue_stage = [&](int c, int st) {
                 const uint32_t s = xit % NST, ph = (xit / NST) & 1;
-                PROF_WAIT(w_xempty, tc::mbar_wait(&x_empty[s], ph ^ 1));
-                if (SW) {
+                const uint32_t* uo = reinterpret_cast<const uint32_t*>(uix) + st * KST;
+                if constexpr (SW) {
                     // 8 lanes = the 8 chunks of one 128-byte row piece; line = (block of 64 columns, union row)
-                    constexpr int NLINE = KST * (NC / 64);
+                    constexpr int NJ = KST * (NC / 64) / 16;
                     const int cidx = pt & 7, l0 = pt >> 3;
-                    // L2 prefetch PF_CH channel chunks ahead (wrapping into the next tile): a stage is consumed when ALL
-                    // its 64 lines have arrived, i.e. after the slowest HBM miss; with the rows already in L2 the 64 KB
-                    // ring covers the (L2-hit) latency.  One lane of every row piece issues the prefetch.
-                    if (PF_CH > 0 && cidx == 0) {
-                        int c2 = c + PF_CH;
-                        const int* ux = uix;
-                        const __nv_bfloat16* Xp = Xb;
-                        bool ok = true;
-                        if (c2 >= nch) {
-                            c2 -= nch, ux = uix_next, Xp = a.X + (size_t)blk_next * a.Nsrc * srow;
-                            ok = has_next && st < nst_next;
-                        }
-                        if (ok) {
+                    uint32_t off[NJ];
 #pragma unroll
-                            for (int j = 0; j < NLINE / 16; ++j) {
-                                const int line = l0 + 16 * j, r = line % KST, xb = line / KST;
-                                const int u = ux[st * KST + r];
-                                if (u >= 0) tc::prefetch_l2(Xp + (size_t)u * srow + (size_t)c2 * NC + xb * 64);
-                            }
-                        }
-                    }
+                    for (int j = 0; j < NJ; ++j) off[j] = uo[(l0 + 16 * j) % KST];
+                    const char* base = Xbytes + (size_t)c * NC * 2 + cidx * 16;
+                    const uint32_t dbase = x_sa + s * STAGE + ((l0 % KST) * 128) + ((cidx ^ (l0 & 7)) << 4);
+                    PROF_WAIT(w_xempty, tc::mbar_wait(&x_empty[s], ph ^ 1));
 #pragma unroll
-                    for (int j = 0; j < NLINE / 16; ++j) {
-                        const int line = l0 + 16 * j, r = line % KST, xb = line / KST;
-                        const int u = uix[st * KST + r];
-                        const __nv_bfloat16* src = Xb + (size_t)c * NC + xb * 64 + cidx * 8 + (u >= 0 ? (size_t)u * srow : 0);
-                        const uint32_t dst = x_sa + s * STAGE + xb * XBLK + r * 128 + ((cidx ^ (r & 7)) << 4);
-                        if (CG) tc::cp_async16_cg_zfill(dst, src, u >= 0);
-                        else tc::cp_async16_zfill(dst, src, u >= 0);
+                    for (int j = 0; j < NJ; ++j) {
+                        // line = l0 + 16 j: row (l0 + 16 j) % 32 (same row & 7 for every j), block (l0 + 16 j) / 32
+                        const int line = l0 + 16 * j;
+                        const bool valid = off[j] != 0xffffffffu;
+                        const char* src = base + (line / KST) * 128 + (valid ? off[j] : 0u);
+                        const uint32_t dst = dbase + (line / KST) * XBLK + ((line % KST) - (l0 % KST)) * 128;
+                        if (CG) tc::cp_async16_cg_zfill(dst, src, valid);
+                        else tc::cp_async16_zfill(dst, src, valid);
                     }
                 } else {
+                    constexpr int NJ = (KST / 8 + KGSTEP - 1) / KGSTEP;
+                    uint32_t off[NJ];
 #pragma unroll
-                for (int kg = kg0; kg < KST / 8; kg += KGSTEP) {
-                    const int u = uix[st * KST + kg * 8 + k8];
-                    const __nv_bfloat16* src = Xq + (size_t)c * NC + (u >= 0 ? (size_t)u * srow : 0);
-                    if (CG)
-                        tc::cp_async16_cg_zfill(dst0 + s * STAGE + kg * XK8, src, u >= 0);
-                    else
-                        tc::cp_async16_zfill(dst0 + s * STAGE + kg * XK8, src, u >= 0);
-                }
+                    for (int j = 0; j < NJ; ++j) {
+                        const int kg = kg0 + j * KGSTEP;
+                        off[j] = kg < KST / 8 ? uo[kg * 8 + k8] : 0xffffffffu;
+                    }
+                    const char* base = Xbytes + ((size_t)c * NC + q * 8) * 2;
+                    PROF_WAIT(w_xempty, tc::mbar_wait(&x_empty[s], ph ^ 1));
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int kg = kg0 + j * KGSTEP;
+                        if (kg < KST / 8) {
+                            const bool valid = off[j] != 0xffffffffu;
+                            if (CG) tc::cp_async16_cg_zfill(dst0 + s * STAGE + kg * XK8, base + (valid ? off[j] : 0u), valid);
+                            else tc::cp_async16_zfill(dst0 + s * STAGE + kg * XK8, base + (valid ? off[j] : 0u), valid);
+                        }
+                    }
                 }
                 // the stage's mbarrier counts one arrival per producer thread, delivered by the copy unit when this
                 // thread's copies have landed: no wait on the issuing side, nothing held back
@@ -747,6 +749,7 @@ int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const void* tile_ent, cons
         max_ku > 0xffff)
         return QC_EUNSUP;
     if ((TP * Bp / 128) * max(16, (Cd + 15) & ~15) > 256) return QC_EUNSUP;   // TMEM: stage-C accumulators
+    if ((size_t)Nsrc * qc_ceil_div(Cs, CC) * Bp * CC * 2 >= 0xffffffffull) return QC_EUNSUP;   // 32-bit row offsets
     MmaArgs a;
     a.X = reinterpret_cast<const __nv_bfloat16*>(Xh);
     a.Y = Yp;
@@ -822,6 +825,7 @@ int qc_dw_mma(const void* Xh, int Nsrc, int Cs, const void* Gh, int Cg, const vo
     const int mdw = 8 * CC, cpp = 1, nch = qc_ceil_div(Cs, CC), ngrp = qc_ceil_div(nch, cpp);
     const int CgP = (Cg + 15) & ~15;
     if (ngrp * CgP > 256) return QC_EUNSUP;                                  // TMEM: one accumulator per chunk group
+    if ((size_t)Nsrc * nch * Bp * CC * 2 >= 0xffffffffull) return QC_EUNSUP;  // 32-bit row offsets
     if (ws == nullptr || ws_bytes < qc_dw_mma_workspace_bytes(Cs, Cg, B)) return QC_EWORKSPACE;
     MmaArgs a;
     a.X = reinterpret_cast<const __nv_bfloat16*>(Xh);

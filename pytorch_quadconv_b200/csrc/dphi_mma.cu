@@ -134,7 +134,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dphi_mma(const DphiMmaArgs a)
             const int tile = wi % a.ntiles, blk = wi / a.ntiles;
             const int u0 = a.tile_uptr[tile], ku = a.tile_uptr[tile + 1] - u0, nst = ku / KST;
             int* uix = uidx_s + (tt & 1) * a.max_ku;
-            for (int i = pt; i < ku; i += 128) uix[i] = __ldg(a.union_idx + u0 + i);
+            const uint32_t rowbytes = (uint32_t)(nch * NC * 2);
+            for (int i = pt; i < ku; i += 128) {
+                const int u = __ldg(a.union_idx + u0 + i);
+                uix[i] = u >= 0 ? (int)((uint32_t)u * rowbytes) : -1;      // byte offset of the row (< 4 GB, host-checked)
+            }
             tc::named_bar_sync(2, 128);
             // G tile: row = (point in tile, batch lane), K-major over the grad channels; pieces of min(16, 2*CCg) bytes
             tc::mbar_wait(g_empty, (tt & 1) ^ 1);
@@ -156,19 +160,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dphi_mma(const DphiMmaArgs a)
                 }
                 tc::cp_async_mbar_arrive_noinc(g_full);
             }
-            const __nv_bfloat16* Xb = a.X + (size_t)blk * a.Nsrc * srow;
-            constexpr int NLINE = KST * (NC / 64);
+            const char* Xbytes = reinterpret_cast<const char*>(a.X + (size_t)blk * a.Nsrc * srow);
+            constexpr int NJ = KST * (NC / 64) / 16;
             const int cidx = pt & 7, l0 = pt >> 3;
             for (int c = 0; c < nch; ++c)
                 for (int st = 0; st < nst; ++st) {
                     const uint32_t s = xit % NST, ph = (xit / NST) & 1;
+                    // byte offsets of this stage's rows, loaded together before the wait (see contract_mma.cu)
+                    const uint32_t* uo = reinterpret_cast<const uint32_t*>(uix) + st * KST;
+                    uint32_t off[NJ];
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) off[j] = uo[(l0 + 16 * j) % KST];
+                    const char* base = Xbytes + (size_t)c * NC * 2 + cidx * 16;
+                    const uint32_t dbase = x_sa + s * STAGE + ((l0 % KST) * 128) + ((cidx ^ (l0 & 7)) << 4);
                     tc::mbar_wait(&x_empty[s], ph ^ 1);
 #pragma unroll
-                    for (int j = 0; j < NLINE / 16; ++j) {
-                        const int line = l0 + 16 * j, r = line % KST, xb = line / KST;
-                        const int u = uix[st * KST + r];
-                        const __nv_bfloat16* src = Xb + (size_t)c * NC + xb * 64 + cidx * 8 + (u >= 0 ? (size_t)u * srow : 0);
-                        tc::cp_async16_zfill(x_sa + s * STAGE + xb * XBLK + r * 128 + ((cidx ^ (r & 7)) << 4), src, u >= 0);
+                    for (int j = 0; j < NJ; ++j) {
+                        const int line = l0 + 16 * j;
+                        const bool valid = off[j] != 0xffffffffu;
+                        tc::cp_async16_zfill(dbase + (line / KST) * XBLK + ((line % KST) - (l0 % KST)) * 128,
+                                             base + (line / KST) * 128 + (valid ? off[j] : 0u), valid);
                     }
                     tc::cp_async_mbar_arrive_noinc(&x_full[s]);
                     ++xit;
@@ -367,6 +378,7 @@ int qc_dphi_mma(const void* Xh, int Nsrc, int Cs, const void* Gh, int Cg, const 
     if (CC == 0 || CCg == 0 || Bp * CC < 64 || H > 8 || H < 1 || (HPphi != 4 && HPphi != 8) || HPphi < H || Cg > 64 ||
         max_ku < KST || (max_ku % KST) || max_ku > DT_COL)
         return QC_EUNSUP;
+    if ((size_t)Nsrc * qc_ceil_div(Cs, CC) * Bp * CC * 2 >= 0xffffffffull) return QC_EUNSUP;   // 32-bit row offsets
     DphiMmaArgs a;
     a.X = reinterpret_cast<const __nv_bfloat16*>(Xh);
     a.G = reinterpret_cast<const __nv_bfloat16*>(Gh);
