@@ -87,7 +87,7 @@ def _nccl_worker(rank, world, port, ret):
     _grads(model, shard_batch(x, rank, world), params)
     flat = red()                                     # pack + ncclAllReduce(AVG)
     torch.cuda.synchronize()
-    ret[rank] = (_rel(flat, full), float(max(_rel(p.grad, g) for p, g in
+    ret[rank] = (_rel(flat, full), float(max(_rel(p.grad.reshape(-1), g) for p, g in
                                              zip(params, torch.split(full, [p.numel() for p in params])))))
     dist.destroy_process_group()
 
