@@ -12,8 +12,8 @@ forward).  The work is done by hand-written sm_100a kernels behind a C ABI (incl
     [P,Ci,Co] filters, gather, einsum, scatter_add_ (:213-227)  fused contraction, nothing P-sized
     autograd                                                    fused analytic backward
 
-Deliberate deviations (documented in DESIGN.md): `filter_mode` other than 'single' raises
-(`share_in` raises AttributeError upstream too, `nested` computes a scrambled layout there);
+Deliberate deviations (documented in DESIGN.md): `filter_mode='share_in'` raises (it raises AttributeError
+upstream too); `'nested'` reproduces upstream's layout on a generic (materialised-filter) path;
 tensors must live on a CUDA device -- there is no CPU path.
 """
 from __future__ import annotations
@@ -89,6 +89,7 @@ class QuadConv(nn.Module):
         else:
             self.decay_param = decay_param
 
+        self.filter_mode = filter_mode
         self._init_filter(filter_seq, filter_mode)
 
         if bias:                                                 # quadconv.py:68-72
@@ -108,10 +109,20 @@ class QuadConv(nn.Module):
             # H/G evaluate the filter densely with plain torch ops; they exist for API parity and
             # for inspection -- forward() never materialises this [P,Ci,Co] tensor.
             self.H = lambda z: self.filter(z).reshape(-1, self.in_channels, self.out_channels)
-        elif filter_mode in ('share_in', 'nested'):
+        elif filter_mode == 'nested':                            # quadconv.py:105-114
+            # one scalar MLP per (in, out) channel pair.  Upstream concatenates the Ci*Co outputs along dim 0 and
+            # reshapes to (-1, Ci, Co), which interleaves the pair and channel indices; that layout is what reference
+            # checkpoints were trained with, so it is reproduced bit for bit (golden: tests/golden/layer_nested.npz).
+            # No factorisation over a shared last hidden activation exists for it: forward() takes the generic path
+            # (materialised filters, ATen contraction on the CUDA device) instead of the fused kernels.
+            mlp_spec = (self.spatial_dim, *filter_seq, 1)
+            self.filter = nn.ModuleList(self._create_mlp(mlp_spec)
+                                        for _ in range(self.in_channels * self.out_channels))
+            self.H = lambda z: torch.cat([m(z) for m in self.filter]).reshape(-1, self.in_channels, self.out_channels)
+        elif filter_mode == 'share_in':
             raise NotImplementedError(
-                f"filter_mode='{filter_mode}' is outside the B200 hot path (SURVEY.md 8f-4): upstream "
-                "'share_in' raises AttributeError and 'nested' interleaves pair and channel indices")
+                "filter_mode='share_in' raises AttributeError upstream (quadconv.py:102 reads self.channels_in, which "
+                "does not exist), so there is no reference behaviour to reproduce")
         else:                                                    # quadconv.py:116-117
             raise ValueError(f'core::modules::quadconv: Filter mode {filter_mode} is not supported.')
         self.G = self.H                                          # quadconv.py:120
@@ -146,6 +157,7 @@ class QuadConv(nn.Module):
         idx = res[0]
         self._tables = tuple(res[1:])
         self._tables_key = None
+        self._last_idx = idx
 
         if self.cache:                                           # quadconv.py:186-188
             self.eval_indices = nn.Parameter(idx, requires_grad=False)
@@ -189,6 +201,9 @@ class QuadConv(nn.Module):
             self._compute_eval_indices(mesh)
             tables = self._tables
 
+        if self.filter_mode != 'single':
+            return self._forward_generic(mesh, features, output_points, input_points)
+
         weights = mesh.weights()                                 # quadconv.py:247 (gather fused)
 
         if not self.output_same:                                 # quadconv.py:253-254
@@ -206,6 +221,24 @@ class QuadConv(nn.Module):
             tc = self._tc_tables(tables, features.shape[0], w_last.shape[1])
         return ops.quadconv_apply(features, weights, hidden_ws, w_last, self.bias, full,
                                   self.in_channels, self.out_channels, self.filter_dtype == torch.bfloat16, tc)
+
+    def _forward_generic(self, mesh, features, output_points, input_points):
+        """quadconv.py:247-263 for filter modes without a shared last hidden activation: the filter tensor is
+        materialised ([P, Ci, Co], like upstream) and contracted with ATen ops on the mesh's CUDA device; the pair
+        list still comes from the grid-binned search kernel."""
+        idx = self.eval_indices if self.cached else self._last_idx
+        io, ii = idx[:, 0], idx[:, 1]
+        w = mesh.weights()[ii]
+        z = output_points[io] - input_points[ii]
+        if not self.output_same:
+            mesh.step()
+        filters = self.G(z)
+        vals = torch.einsum('n,nij,bin->bjn', w, filters, features[:, :, ii])
+        out = torch.zeros(features.shape[0], self.out_channels, self.out_points, device=features.device,
+                          dtype=vals.dtype).index_add_(2, io, vals)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
 
     def _tc_tables(self, tables, B, H):
         """Union-tile tables of the tensor-core path (ops.build_union_tables), cached with the pair tables."""

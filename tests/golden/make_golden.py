@@ -123,6 +123,34 @@ def golden_layer(name, d, n, ci, co, B, fs, bias, seed, weight_args=None, r=None
     save(name, **arrs)
 
 
+def golden_nested(name="layer_nested", d=2, n=200, ci=2, co=3, B=2, fs=(4,), seed=9):
+    """filter_mode='nested' (quadconv.py:105-114): Ci*Co scalar MLPs whose outputs are concatenated along dim 0 and
+    reshaped -- the reference's (scrambled) layout is part of the contract, so it is pinned here."""
+    torch.manual_seed(seed)
+    pts = torch.rand(n, d)
+    x = torch.randn(B, ci, n, requires_grad=True)
+    mesh = MeshHandler(pts).construct([n])
+    qc = QuadConv(spatial_dim=d, in_points=n, out_points=n, in_channels=ci, out_channels=co, filter_seq=list(fs),
+                  filter_mode='nested', bias=True, output_same=True)
+    y = qc(mesh, x)
+    g = torch.randn(y.shape, generator=torch.Generator().manual_seed(seed + 1))
+    (y * g).sum().backward()
+    arrs = dict(pts=pts, x=x, grad_out=g, y=y, dx=x.grad, pairs=qc.eval_indices, r=np.float64(qc.decay_param), ci=ci, co=co,
+                bias=qc.bias, dbias=qc.bias.grad)
+    for k, v in qc.state_dict().items():
+        if k.startswith("filter."):
+            arrs["sd/" + k] = v
+    for k, p_ in qc.named_parameters():
+        if k.startswith("filter."):
+            arrs["grad/" + k] = p_.grad
+    for k, v in mesh.state_dict().items():
+        arrs["mesh/" + k] = v
+    for k, p_ in mesh.named_parameters():
+        if p_.grad is not None:
+            arrs["meshgrad/" + k] = p_.grad
+    save(name, **arrs)
+
+
 def golden_pool():
     torch.manual_seed(7)
     pts = torch.rand(600, 2)
@@ -221,3 +249,4 @@ if __name__ == "__main__":
     golden_pool()
     golden_mfnus()
     golden_autoencoder()
+    golden_nested()

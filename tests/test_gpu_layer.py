@@ -394,3 +394,38 @@ def test_fused_weight_map_matches_torch_composition(cuda_lib, d, n):
         assert relerr(got["_weight_network." + k].cpu().numpy(), p.grad.numpy()) < 1e-5, k
     # deterministic (no atomic scatter): bitwise reproducible
     assert torch.equal(mesh.weights(), w)
+
+
+def test_nested_filter_mode_matches_reference_golden(cuda_lib):
+    """filter_mode='nested' (quadconv.py:105-114): same state_dict keys as upstream, and -- with upstream's own
+    (interleaved) filter layout -- its output and every gradient, against the live-reference golden."""
+    import pytorch_quadconv_b200 as q
+    L = load_golden("layer_nested")
+    pts = torch.from_numpy(L["pts"])
+    n, ci, co = pts.shape[0], int(L["ci"]), int(L["co"])
+    mesh = q.MeshHandler(pts).construct([n])
+    mesh.load_state_dict({k[5:]: torch.from_numpy(L[k]) for k in L.files if k.startswith("mesh/")})
+    layer = q.QuadConv(spatial_dim=2, in_points=n, out_points=n, in_channels=ci, out_channels=co, filter_seq=[4],
+                       filter_mode='nested', bias=True, output_same=True)
+    ref_keys = sorted(k[3:] for k in L.files if k.startswith("sd/"))
+    assert sorted(k for k in layer.state_dict() if k.startswith("filter.")) == ref_keys
+    sd = {k[3:]: torch.from_numpy(L[k]) for k in L.files if k.startswith("sd/")}
+    sd["bias"] = torch.from_numpy(L["bias"])
+    layer.load_state_dict(sd)
+    mesh, layer = mesh.cuda(), layer.cuda()
+    x = torch.from_numpy(L["x"]).cuda().requires_grad_()
+    y = layer(mesh, x)
+    assert np.array_equal(layer.eval_indices.cpu().numpy(), L["pairs"])
+    assert relerr(y.detach().cpu().numpy(), L["y"]) < TOL
+    (y * torch.from_numpy(L["grad_out"]).cuda()).sum().backward()
+    assert relerr(x.grad.cpu().numpy(), L["dx"]) < TOL
+    assert relerr(layer.bias.grad.cpu().numpy(), L["dbias"]) < TOL
+    for k, p in layer.named_parameters():
+        if k.startswith("filter."):
+            assert relerr(p.grad.cpu().numpy(), L["grad/" + k]) < 2e-5, k
+    for k, p in mesh.named_parameters():
+        if p.requires_grad:
+            assert relerr(p.grad.cpu().numpy(), L["meshgrad/" + k]) < 5e-5, k
+    with pytest.raises(NotImplementedError):
+        q.QuadConv(spatial_dim=2, in_points=n, out_points=n, in_channels=ci, out_channels=co, filter_seq=[4],
+                   filter_mode='share_in')
