@@ -196,6 +196,39 @@ int qc_repack_wlast(const float* w_last, int Ci, int Co, int H, int HP, int mode
 int qc_unpack_dwlast(const float* dW2, int Ci, int Co, int H, float* d_w_last, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The whole layer in one call, fp32 parity mode, for hosts that do not compose the kernels themselves.
+ *   qc_layer_forward  replaces QuadConv.forward + _integrate, torch_quadconv/quadconv.py:238-265, :213-227:
+ *                     features [B][Ci][Ni] -> out [B][Co][No] (+ bias [Co][No] when given), reference layouts.
+ *   qc_layer_backward replaces autograd of the above: grad_out [B][Co][No] -> d_features [B][Ci][Ni], d_quad_w [Ni]
+ *                     (may be NULL), d_w_last [Ci*Co][H], d_hidden[l] (host array of device pointers, same shapes as
+ *                     mlp.w[l]), d_bias [Co][No] (may be NULL).  All outputs are overwritten.
+ * The descriptor holds device pointers to the mesh, the pair tables (from qc_search_* / qc_pairs_to_csr / qc_csc_*)
+ * and the filter weights; nothing in it is modified.  `ws` (qc_layer_workspace_bytes) is caller-owned scratch that
+ * ALSO carries the saved activations: qc_layer_backward must get the workspace of the matching qc_layer_forward
+ * call, untouched.  Last hidden width H <= 32 (QC_EUNSUP otherwise).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int d, Ni, No, Ci, Co, H;           /* spatial dim, points, channels, last hidden width (= mlp.dims[n_hidden]) */
+    int64_t P;                          /* number of pairs (rows of eval_indices) */
+    const float* out_pts;               /* [No][d] */
+    const float* in_pts;                /* [Ni][d] */
+    const float* quad_w;                /* [Ni] quadrature weights (MeshHandler.weights()), NULL = ones */
+    qc_mlp_t mlp;                       /* hidden layers of the filter MLP (filter.{0,2,..}.weight) */
+    const float* w_last;                /* [Ci*Co][H] last Linear (filter.{2L}.weight) */
+    const float* bias;                  /* [Co][No] or NULL */
+    const int *pair_row, *pair_col;     /* [P] */
+    const int *row_ptr;                 /* [No+1] */
+    const int *csc_ptr, *csc_pair, *csc_row;   /* [Ni+1], [P], [P] */
+    const int *order_out, *order_in;    /* processing orders or NULL */
+} qc_layer_t;
+
+size_t qc_layer_workspace_bytes(const qc_layer_t* layer, int B);
+int qc_layer_forward(const qc_layer_t* layer, const float* features, int B, float* out, void* ws, size_t ws_bytes,
+                     void* stream);
+int qc_layer_backward(const qc_layer_t* layer, const float* grad_out, int B, float* d_features, float* d_quad_w,
+                      float* d_w_last, float* const* d_hidden, float* d_bias, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K5/K6  Mesh_MaxPool.  Replaces scatter_reduce_(amax, include_self=False) (mesh_pool.py:88-89)
  * and gather (mesh_pool.py:93) and their autograd.  Groups are given as CSR over the fine points:
  * grp_ptr[Nout+1], grp_mem[Nin] (members of each group).  Empty groups produce 0 like the

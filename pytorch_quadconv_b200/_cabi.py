@@ -25,6 +25,18 @@ class QcMlp(ctypes.Structure):
                 ("operand_bf16", c_int)]
 
 
+class QcLayer(ctypes.Structure):
+    """qc_layer_t"""
+    _fields_ = [("d", c_int), ("Ni", c_int), ("No", c_int), ("Ci", c_int), ("Co", c_int), ("H", c_int),
+                ("P", c_int64),
+                ("out_pts", c_void_p), ("in_pts", c_void_p), ("quad_w", c_void_p),
+                ("mlp", QcMlp),
+                ("w_last", c_void_p), ("bias", c_void_p),
+                ("pair_row", c_void_p), ("pair_col", c_void_p), ("row_ptr", c_void_p),
+                ("csc_ptr", c_void_p), ("csc_pair", c_void_p), ("csc_row", c_void_p),
+                ("order_out", c_void_p), ("order_in", c_void_p)]
+
+
 _SIGNATURES = {
     "qc_version": (c_int, []),
     "qc_search_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
@@ -81,6 +93,10 @@ _SIGNATURES = {
     "qc_dphi_mma_smem_bytes": (c_int, [c_int, c_int, c_int, c_int]),
     "qc_dphi_mma": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                             c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "qc_layer_workspace_bytes": (c_size_t, [ctypes.POINTER(QcLayer), c_int]),
+    "qc_layer_forward": (c_int, [ctypes.POINTER(QcLayer), c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "qc_layer_backward": (c_int, [ctypes.POINTER(QcLayer), c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                  ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_size_t, c_void_p]),
     "qc_tc_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "qc_tc_selftest_ss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "qc_tc_probe_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

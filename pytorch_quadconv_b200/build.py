@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libquadconv_b200.so")
-SOURCES = ["search.cu", "pack.cu", "pair_mlp.cu", "contract.cu", "contract_fast.cu", "contract_tc.cu", "contract_mma.cu", "dphi_mma.cu", "contract_wide.cu", "gemm_tc.cu", "tc_selftest.cu", "weight_map.cu", "pool.cu"]
+SOURCES = ["search.cu", "pack.cu", "pair_mlp.cu", "contract.cu", "contract_fast.cu", "contract_tc.cu", "contract_mma.cu", "dphi_mma.cu", "contract_wide.cu", "gemm_tc.cu", "tc_selftest.cu", "weight_map.cu", "pool.cu", "layer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 

@@ -64,3 +64,67 @@ def test_tcgen05_bf16_operand_majorness(cuda_lib):
         C.check(cuda_lib.qc_tc_probe_bf16(C.ptr(A), C.ptr(B), C.ptr(D), mode, C.stream()), "qc_tc_probe_bf16")
         torch.cuda.synchronize()
         assert float((D.double() - ref).norm() / ref.norm()) < 1e-6, mode
+
+
+def test_single_call_layer_entry_points(cuda_lib):
+    """qc_layer_forward / qc_layer_backward: the whole layer through two C calls on [B,C,N] tensors with a
+    caller-owned workspace -- no ops.py composition -- against the float64 oracle (1e-5) for the output and every
+    gradient.  The pair tables come from the search entry points, as a non-Python host would build them."""
+    import ctypes
+    import numpy as np
+    from conftest import relerr
+    from oracle import quadconv_oracle as O
+    from pytorch_quadconv_b200 import _cabi as C, ops
+    L = C.lib()
+    g = torch.Generator().manual_seed(2024)
+    d, n, ci, co, B, fs, r = 2, 700, 6, 10, 5, [8, 8], 0.1
+    pts = torch.rand(n, d, generator=g)
+    x = torch.randn(B, ci, n, generator=g)
+    qw = torch.rand(n, generator=g) + 0.5
+    dims = [d] + fs + [ci * co]
+    ws_ = [torch.randn(dims[l + 1], dims[l], generator=g) / np.sqrt(dims[l]) for l in range(len(dims) - 1)]
+    bias = torch.randn(co, n, generator=g)
+    go = torch.randn(B, co, n, generator=g)
+    dev = "cuda"
+    res = [t for t in ops.build_pairs(pts.to(dev), pts.to(dev), r, True)]      # tables only (search kernels)
+    ev, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = res[:9]
+    dp = [t.to(dev).contiguous() for t in (pts, x, qw, bias, go)]
+    wd = [w.to(dev).contiguous() for w in ws_]
+    desc = C.QcLayer()
+    desc.d, desc.Ni, desc.No, desc.Ci, desc.Co, desc.H, desc.P = d, n, n, ci, co, fs[-1], ev.shape[0]
+    desc.out_pts = desc.in_pts = C.ptr(dp[0])
+    desc.quad_w = C.ptr(dp[2])
+    desc.mlp = C.make_mlp(d, wd[:-1])
+    desc.w_last, desc.bias = C.ptr(wd[-1]), C.ptr(dp[3])
+    for k, t in (("pair_row", pair_row), ("pair_col", pair_col), ("row_ptr", row_ptr), ("csc_ptr", csc_ptr),
+                 ("csc_pair", csc_pair), ("csc_row", csc_row), ("order_out", order_out), ("order_in", order_in)):
+        setattr(desc, k, C.ptr(t.contiguous()))
+    wsb = L.qc_layer_workspace_bytes(ctypes.byref(desc), B)
+    assert wsb > 0
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    out = torch.empty(B, co, n, device=dev)
+    st = C.stream()
+    assert L.qc_layer_forward(ctypes.byref(desc), C.ptr(dp[1]), B, C.ptr(out), C.ptr(ws), wsb - 1, st) == -3   # QC_EWORKSPACE
+    C.check(L.qc_layer_forward(ctypes.byref(desc), C.ptr(dp[1]), B, C.ptr(out), C.ptr(ws), wsb, st), "qc_layer_forward")
+    dx = torch.empty_like(dp[1])
+    dqw = torch.empty(n, device=dev)
+    dwl = torch.empty_like(wd[-1])
+    dhid = [torch.empty_like(w) for w in wd[:-1]]
+    dbias = torch.empty(co, n, device=dev)
+    dptrs = (ctypes.c_void_p * len(dhid))(*[C.ptr(t) for t in dhid])
+    C.check(L.qc_layer_backward(ctypes.byref(desc), C.ptr(dp[4]), B, C.ptr(dx), C.ptr(dqw), C.ptr(dwl), dptrs, C.ptr(dbias),
+                                C.ptr(ws), wsb, st), "qc_layer_backward")
+    torch.cuda.synchronize()
+    # float64 oracle of the reference formulas
+    x64, qw64 = x.double().requires_grad_(), qw.double().requires_grad_()
+    w64 = [w.double().requires_grad_() for w in ws_]
+    b64 = bias.double().unsqueeze(0).requires_grad_()
+    y64 = O.quadconv_forward(pts, pts, qw64, w64, x64, ev.cpu(), ci, co, b64)
+    (y64 * go.double()).sum().backward()
+    assert relerr(out.cpu().numpy(), y64.detach().numpy()) < 1e-5
+    assert relerr(dx.cpu().numpy(), x64.grad.numpy()) < 1e-5
+    assert relerr(dqw.cpu().numpy(), qw64.grad.numpy()) < 1e-5
+    assert relerr(dwl.cpu().numpy(), w64[-1].grad.numpy()) < 1e-5
+    for a_, b_ in zip(dhid, w64[:-1]):
+        assert relerr(a_.cpu().numpy(), b_.grad.numpy()) < 1e-5
+    assert relerr(dbias.cpu().numpy(), b64.grad[0].numpy()) < 1e-5
