@@ -351,32 +351,19 @@ def run_ours(args, w, rank, local_rank, world, dev, sub=False, tc_table=False):
     P = layer.pairs() if is_ae else int(layer._tables[0].numel())
 
     if args.graph:
-        x_static = x.detach().clone().requires_grad_(x.requires_grad)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                step(x_static)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        g_compute = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_compute):
-            loss_static = compute(x_static)
-        g_update = None
-        if update is not None:
-            g_update = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_update):
-                update()
+        # compute piece and update piece replayed from CUDA graphs (pytorch_quadconv_b200.graphed), the collective between them
+        from pytorch_quadconv_b200 import graphed
+        g_compute = graphed(compute, x, warmup=3)
+        x_static = g_compute.static_inputs[0]
+        g_update = graphed(update, warmup=1) if update is not None else None
 
         def step(xin):
-            if xin is not x_static:
-                x_static.data.copy_(xin.detach(), non_blocking=True)
-            g_compute.replay()
+            loss = g_compute(xin)
             if world > 1:
                 reducer.reduce()
             if g_update is not None:
-                g_update.replay()
-            return loss_static
+                g_update()
+            return loss
         x = x_static
 
     # ---- device-resident timing --------------------------------------------------------------

@@ -10,5 +10,6 @@ Python module names cannot contain '-'.)
 from .quadconv import QuadConv
 from .mesh_pool import Mesh_MaxPool, MeshMaxPool
 from .mesh_handler import MeshHandler
+from .graphs import graphed
 
-__all__ = ["QuadConv", "Mesh_MaxPool", "MeshMaxPool", "MeshHandler"]
+__all__ = ["QuadConv", "Mesh_MaxPool", "MeshMaxPool", "MeshHandler", "graphed"]
