@@ -572,11 +572,15 @@ def main():
                     help="capture the step in a CUDA graph and replay it (small meshes are launch-latency bound)")
     ap.add_argument("--no-tc", action="store_true", help="skip the bf16 tensor-core-mode sub-record of the default (c3) line")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 sub-record that rides on the default (c3) line")
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's batch size (profiling aid)")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel timing table (json) here")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     w = workload(args.workload)
+    if args.batch:
+        w["B"] = args.batch
+        w["name"] += f" [batch overridden: {args.batch}]"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -283,7 +283,8 @@ int qc_weight_map_bwd(const float* pts, const int* adj, int M, int E, int d, con
  * ------------------------------------------------------------------------------------------ */
 int qc_mma_chunk_channels(int C, int B);          /* 0: batch lanes < 8, not served */
 int qc_mma_smem_bytes(int Cs, int Cd, int B, int max_ku);
-int qc_pack_features_bf16(const float* x /*[B][C][N]*/, int B, int C, int N, int CC, void* xh, void* stream);
+int qc_pack_features_bf16(const void* x /*[B][C][N] fp32, or bf16 when src_bf16 != 0*/, int src_bf16, int B, int C, int N,
+                          int CC, void* xh, void* stream);
 int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const void* tile_ent, const int* tile_pptr, const int* tile_uptr,
                     const int* union_idx, int ntiles, int max_ku, const float* phi, int H, int HPphi,
                     const float* w_last, int Cd, int transposed, const int* order, int Ndst, int B, float* Yp,

@@ -676,7 +676,13 @@ __global__ void k_dw_mma_reduce(const float* __restrict__ part, int ncta, int ng
 // padded shared-memory tile; 128-byte row pieces on the [B,C,N] side, CC*2-byte pieces, 2*NC contiguous bytes per
 // point, on the packed side.
 constexpr int PTB = 64, RSB = 65;
-__global__ void __launch_bounds__(256) k_pack_bf16(const float* __restrict__ x, int B, int C, int N, int Bp, int CC,
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// TIn = float (the module's fp32 features / grad_out) or __nv_bfloat16 (features handed over in bf16: half the
+// host-to-device and HBM read traffic; the values are the ones the tensor cores would see anyway)
+template <typename TIn>
+__global__ void __launch_bounds__(256) k_pack_bf16(const TIn* __restrict__ x, int B, int C, int N, int Bp, int CC,
                                                    __nv_bfloat16* __restrict__ xp)
 {
     __shared__ float tile[128 * RSB];      // [(channel in chunk) * Bp + batch lane][point]
@@ -690,7 +696,7 @@ __global__ void __launch_bounds__(256) k_pack_bf16(const float* __restrict__ x, 
         for (int half = 0; half < 2; ++half) {
             const int n = n0 + half * 32 + lane;
             float v = 0.f;
-            if (ch < C && b < B && n < N) v = x[((size_t)b * C + ch) * N + n];
+            if (ch < C && b < B && n < N) v = to_f32(x[((size_t)b * C + ch) * N + n]);
             tile[r * RSB + half * 32 + lane] = v;
         }
     }
@@ -721,12 +727,16 @@ int qc_mma_chunk_channels(int Cs, int B)
     return cc;
 }
 
-int qc_pack_features_bf16(const float* x, int B, int C, int N, int CC, void* xp, void* stream)
+int qc_pack_features_bf16(const void* x, int src_bf16, int B, int C, int N, int CC, void* xp, void* stream)
 {
     const int Bp = qc_bp(B);
     if (B <= 0 || C <= 0 || N <= 0 || (CC != 4 && CC != 8 && CC != 16) || Bp * CC > 128) return QC_EINVAL;
     dim3 grid(qc_ceil_div(N, PTB), qc_ceil_div(C, CC), qc_nblk(B));
-    k_pack_bf16<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, C, N, Bp, CC, reinterpret_cast<__nv_bfloat16*>(xp));
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(xp);
+    if (src_bf16)
+        k_pack_bf16<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), B, C, N, Bp, CC, out);
+    else
+        k_pack_bf16<float><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(x), B, C, N, Bp, CC, out);
     QC_CHECK_LAUNCH();
     return 0;
 }

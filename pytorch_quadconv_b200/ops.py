@@ -378,10 +378,15 @@ def tc_backward_supported(Ci: int, Co: int, H: int, B: int, max_ku_fwd: int, max
 
 
 def _pack_bf16(x: Tensor) -> Tensor:
+    """[B,C,N] fp32 or bf16 -> bf16 packed [nblk][N][chunks][Bp][CC] (operand layout of the tensor-core kernels)."""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"features must be float32 or bfloat16 (got {x.dtype})")
+    x = x.contiguous()
     B, Cc, N = x.shape
     CC = C.lib().qc_mma_chunk_channels(Cc, B)
     xh = torch.empty((_nblk(B), N, (Cc + CC - 1) // CC, _bp(B), CC), dtype=torch.bfloat16, device=x.device)
-    C.check(C.lib().qc_pack_features_bf16(C.ptr(x), B, Cc, N, CC, C.ptr(xh), C.stream()), "qc_pack_features_bf16")
+    C.check(C.lib().qc_pack_features_bf16(C.ptr(x), int(x.dtype == torch.bfloat16), B, Cc, N, CC, C.ptr(xh), C.stream()),
+            "qc_pack_features_bf16")
     return xh
 
 
@@ -394,8 +399,9 @@ def qc_forward_tc(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Ten
                   in_channels: int, out_channels: int) -> Tuple[Tensor, Tensor, Tensor]:
     """Forward of the reduced-precision mode: per-pair hidden layers in fp32 (qc_pair_phi_fwd), then both
     contraction stages on the tensor cores with bf16 operands (qc_contract_mma).  Returns (out, phi, bf16
-    packed features)."""
-    features = _f32c(features, "features")
+    packed features).  `features` may already be bfloat16 (half the host-to-device / HBM read traffic)."""
+    if features.dtype != torch.bfloat16:
+        features = _f32c(features, "features")
     out_pts, in_pts, quad_w = _f32c(out_pts, "points"), _f32c(in_pts, "points"), _f32c(quad_w, "weights")
     hidden_ws = [_f32c(w, "filter weight") for w in hidden_ws]
     w_last = _f32c(w_last, "filter weight")
