@@ -186,6 +186,28 @@ def _(eval_indices, n_out, n_in):
 # fused QuadConv layer
 # ---------------------------------------------------------------------------------------------
 
+def _flat_layout(shapes):
+    """Offsets of tensors of the given shapes inside one flat fp32 buffer (16-byte aligned pieces)."""
+    sizes = [int(np.prod(sh)) if len(sh) else 1 for sh in shapes]
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + 3) & ~3
+    return offs, sizes, max(total, 1)
+
+
+def _carve(flat: Tensor, shapes):
+    """Views of `flat` with the given shapes (see _flat_layout).  Custom ops may not return tensors that alias one
+    another, so the ops below return the ONE zero-filled buffer their kernels accumulated into (one fill launch
+    instead of one per gradient) and the autograd glue carves it."""
+    offs, sizes, _ = _flat_layout(shapes)
+    return [flat[o:o + n].view(sh) for o, n, sh in zip(offs, sizes, shapes)]
+
+
+def _grad_shapes(hidden_ws, Ni, Ci, Co, H):
+    return [tuple(w.shape) for w in hidden_ws] + [(Ni,), (Ci * Co, H)]
+
+
 def _pack(x: Tensor) -> Tensor:
     B, Cc, N = x.shape
     xp = torch.empty(_packed_shape(B, Cc, N), dtype=torch.float32, device=x.device)
@@ -450,7 +472,7 @@ def qc_backward_tc(grad_out: Tensor, xh: Tensor, phi: Tensor, out_pts: Tensor, i
     """Backward of the reduced-precision mode, all three contractions on the tensor cores (bf16 operands, fp32
     accumulation): d(phi) (qc_dphi_mma), d W_last (qc_dw_mma), d features (qc_contract_mma on the CSC view); the
     per-pair chain rule through the hidden layers stays fp32 (qc_pair_phi_bwd).
-    Returns [d_features, d_quad_w, d_w_last, d_bias (or empty), *d_hidden_ws]."""
+    Returns [d_features, d_bias (or empty), flat] -- flat holds d_hidden_ws..., d_quad_w, d_w_last (_grad_shapes)."""
     import ctypes
     grad_out = _f32c(grad_out, "grad_out")
     hidden_ws = [_f32c(w, "filter weight") for w in hidden_ws]
@@ -474,14 +496,14 @@ def qc_backward_tc(grad_out: Tensor, xh: Tensor, phi: Tensor, out_pts: Tensor, i
     dphi = (torch.zeros if _nblk(B) > 1 else torch.empty)((1, max(P, 1), HP), **f32)
     C.check(L.qc_dphi_mma(C.ptr(xh), Ni, Ci, C.ptr(gh), Co, C.ptr(f_ent), C.ptr(f_pptr), C.ptr(f_uptr), C.ptr(f_uidx), nft,
                           f_max_ku, C.ptr(w_last), H, HP, C.ptr(order_out), No, B, C.ptr(dphi), st), "qc_dphi_mma")
-    d_hidden = [torch.zeros_like(w) for w in hidden_ws]
-    d_quad_w = torch.zeros(Ni, **f32)
+    shapes = _grad_shapes(hidden_ws, Ni, Ci, Co, H)
+    flat = torch.zeros(_flat_layout(shapes)[2], **f32)
+    *d_hidden, d_quad_w, d_w_last = _carve(flat, shapes)
     mlp = C.make_mlp(d, hidden_ws, False)
     dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
     C.check(L.qc_pair_phi_bwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row), C.ptr(pair_col),
                               P, d, mlp, HP, C.ptr(dphi), 1, dptrs, C.ptr(d_quad_w), st), "qc_pair_phi_bwd")
     # d W_last (same tiles, the stage-B result recomputed and contracted with the grad rows)
-    d_w_last = torch.empty((Ci * Co, H), **f32)
     wsb = L.qc_dw_mma_workspace_bytes(Ci, Co, B)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     C.check(L.qc_dw_mma(C.ptr(xh), Ni, Ci, C.ptr(gh), Co, C.ptr(f_ent), C.ptr(f_pptr), C.ptr(f_uptr), C.ptr(f_uidx), nft,
@@ -492,7 +514,7 @@ def qc_backward_tc(grad_out: Tensor, xh: Tensor, phi: Tensor, out_pts: Tensor, i
                               C.ptr(phi), H, HP, C.ptr(w_last), Ci, 1, C.ptr(order_in), Ni, B, C.ptr(dxp), st),
             "qc_contract_mma (d features)")
     d_features = _unpack(dxp, B, Ci, Ni, None)
-    return [d_features, d_quad_w, d_w_last, d_bias] + d_hidden
+    return [d_features, d_bias, flat]
 
 
 @qc_backward_tc.register_fake
@@ -501,8 +523,8 @@ def _(grad_out, xh, phi, out_pts, in_pts, quad_w, hidden_ws, w_last, pair_row, p
       out_channels, has_bias):
     Ni, No = in_pts.shape[0], out_pts.shape[0]
     e = grad_out.new_empty
-    return [e((batch, in_channels, Ni)), e(Ni), e(w_last.shape),
-            e((1, out_channels, No)) if has_bias else e(0)] + [e(w.shape) for w in hidden_ws]
+    shapes = _grad_shapes(hidden_ws, Ni, in_channels, out_channels, w_last.shape[1])
+    return [e((batch, in_channels, Ni)), e((1, out_channels, No)) if has_bias else e(0), e(_flat_layout(shapes)[2])]
 
 
 @qc_forward.register_fake
@@ -522,7 +544,7 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
                 row_ptr: Tensor, csc_ptr: Tensor, csc_pair: Tensor, csc_row: Tensor,
                 order_out: Optional[Tensor], order_in: Optional[Tensor], batch: int, in_channels: int,
                 out_channels: int, has_bias: bool, mlp_bf16: bool = False) -> List[Tensor]:
-    """Returns [d_features, d_quad_w, d_w_last, d_bias (or empty), *d_hidden_ws]."""
+    """Returns [d_features, d_bias (or empty), flat] -- flat holds d_hidden_ws..., d_quad_w, d_w_last (_grad_shapes)."""
     grad_out = _f32c(grad_out, "grad_out")
     hidden_ws = [_f32c(w, "filter weight") for w in hidden_ws]
     w_last = _f32c(w_last, "filter weight")
@@ -573,7 +595,11 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
             x = _unpack(xp, B, Ci, Ni, None)
             dWt = torch.matmul(x.permute(1, 0, 2).reshape(Ci, B * Ni), Tp.reshape(B * Ni, Co * H))   # [i, (j,h)]
             d_w_last = dWt.reshape(Ci * Co, H)
-        return [d_features, d_quad_w, d_w_last, d_bias] + d_hidden
+        shapes = _grad_shapes(hidden_ws, Ni, Ci, Co, H)
+        flat = torch.empty(_flat_layout(shapes)[2], **f32)
+        for dst, src in zip(_carve(flat, shapes), d_hidden + [d_quad_w, d_w_last]):
+            dst.copy_(src)
+        return [d_features, d_bias, flat]
 
     # d phi (grouped by out point), then back through the hidden layers per pair
     W3 = torch.empty((Co, Ci, HP), **f32)
@@ -582,8 +608,11 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
     dphi = torch.empty((nsl, max(P, 1), HP), **f32)
     C.check(L.qc_dphi(C.ptr(xp), Ni, Ci, C.ptr(gp), Co, C.ptr(row_ptr), C.ptr(pair_col), C.ptr(W3), H, HP,
                       C.ptr(order_out), No, B, P, C.ptr(dphi), st), "qc_dphi")
-    d_hidden = [torch.zeros_like(w) for w in hidden_ws]
-    d_quad_w = torch.zeros(Ni, **f32)
+    # every accumulated output of this step lives in ONE zero-filled buffer (one fill launch instead of five)
+    CiP = (Ci + 3) & ~3
+    shapes = _grad_shapes(hidden_ws, Ni, Ci, Co, H) + [(Co * H, CiP)]
+    flat = torch.zeros(_flat_layout(shapes)[2], **f32)
+    *d_hidden, d_quad_w, d_w_last, dW2 = _carve(flat, shapes)
     mlp = C.make_mlp(d, hidden_ws, mlp_bf16)
     import ctypes
     dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
@@ -591,10 +620,8 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
                               P, d, mlp, HP, C.ptr(dphi), nsl, dptrs, C.ptr(d_quad_w), st), "qc_pair_phi_bwd")
 
     # d features (grouped by in point through the CSC tables) + d W_last in the same pass
-    CiP = (Ci + 3) & ~3
     W2t = torch.empty((Co * H, CiP), **f32)
     C.check(L.qc_repack_wlast(C.ptr(w_last), Ci, Co, H, HP, 1, C.ptr(W2t), st), "qc_repack_wlast")
-    dW2 = torch.zeros((Co * H, CiP), **f32)
     dxp = torch.empty(_packed_shape(B, Ci, Ni), **f32)
     ws_bytes = L.qc_contract_workspace_bytes(Co, H, HP, Ci, Ni, B)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
@@ -602,10 +629,9 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
                           C.ptr(W2t), Ci, C.ptr(order_in), Ni, B, C.ptr(dxp), C.ptr(xp), C.ptr(dW2),
                           C.ptr(ws), ws_bytes, st),
             "qc_contract (backward)")
-    d_w_last = torch.zeros((Ci * Co, H), **f32)
     C.check(L.qc_unpack_dwlast(C.ptr(dW2), Ci, Co, H, C.ptr(d_w_last), st), "qc_unpack_dwlast")
     d_features = _unpack(dxp, B, Ci, Ni, None)
-    return [d_features, d_quad_w, d_w_last, d_bias] + d_hidden
+    return [d_features, d_bias, flat]
 
 
 @qc_backward.register_fake
@@ -613,8 +639,10 @@ def _(grad_out, xp, phi, out_pts, in_pts, quad_w, hidden_ws, w_last, pair_row, p
       csc_pair, csc_row, order_out, order_in, batch, in_channels, out_channels, has_bias, mlp_bf16=False):
     Ni, No = in_pts.shape[0], out_pts.shape[0]
     e = grad_out.new_empty
-    return [e((batch, in_channels, Ni)), e(Ni), e(w_last.shape),
-            e((1, out_channels, No)) if has_bias else e(0)] + [e(w.shape) for w in hidden_ws]
+    H = w_last.shape[1]
+    CiP = (in_channels + 3) & ~3
+    shapes = _grad_shapes(hidden_ws, Ni, in_channels, out_channels, H) + [(out_channels * H, CiP)]
+    return [e((batch, in_channels, Ni)), e((1, out_channels, No)) if has_bias else e(0), e(_flat_layout(shapes)[2])]
 
 
 class _QuadConvFn(torch.autograd.Function):
@@ -648,14 +676,18 @@ class _QuadConvFn(torch.autograd.Function):
             tc = ctx.tc
             res = qc_backward_tc(grad_out, xp, phi, out_pts, in_pts, quad_w, list(hidden_ws), w_last, pair_row, pair_col,
                                  tc["order_out"], tc["order_in"], *tc["fwd"], *tc["bwd"], B, Ci, Co, has_bias)
-            return (res[0], res[1], res[2], res[3] if has_bias else None, None, None, *res[4:])
+            return _QuadConvFn._unpack_grads(res, hidden_ws, in_pts.shape[0], Ci, Co, w_last.shape[1], has_bias)
         if ctx.tc is not None:
             with torch.cuda.device(xp.device):
                 xp = _pack(_f32c(xp, "features"))
         res = qc_backward(grad_out, xp, phi, out_pts, in_pts, quad_w, list(hidden_ws), w_last, pair_row, pair_col,
                           row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in, B, Ci, Co, has_bias, mlp_bf16)
-        d_features, d_quad_w, d_w_last, d_bias = res[:4]
-        d_hidden = res[4:]
+        return _QuadConvFn._unpack_grads(res, hidden_ws, in_pts.shape[0], Ci, Co, w_last.shape[1], has_bias)
+
+    @staticmethod
+    def _unpack_grads(res, hidden_ws, Ni, Ci, Co, H, has_bias):
+        d_features, d_bias, flat = res
+        *d_hidden, d_quad_w, d_w_last = _carve(flat, _grad_shapes(hidden_ws, Ni, Ci, Co, H))
         return (d_features, d_quad_w, d_w_last, d_bias if has_bias else None, None, None, *d_hidden)
 
 
@@ -697,20 +729,22 @@ def _(points, adj32, inc_ptr, inc_idx, params):
 
 @torch.library.custom_op("quadconv_b200::weight_map_bwd", mutates_args=())
 @_on_device
-def weight_map_bwd(grad_w: Tensor, points: Tensor, adj32: Tensor, params: Sequence[Tensor]) -> List[Tensor]:
+def weight_map_bwd(grad_w: Tensor, points: Tensor, adj32: Tensor, params: Sequence[Tensor]) -> Tensor:
     grad_w = _f32c(grad_w, "grad")
     points = _f32c(points, "points")
     params = [_f32c(p, "weight-network parameter") for p in params]
     M, E = adj32.shape
-    grads = [torch.zeros_like(p) for p in params]
+    shapes = [tuple(p.shape) for p in params]
+    flat = torch.zeros(_flat_layout(shapes)[2], dtype=torch.float32, device=grad_w.device)
+    grads = _carve(flat, shapes)
     C.check(C.lib().qc_weight_map_bwd(C.ptr(points), C.ptr(adj32), M, E, points.shape[1], _ptr_array(params),
                                       C.ptr(grad_w), _ptr_array(grads), C.stream()), "qc_weight_map_bwd")
-    return grads
+    return flat
 
 
 @weight_map_bwd.register_fake
 def _(grad_w, points, adj32, params):
-    return [torch.empty_like(p) for p in params]
+    return grad_w.new_empty(_flat_layout([tuple(p.shape) for p in params])[2])
 
 
 class _WeightMapFn(torch.autograd.Function):
@@ -722,8 +756,8 @@ class _WeightMapFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_w):
         points, adj32, *params = ctx.saved_tensors
-        grads = weight_map_bwd(grad_w, points, adj32, list(params))
-        return (None, None, None, None, *grads)
+        flat = weight_map_bwd(grad_w, points, adj32, list(params))
+        return (None, None, None, None, *_carve(flat, [tuple(p.shape) for p in params]))
 
 
 def weight_map_apply(points, adj32, inc_ptr, inc_idx, params):

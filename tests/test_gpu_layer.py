@@ -449,7 +449,7 @@ def test_graphed_step_matches_eager(cuda_lib):
     x0 = torch.from_numpy(L["x"]).cuda()
     gstep = q.graphed(step, x0)
     x1 = torch.randn_like(x0)
-    y_g = gstep(x1).clone()
+    y_g = gstep(x1).detach().clone()
     grads_g = [p.grad.clone() for p in params]
     y_e = step(x1)
     assert relerr(y_g.cpu().numpy(), y_e.detach().cpu().numpy()) < 1e-6
