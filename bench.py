@@ -185,6 +185,28 @@ class ClockSampler:
 # our arm
 # --------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(dev):
+    """Pin this rank's threads to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are
+    allocated (first touch then places them on that node): at 8 ranks the end-to-end arm moves 8 x 410 MB of pinned
+    fp32 per step through one host, and remote-node pages halve the achievable H2D rate.  Returns the node or None."""
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read().strip())
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def build_problem(w, dev, cache=True, filter_dtype=torch.float32, compute_dtype=torch.float32):
     import pytorch_quadconv_b200 as q
     torch.manual_seed(0)
@@ -543,7 +565,11 @@ def run_ours(args, w, rank, local_rank, world, dev, sub=False, tc_table=False):
                        "compute_dtype": args.compute_dtype},
             "clocks": clk.summary(),
             "e2e": {"value": units / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    # achieved host-to-device rate of THIS rank's input stream (the copies overlap the compute; when
+                    # this approaches the link / host-memory rate the end-to-end step is input bound, as at 8 ranks)
+                    "h2d_gbs_per_rank": h2d / (e2e_ms * 1e-3) / 1e9, "numa_node": getattr(args, "numa_node", None),
+                    "returns": "loss + every parameter gradient (a training step); y and d_features stay on the device"},
             "gpu_launches": launches * args.steps,
             "roofline": roof, "cpu_baseline": cb, "kernels_ms": table,
         }
@@ -607,6 +633,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from pytorch_quadconv_b200 import _cabi  # fails loudly if the .so is missing
     _cabi.lib()
+    args.numa_node = bind_to_gpu_numa_node(dev) if world > 1 else None
 
     line = run_ours(args, w, rank, local_rank, world, dev)
     if args.workload == "c3" and args.compute_dtype == "f32" and not args.no_tc:

@@ -311,6 +311,14 @@ int qc_dphi_mma(const void* Xh, int Nsrc, int Cs, const void* Gh, int Cg, const 
                 const int* tile_uptr, const int* union_idx, int ntiles, int max_ku, const float* w_last, int H, int HPphi,
                 const int* order, int Ndst, int B, float* dphi, void* stream);
 
+/* Producer variant of the union-row gather in qc_contract_mma / qc_dw_mma / qc_dphi_mma (bit mask; default 4 = per-lane
+ * cp.async copies into 128-byte-swizzled rows; 12 = the same layout filled by TMA: cp.async.bulk.tensor.2d tile::gather4,
+ * four rows per instruction through a tensor map over the packed features -- measured 2.4x slower at C3, 128-byte boxes
+ * are too small for the copy engine, so it is opt-in).  Also read once from QC_MMA_VAR.  set returns the previous value;
+ * a negative argument only queries. */
+int qc_mma_get_variant(void);
+int qc_mma_set_variant(int var);
+
 /* Known-answer self test of the tcgen05 building blocks (TMEM alloc, tcgen05.st/ld, kind::tf32 MMA with
  * A in TMEM and B through a K-major shared-memory descriptor, 3xTF32 split):
  * D[128][32] = A[128][64] * B[32][64]^T.  Used by tests only. */

@@ -26,8 +26,10 @@
 // All hand-offs are mbarriers; the MMAs of channel chunk c+1 run while chunk c is regrouped.
 #include <cuda_bf16.h>
 #include <cstdio>
+#include <cstring>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -100,7 +102,7 @@ __host__ __device__ constexpr size_t mma_smem_bytes(int CC, int Bp, int nch, int
 // chunks side by side in the regroup tile; the accumulators stay in TMEM for the whole kernel (one per chunk group) and
 // every CTA writes its partial sums once at the end.
 template <int CC, int LB, int VAR, bool DW>
-__global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
+__global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a, const __grid_constant__ CUtensorMap xmap)
 {
     constexpr int Bp = 1 << LB, NC = Bp * CC, QN = NC / 8;
     // (one channel chunk per accumulator: pairing two 32-value chunks into one M = 64 operand would need both halves of
@@ -112,6 +114,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     // 16-byte chunks XOR-ed with the row index inside 1 KB atoms): a 128-byte line from L2 lands as ONE shared-memory
     // wavefront (the no-swizzle layouts scatter it into eight 16-byte pieces, 6x the LSU data-pipe traffic, ncu)
     constexpr bool SW = (VAR & 4) != 0 && (NC % 64 == 0);
+    // bit 3: the union rows arrive by TMA (tma.cuh): one gather4 instruction per four rows and 64-column block, issued
+    // by the lanes of ONE producer warp, completion counted in bytes on the stage's mbarrier; padding slots name a row
+    // past the end of the tensor and are zero-filled by the copy unit.  xmap: X as [nblk * Nsrc][nch * NC] bf16.
+    constexpr bool TMA = SW && (VAR & 8) != 0;
     constexpr uint32_t XSB = ROWMAJ ? 144 : 128;          // bytes between 8-column chunks of the gathered operand
     constexpr int rows = TP * Bp, MBC = rows / 128;       // rows of the stage-C GEMM per tile, its 128-row blocks
     constexpr uint32_t ACR = ac_row8(CC * CPP, Bp);
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     // ---- one-time setup ---------------------------------------------------------------------------------
     if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
     if (tid == 32) {
-        for (int i = 0; i < NST; ++i) tc::mbar_init(&x_full[i], 128), tc::mbar_init(&x_empty[i], 1);
+        for (int i = 0; i < NST; ++i) tc::mbar_init(&x_full[i], TMA ? 1 : 128), tc::mbar_init(&x_empty[i], 1);
         for (int i = 0; i < 2; ++i) tc::mbar_init(&d_full[i], 1), tc::mbar_init(&d_empty[i], 8);
         tc::mbar_init(&ac_full[0], 8), tc::mbar_init(&ac_full[1], 8), tc::mbar_init(ac_empty, 1);
         tc::mbar_init(phi_full, 4), tc::mbar_init(phi_empty, 1);
@@ -235,14 +241,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             int nst_next = 0, blk_next = 0;
             tc::named_bar_sync(2, 128);
             const uint32_t rowbytes = (uint32_t)(nch * NC * 2);
-            auto row_off = [&](int u) { return u >= 0 ? (int)((uint32_t)u * rowbytes) : -1; };   // (< 4 GB: checked by the host)
+            // cp.async: byte offset of the row inside this batch block (< 4 GB: checked by the host), -1 = padding;
+            // TMA: row index of the 2-D view (batch block included), the row count = out of bounds = zero fill
+            const int oob_row = a.nblk * a.Nsrc;
+            auto row_off = [&](int u, int bk) {
+                if (TMA) return u >= 0 ? bk * a.Nsrc + u : oob_row;
+                return u >= 0 ? (int)((uint32_t)u * rowbytes) : -1;
+            };
             if (tt == 0)
-                for (int i = pt; i < ku; i += 128) uix[i] = row_off(__ldg(a.union_idx + u0 + i));
+                for (int i = pt; i < ku; i += 128) uix[i] = row_off(__ldg(a.union_idx + u0 + i), blk);
             if (has_next) {
                 const int tile2 = wi2 % a.ntiles;
                 const int v0 = a.tile_uptr[tile2], kv = a.tile_uptr[tile2 + 1] - v0;
                 nst_next = kv / KST, blk_next = wi2 / a.ntiles;
-                for (int i = pt; i < kv; i += 128) uix_next[i] = row_off(__ldg(a.union_idx + v0 + i));
+                for (int i = pt; i < kv; i += 128) uix_next[i] = row_off(__ldg(a.union_idx + v0 + i), blk_next);
             }
             tc::named_bar_sync(2, 128);
 
@@ -266,6 +278,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
             auto issue_stage = [&](int c, int st) {
                 const uint32_t s = xit % NST, ph = (xit / NST) & 1;
                 const uint32_t* uo = reinterpret_cast<const uint32_t*>(uix) + st * KST;
+                if constexpr (TMA) {
+                    if (pt < 32) {
+                        constexpr int NI = (KST / 4) * (NC / 64);          // gather4 instructions per stage
+                        const int rg = pt % (KST / 4), b64 = pt / (KST / 4);
+                        int4 r = make_int4(0, 0, 0, 0);
+                        if (pt < NI) r = *reinterpret_cast<const int4*>(uo + rg * 4);
+                        PROF_WAIT(w_xempty, tc::mbar_wait(&x_empty[s], ph ^ 1));
+                        if (pt == 0) tma::mbar_arrive_expect_tx(&x_full[s], STAGE);
+                        __syncwarp();
+                        if (pt < NI)
+                            tma::gather4(x_sa + s * STAGE + b64 * XBLK + rg * 512, &xmap, &x_full[s], c * NC + b64 * 64, r.x, r.y,
+                                         r.z, r.w);
+                    }
+                    ++xit;
+                    return;
+                }
                 if constexpr (SW) {
                     // 8 lanes = the 8 chunks of one 128-byte row piece; line = (block of 64 columns, union row)
                     constexpr int NJ = KST * (NC / 64) / 16;
@@ -637,6 +665,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_contract_mma(const MmaArgs a)
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+// producer variant of the gather (see the VAR bits of k_contract_mma): QC_MMA_VAR read once per process, or set through
+// qc_mma_set_variant (tests compare the TMA producers with the cp.async ones in one process)
+int g_mma_var = -1;
+inline int mma_var()
+{
+    if (g_mma_var < 0) g_mma_var = getenv("QC_MMA_VAR") ? atoi(getenv("QC_MMA_VAR")) : 4;
+    return g_mma_var;
+}
+
 inline int mma_grid(const MmaArgs& a)
 {
     const int grid = min(qc_num_sms(), a.ntiles * a.nblk);
@@ -649,8 +686,14 @@ int launch_mma(const MmaArgs& a, cudaStream_t st)
     const int CdP = max(16, (a.Cd + 15) & ~15);
     const size_t smem = mma_smem_bytes(CC, 1 << LB, a.nch, CdP, a.max_ku, DW, (a.Cg + 15) & ~15);
     if (smem > 227 * 1024) return 0;
+    CUtensorMap xmap;
+    memset(&xmap, 0, sizeof(xmap));
+    if ((VAR & 8) && ((CC << LB) % 64 == 0)) {
+        // X as a 2-D tensor [nblk * Nsrc rows][nch * NC columns] of bf16, boxes of 64 columns (128 bytes) x 1 row
+        if (!tma::make_map_2d(&xmap, a.X, 2, (uint64_t)a.nblk * a.Nsrc, (uint64_t)a.nch * (CC << LB), 64, 1)) return 0;
+    }
     QC_CUDA((qc_set_max_smem<k_contract_mma<CC, LB, VAR, DW>>((int)smem)));
-    k_contract_mma<CC, LB, VAR, DW><<<mma_grid(a), NTHREADS, smem, st>>>(a);
+    k_contract_mma<CC, LB, VAR, DW><<<mma_grid(a), NTHREADS, smem, st>>>(a, xmap);
     QC_CHECK_LAUNCH();
     return 1;
 }
@@ -717,6 +760,15 @@ __global__ void __launch_bounds__(256) k_pack_bf16(const TIn* __restrict__ x, in
 
 extern "C" {
 
+int qc_mma_get_variant(void) { return mma_var(); }
+
+int qc_mma_set_variant(int var)
+{
+    const int old = mma_var();
+    if (var >= 0) g_mma_var = var;
+    return old;
+}
+
 int qc_mma_chunk_channels(int Cs, int B)
 {
     // channels per column chunk: NC = Bp * CC <= 128 columns, CC in {4, 8, 16}
@@ -782,8 +834,14 @@ int qc_contract_mma(const void* Xh, int Nsrc, int Cs, const void* tile_ent, cons
     a.dbg = dbg;
 #endif
     int rc = 0;
-    static const int var = getenv("QC_MMA_VAR") ? atoi(getenv("QC_MMA_VAR")) : 4;
-    if (Bp == 32) rc = var == 2 ? launch_mma<4, 5, 2>(a, st) : (var == 5 ? launch_mma<4, 5, 5>(a, st) : launch_mma<4, 5, 4>(a, st));
+    const int var = mma_var();
+    if (var & 8) {   // union rows by TMA gather4 (falls through to the cp.async producers when the map cannot be made)
+        if (Bp == 32) rc = launch_mma<4, 5, 12>(a, st);
+        else if (Bp == 16) rc = CC == 8 ? launch_mma<8, 4, 12>(a, st) : launch_mma<4, 4, 12>(a, st);
+        else if (Bp == 8 && CC >= 8) rc = CC == 16 ? launch_mma<16, 3, 12>(a, st) : launch_mma<8, 3, 12>(a, st);
+    }
+    if (rc != 0) {
+    } else if (Bp == 32) rc = var == 2 ? launch_mma<4, 5, 2>(a, st) : (var == 5 ? launch_mma<4, 5, 5>(a, st) : launch_mma<4, 5, 4>(a, st));
     else if (Bp == 16) rc = CC == 8 ? launch_mma<8, 4, 4>(a, st) : launch_mma<4, 4, 4>(a, st);
     else if (Bp == 8) rc = CC == 16 ? launch_mma<16, 3, 4>(a, st) : (CC == 8 ? launch_mma<8, 3, 4>(a, st) : launch_mma<4, 3, 2>(a, st));
 #ifdef QC_MMA_PROFILE
@@ -855,7 +913,13 @@ int qc_dw_mma(const void* Xh, int Nsrc, int Cs, const void* Gh, int Cg, const vo
     a.dbg = nullptr;
     const cudaStream_t st = (cudaStream_t)stream;
     int rc = 0;
-    if (Bp == 32) rc = launch_mma<4, 5, 4, true>(a, st);
+    if (mma_var() & 8) {
+        if (Bp == 32) rc = launch_mma<4, 5, 12, true>(a, st);
+        else if (Bp == 16) rc = CC == 8 ? launch_mma<8, 4, 12, true>(a, st) : launch_mma<4, 4, 12, true>(a, st);
+        else if (Bp == 8 && CC >= 8) rc = CC == 16 ? launch_mma<16, 3, 12, true>(a, st) : launch_mma<8, 3, 12, true>(a, st);
+    }
+    if (rc != 0) {
+    } else if (Bp == 32) rc = launch_mma<4, 5, 4, true>(a, st);
     else if (Bp == 16) rc = CC == 8 ? launch_mma<8, 4, 4, true>(a, st) : launch_mma<4, 4, 4, true>(a, st);
     else if (Bp == 8) rc = CC == 16 ? launch_mma<16, 3, 4, true>(a, st) : (CC == 8 ? launch_mma<8, 3, 4, true>(a, st) : launch_mma<4, 3, 2, true>(a, st));
     if (rc == 0) return QC_EUNSUP;

@@ -42,7 +42,13 @@ constexpr int PCH = 64;  // pairs staged per chunk
 // L1, made no measurable difference on its own), depth 2 loses the overlap (+45 %).
 __host__ __device__ constexpr int ctc_ring_depth(bool dw, int kch, int ng) { return (dw ? 8 : (kch == 32 ? 6 : 8)) / ng; }
 __host__ __device__ constexpr int dtc_ring_depth(int ng) { return 8 / ng; }
-constexpr int DW_FLUSH = 8;   // uses of the dW operand buffer between two flushes of the TMEM dW accumulators
+// uses of the dW operand buffer between two flushes of the TMEM dW accumulators (QC_DW_FLUSH overrides): 16 uses = 192
+// accumulating MMAs per chain, measured 4.2e-6 on dW_last at C3 (8 uses: 2.4e-6) against the 1e-5 bound
+inline int dw_flush_interval()
+{
+    static const int v = []() { const char* e = getenv("QC_DW_FLUSH"); const int x = e ? atoi(e) : 16; return x < 1 ? 1 : x; }();
+    return v;
+}
 
 // KCH = K of one channel chunk = channels per chunk x HP.  KCH = 64 runs one CTA per SM (TMEM: 2 row
 // blocks x (64 hi + 64 lo + 32 D) = 320 of 512 columns); KCH = 32 halves the register tile and the
@@ -52,7 +58,7 @@ constexpr int DW_FLUSH = 8;   // uses of the dW operand buffer between two flush
 // thread) -- more resident warps per scheduler to cover the FP32 pipe's dependency stalls.
 template <int HP, int KCH, int LB, bool DW, int NW>
 __global__ void __launch_bounds__(NW * 32, KCH == 32 ? 2 : 1)
-k_contract_tc(const ContractArgs a, const int nkc, const int dw_nslots)
+k_contract_tc(const ContractArgs a, const int nkc, const int dw_nslots, const int DW_FLUSH)
 {
     static_assert(!DW || KCH == 64, "the dW mini-GEMM assumes 64-wide chunks");
     static_assert(!DW || NW == 8, "the dW mini-GEMM assumes 256 threads");
@@ -350,19 +356,10 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_nslots)
             }
             if (leader) {
                 tc::fence_after_sync();
-                const uint32_t bhi = bs_addr + (uint32_t)(kc * 2) * BSLICE * 4, blo = bhi + BSLICE * 4;
-                constexpr uint32_t SBO = (KCH / 4) * 128;
-#pragma unroll
-                for (int ks = 0; ks < KCH / 8; ++ks) {
-                    const uint64_t dhi = tc::make_smem_desc(bhi + ks * 256, 128, SBO);
-                    const uint64_t dlo = tc::make_smem_desc(blo + ks * 256, 128, SBO);
-                    tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dhi, idesc, !(kc == 0 && ks == 0));
-                    tc::mma_tf32_ts(d_acc, a_lo + ks * 8, dhi, idesc, true);
-                    tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dlo, idesc, true);
-                }
-                tc::mma_commit(&bars[rb]);
                 if (DW) {
-                    // dW2 chunk kc: D_dw[m][j] += sum_r T[r][m] * Z[r][j]  (M = 128: rows 64.. are don't-care)
+                    // dW2 chunk kc: D_dw[m][j] += sum_r T[r][m] * Z[r][j]  (M = 128: rows 64.. are don't-care).  Issued
+                    // BEFORE the stage-C MMAs of this chunk: the tensor pipe retires in order, and the next user of
+                    // the operand buffer waits for exactly these MMAs.
                     const uint32_t op = tc::smem_u32(opbuf);
                     const uint32_t d_dw = tmem + 2 * RBCOLS + kc * 32;
                     const bool fresh = lockw[2 + kc] == 0;   // first MMA group of this CTA into accumulator kc (under the lock)
@@ -382,6 +379,17 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_nslots)
                     __threadfence_block();
                     atomicExch(&lockw[0], 0);
                 }
+                const uint32_t bhi = bs_addr + (uint32_t)(kc * 2) * BSLICE * 4, blo = bhi + BSLICE * 4;
+                constexpr uint32_t SBO = (KCH / 4) * 128;
+#pragma unroll
+                for (int ks = 0; ks < KCH / 8; ++ks) {
+                    const uint64_t dhi = tc::make_smem_desc(bhi + ks * 256, 128, SBO);
+                    const uint64_t dlo = tc::make_smem_desc(blo + ks * 256, 128, SBO);
+                    tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dhi, idesc, !(kc == 0 && ks == 0));
+                    tc::mma_tf32_ts(d_acc, a_lo + ks * 8, dhi, idesc, true);
+                    tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dlo, idesc, true);
+                }
+                tc::mma_commit(&bars[rb]);
             }
             ++g;
         }
@@ -489,6 +497,7 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
         ContractArgs a2 = a;
         const int tiles_per_cta = qc_ceil_div(ntiles, gx);
         const int max_commits = tiles_per_cta * (NW / 4) * nkc;
+        const int DW_FLUSH = dw_flush_interval();
         const int nslots = (max_commits - 1) / DW_FLUSH + 1;
         const int nctas = gx * nblk, per = nkc * 64 * 32;
         const size_t fbytes = (size_t)nctas * nslots * per * sizeof(float);
@@ -497,7 +506,7 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
         if (own) QC_CUDA(cudaMallocAsync((void**)&buf, fbytes + (size_t)nctas * sizeof(int), st));
         a2.dW_scratch = reinterpret_cast<float*>(buf);
         a2.dW_counts = reinterpret_cast<int*>(buf + fbytes);
-        k_contract_tc<HP, KCH, LB, DW, NW><<<grid, NW * 32, smem, st>>>(a2, nkc, nslots);
+        k_contract_tc<HP, KCH, LB, DW, NW><<<grid, NW * 32, smem, st>>>(a2, nkc, nslots, DW_FLUSH);
         cudaError_t le = cudaGetLastError();
         if (le == cudaSuccess) {
             k_dw_reduce<HP><<<dim3(qc_ceil_div(per, 256), nctas), 256, 0, st>>>(a2.dW_scratch, a2.dW_counts, nslots, nkc,
@@ -508,7 +517,7 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
         if (le != cudaSuccess) return (int)le;
         return 1;
     }
-    k_contract_tc<HP, KCH, LB, DW, NW><<<grid, NW * 32, smem, st>>>(a, nkc, 0);
+    k_contract_tc<HP, KCH, LB, DW, NW><<<grid, NW * 32, smem, st>>>(a, nkc, 0, 1);
     QC_CHECK_LAUNCH();
     return 1;
 }
@@ -902,7 +911,7 @@ size_t qc_contract_tc_ws_bytes(int Ndst, int Cx, int Cy, int HP, int B)
     if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     const int max_commits = qc_ceil_div(ntiles, gx) * 2 * nkc;
-    const int nslots = (max_commits - 1) / DW_FLUSH + 1;
+    const int nslots = (max_commits - 1) / dw_flush_interval() + 1;
     const size_t nctas = (size_t)gx * nblk;
     return nctas * nslots * ((size_t)nkc * 64 * 32) * sizeof(float) + nctas * sizeof(int);
 }

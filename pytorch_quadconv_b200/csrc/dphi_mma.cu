@@ -16,6 +16,10 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma.cuh"
+#include <cstring>
+
+extern "C" int qc_mma_get_variant(void);
 
 namespace {
 
@@ -57,8 +61,10 @@ __host__ __device__ constexpr size_t dphi_smem_bytes(int CC, int Bp, int nch, in
            + (size_t)max_ku * 8 + 64 * 8 + 1024;        // union lists, barriers, alignment slack
 }
 
-template <int CC, int LB>
-__global__ void __launch_bounds__(NTHREADS, 1) k_dphi_mma(const DphiMmaArgs a)
+// TMA = true: the union rows arrive by TMA gather4 (tma.cuh; xmap = X as [nblk * Nsrc][nch * NC] bf16), issued by the
+// lanes of one producer warp, instead of per-lane cp.async copies
+template <int CC, int LB, bool TMA>
+__global__ void __launch_bounds__(NTHREADS, 1) k_dphi_mma(const DphiMmaArgs a, const __grid_constant__ CUtensorMap xmap)
 {
     constexpr int Bp = 1 << LB, NC = Bp * CC;
     static_assert(NC % 64 == 0, "the gather ring uses 128-byte rows");
@@ -97,7 +103,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dphi_mma(const DphiMmaArgs a)
 
     if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
     if (tid == 32) {
-        for (int i = 0; i < NST; ++i) tc::mbar_init(&x_full[i], 128), tc::mbar_init(&x_empty[i], 1);
+        for (int i = 0; i < NST; ++i) tc::mbar_init(&x_full[i], TMA ? 1 : 128), tc::mbar_init(&x_empty[i], 1);
         for (int i = 0; i < 2; ++i) tc::mbar_init(&a2_full[i], 8), tc::mbar_init(&a2_empty[i], 1);
         tc::mbar_init(g_full, 128), tc::mbar_init(g_empty, 1);
         tc::mbar_init(dt_full, 1), tc::mbar_init(dt_empty, 8);
@@ -137,7 +143,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dphi_mma(const DphiMmaArgs a)
             const uint32_t rowbytes = (uint32_t)(nch * NC * 2);
             for (int i = pt; i < ku; i += 128) {
                 const int u = __ldg(a.union_idx + u0 + i);
-                uix[i] = u >= 0 ? (int)((uint32_t)u * rowbytes) : -1;      // byte offset of the row (< 4 GB, host-checked)
+                if (TMA) uix[i] = u >= 0 ? blk * a.Nsrc + u : a.nblk * a.Nsrc;   // row of the 2-D view; past the end = zero fill
+                else uix[i] = u >= 0 ? (int)((uint32_t)u * rowbytes) : -1;      // byte offset of the row (< 4 GB, host-checked)
             }
             tc::named_bar_sync(2, 128);
             // G tile: row = (point in tile, batch lane), K-major over the grad channels; pieces of min(16, 2*CCg) bytes
@@ -168,6 +175,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dphi_mma(const DphiMmaArgs a)
                     const uint32_t s = xit % NST, ph = (xit / NST) & 1;
                     // byte offsets of this stage's rows, loaded together before the wait (see contract_mma.cu)
                     const uint32_t* uo = reinterpret_cast<const uint32_t*>(uix) + st * KST;
+                    if constexpr (TMA) {
+                        if (pt < 32) {
+                            constexpr int NI = (KST / 4) * (NC / 64);          // gather4 instructions per stage
+                            const int rg = pt % (KST / 4), b64 = pt / (KST / 4);
+                            int4 r = make_int4(0, 0, 0, 0);
+                            if (pt < NI) r = *reinterpret_cast<const int4*>(uo + rg * 4);
+                            tc::mbar_wait(&x_empty[s], ph ^ 1);
+                            if (pt == 0) tma::mbar_arrive_expect_tx(&x_full[s], STAGE);
+                            __syncwarp();
+                            if (pt < NI)
+                                tma::gather4(x_sa + s * STAGE + b64 * XBLK + rg * 512, &xmap, &x_full[s], c * NC + b64 * 64, r.x,
+                                             r.y, r.z, r.w);
+                        }
+                        ++xit;
+                        continue;
+                    }
                     uint32_t off[NJ];
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) off[j] = uo[(l0 + 16 * j) % KST];
@@ -342,18 +365,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dphi_mma(const DphiMmaArgs a)
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-template <int CC, int LB>
-int launch_dphi(const DphiMmaArgs& a, cudaStream_t st)
+template <int CC, int LB, bool TMA>
+int launch_dphi_v(const DphiMmaArgs& a, cudaStream_t st)
 {
     const int CgP = (a.Cg + 15) & ~15;
     const size_t smem = dphi_smem_bytes(CC, 1 << LB, a.nch, CgP, a.max_ku);
     if (smem > 227 * 1024) return 0;
-    QC_CUDA((qc_set_max_smem<k_dphi_mma<CC, LB>>((int)smem)));
+    CUtensorMap xmap;
+    memset(&xmap, 0, sizeof(xmap));
+    if (TMA && !tma::make_map_2d(&xmap, a.X, 2, (uint64_t)a.nblk * a.Nsrc, (uint64_t)a.nch * (CC << LB), 64, 1)) return 0;
+    QC_CUDA((qc_set_max_smem<k_dphi_mma<CC, LB, TMA>>((int)smem)));
     int grid = min(qc_num_sms(), a.ntiles * a.nblk);
     if (grid < 1) grid = 1;
-    k_dphi_mma<CC, LB><<<grid, NTHREADS, smem, st>>>(a);
+    k_dphi_mma<CC, LB, TMA><<<grid, NTHREADS, smem, st>>>(a, xmap);
     QC_CHECK_LAUNCH();
     return 1;
+}
+
+// QC_MMA_VAR bit 3 selects the TMA producers (same switch as contract_mma.cu); the cp.async variant is the fallback
+template <int CC, int LB>
+int launch_dphi(const DphiMmaArgs& a, cudaStream_t st)
+{
+    if (qc_mma_get_variant() & 8) {
+        const int rc = launch_dphi_v<CC, LB, true>(a, st);
+        if (rc != 0) return rc;
+    }
+    return launch_dphi_v<CC, LB, false>(a, st);
 }
 
 }  // namespace

@@ -28,7 +28,7 @@ METRICS = [
 print(f"# ncu summary of `{rep.split('/')[-1]}`\n")
 print("Captured with `ncu --set full --clock-control none --import-source on` on one B200 (sm_100a); durations are")
 print("under the profiler (serialised, cold cache) -- bench.py's CUDA-event numbers are the ones to quote.\n")
-for r in rows[2:]:
+for launch_no, r in enumerate(rows[2:]):
     name = r[idx["Kernel Name"]]
     print(f"## {name}\n")
     print("| metric | value |\n|---|---|")
@@ -38,8 +38,10 @@ for r in rows[2:]:
     print()
     short = name.split("(")[0].split("::")[-1].split("<")[0]
     for view, title in (("cuda", "Hottest source lines (warp-stall samples)"),):
-        out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name",
-                              "regex:" + short, "--launch-skip", "0", "--launch-count", "1"], capture_output=True, text=True).stdout
+        # select by position in the report: template instances of one kernel share a name prefix, and a name filter
+        # would return the first instance's source page for all of them
+        out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass",
+                              "--launch-skip", str(launch_no), "--launch-count", "1"], capture_output=True, text=True).stdout
         rr = list(csv.reader(io.StringIO(out)))
         h2, cur, lines = None, "", []
         ops = collections.Counter()

@@ -94,6 +94,40 @@ def test_tc_forward_matches_same_rounding_oracle(cuda_lib, d, n, ci, co, B, fs, 
         assert relerr(m.weight.grad.cpu().numpy(), w.grad.numpy()) < TOL_VS_FP32
 
 
+@pytest.mark.parametrize("d,n,ci,co,B,fs,r", [(3, 1500, 32, 32, 32, [8, 8], 0.16), (2, 800, 8, 12, 16, [8, 8], 0.09),
+                                             (2, 700, 20, 24, 40, [8], 0.1)])
+def test_tma_gather4_producers_match_cp_async(cuda_lib, d, n, ci, co, B, fs, r):
+    """The union rows fetched by TMA (cp.async.bulk.tensor.2d tile::gather4 into the same 128-byte-swizzled stages, out
+    of bounds rows for the padding slots) feed the same MMAs: output and every gradient are bit-identical to the
+    cp.async producers'."""
+    res = []
+    c = _oracle_case(d, n, ci, co, B, fs, r, True, seed=4100 + n)
+    # ONE layer for both runs: the union lists are built once (slot order inside a tile is not fixed across builds)
+    layer, lin = _layer(c, d, n, ci, co, fs, r, True, n, True)
+    w_dev = c["qw"].detach().cuda().requires_grad_()
+    mesh = _StubMesh(c["pts"].cuda(), c["out_pts"].cuda(), w_dev)
+    x = c["x"].detach().cuda().requires_grad_()
+    old = cuda_lib.qc_mma_set_variant(-1)
+    try:
+        for var in (4, 12):
+            cuda_lib.qc_mma_set_variant(var)
+            assert cuda_lib.qc_mma_get_variant() == var
+            for t in [x, w_dev] + [m.weight for m in lin]:
+                t.grad = None
+            y = layer(mesh, x)
+            assert layer.tc_active and layer.tc_backward_active
+            (y * c["go"].cuda()).sum().backward()
+            torch.cuda.synchronize()
+            res.append(([y.detach().clone(), x.grad.clone(), lin[-1].weight.grad.clone()],
+                        [w_dev.grad.clone()] + [m.weight.grad.clone() for m in lin[:-1]]))
+    finally:
+        cuda_lib.qc_mma_set_variant(old)
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    for a, b in zip(res[0][1], res[1][1]):      # accumulated with float atomics downstream of the (identical) d(phi)
+        assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+
+
 def test_tc_falls_back_outside_its_shapes(cuda_lib):
     """H = 16 (wide filter) and batch 3 are not served by the tensor-core kernels: the layer runs the fp32 path."""
     import pytorch_quadconv_b200 as q
