@@ -246,6 +246,18 @@ int qc_gather_fwd(const float* x, const int* index /*[Nout]*/, int BC, int Nin, 
 int qc_gather_bwd(const float* grad_out, const int* grp_ptr, const int* grp_mem, int BC, int Nfine,
                   int Ncoarse, float* grad_x, void* stream);
 
+/* The same four kernels with the activation that precedes the pool in the reference's autoencoders fused in (SURVEY 8
+ * f-4; the reference composes torch.sin and Mesh_MaxPool as separate modules): act = 0 is exactly the functions above,
+ * act = 1 computes pool(sin(x)) / gather(sin(x)) and, backward, the routed gradient times cos(x).  qc_gather_act_bwd
+ * reads x (the coarse input of the forward call, [BC][Ncoarse]) only when act != 0. */
+int qc_segmax_act_fwd(const float* x, const int* grp_ptr, const int* grp_mem, int BC, int Nin, int Nout, int act,
+                      float* out, void* stream);
+int qc_segmax_act_bwd(const float* x, const float* out, const float* grad_out, const int* group, const int* grp_ptr,
+                      const int* grp_mem, int BC, int Nin, int Nout, int act, float* grad_x, void* stream);
+int qc_gather_act_fwd(const float* x, const int* index, int BC, int Nin, int Nout, int act, float* out, void* stream);
+int qc_gather_act_bwd(const float* grad_out, const float* x, const int* grp_ptr, const int* grp_mem, int BC, int Nfine,
+                      int Ncoarse, int act, float* grad_x, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Learned quadrature-weight map.  Replaces MeshHandler.weight_map,
  * torch_quadconv/mesh_handler.py:101-112 (per-simplex Linear/Sigmoid x4 + scatter_add_) and its

@@ -101,7 +101,23 @@ class MeshHandler(nn.Module):
                     params = [p for lin in (self._weight_network[0], self._weight_network[2],
                                             self._weight_network[4], self._weight_network[6])
                               for p in (lin.weight, lin.bias)]
-                    return ops.weight_map_apply(points.detach(), adj32, inc_ptr, inc_idx, params)
+                    # The map is a pure function of (level, parameters): an encoder layer and its mirrored decoder layer
+                    # ask for the same level in one step, so the result is memoised until a parameter changes (in-place
+                    # optimiser updates bump ._version) or its autograd graph is consumed by a backward pass.  Both
+                    # users then share ONE node: one backward launch per level with the summed gradient, half the
+                    # weight-map launches and gradient-accumulation adds of an autoencoder step.  Same values as the
+                    # reference's per-call evaluation (mesh_handler.py:101-112).
+                    level = self._get_index()
+                    memo = self.__dict__.setdefault("_w_memo", {})
+                    key = (torch.is_grad_enabled(), points.data_ptr(),
+                           tuple((p.data_ptr(), p._version, p.requires_grad) for p in params))
+                    hit = memo.get(level)
+                    if hit is not None and hit[0] == key:
+                        return hit[1]
+                    w = ops.weight_map_apply(points.detach(), adj32, inc_ptr, inc_idx, params,
+                                             on_backward=lambda: memo.pop(level, None))
+                    memo[level] = (key, w)
+                    return w
                 el_points = points[element_list].reshape(-1, element_size * dimension)
                 el_weights = self._weight_network(el_points)
                 weights = torch.zeros(points.shape[0], device=points.device)

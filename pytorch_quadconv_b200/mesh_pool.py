@@ -28,9 +28,15 @@ def _group_of_fine_points(elim_map: dict, n_fine: int) -> np.ndarray:
 
 class Mesh_MaxPool(nn.Module):
 
-    def __init__(self, adjoint=False):
+    def __init__(self, adjoint=False, activation=None):
         super().__init__()
         self.adjoint = adjoint
+        # extension over the reference's signature: activation='sin' computes pool(sin(data)) in the pool
+        # kernels -- the composition the reference's autoencoders write as separate modules -- saving the activation's
+        # own launch and its [B,C,N] round trip in both directions.  None = the reference's module.
+        if activation not in (None, 'sin'):
+            raise ValueError(f"activation must be None or 'sin' (got {activation!r})")
+        self.activation = activation
         self.cached = False
         self.index = None
         self.output_shape = None
@@ -69,12 +75,13 @@ class Mesh_MaxPool(nn.Module):
         if self.index is None:
             self._build(handler, x)
         group32, grp_ptr, grp_mem, n_groups = self._tables
+        act = 1 if self.activation == 'sin' else 0
         self.output_shape = (x.shape[0], x.shape[1], self.output_shape[2])
 
         if not self.adjoint:
-            output = ops.segmax(x, group32, grp_ptr, grp_mem, n_groups)  # mesh_pool.py:88-89
+            output = ops.segmax(x, group32, grp_ptr, grp_mem, n_groups, act)  # mesh_pool.py:88-89
         else:
-            output = ops.gather_pool_apply(x, group32, grp_ptr, grp_mem)  # mesh_pool.py:93
+            output = ops.gather_pool_apply(x, group32, grp_ptr, grp_mem, act)  # mesh_pool.py:93
 
         handler.step()                                                    # mesh_pool.py:96
         return output

@@ -749,19 +749,22 @@ def _(grad_w, points, adj32, params):
 
 class _WeightMapFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, points, adj32, inc_ptr, inc_idx, *params):
+    def forward(ctx, on_backward, points, adj32, inc_ptr, inc_idx, *params):
         ctx.save_for_backward(points, adj32, *params)
+        ctx.on_backward = on_backward
         return weight_map(points, adj32, inc_ptr, inc_idx, list(params))
 
     @staticmethod
     def backward(ctx, grad_w):
         points, adj32, *params = ctx.saved_tensors
+        if ctx.on_backward is not None:
+            ctx.on_backward()          # the graph behind the memoised weights is being consumed (MeshHandler.weight_map)
         flat = weight_map_bwd(grad_w, points, adj32, list(params))
-        return (None, None, None, None, *_carve(flat, [tuple(p.shape) for p in params]))
+        return (None, None, None, None, None, *_carve(flat, [tuple(p.shape) for p in params]))
 
 
-def weight_map_apply(points, adj32, inc_ptr, inc_idx, params):
-    return _WeightMapFn.apply(points, adj32, inc_ptr, inc_idx, *params)
+def weight_map_apply(points, adj32, inc_ptr, inc_idx, params, on_backward=None):
+    return _WeightMapFn.apply(on_backward, points, adj32, inc_ptr, inc_idx, *params)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -770,76 +773,83 @@ def weight_map_apply(points, adj32, inc_ptr, inc_idx, params):
 
 @torch.library.custom_op("quadconv_b200::segmax", mutates_args=())
 @_on_device
-def segmax(x: Tensor, group: Tensor, grp_ptr: Tensor, grp_mem: Tensor, n_out: int) -> Tensor:
+def segmax(x: Tensor, group: Tensor, grp_ptr: Tensor, grp_mem: Tensor, n_out: int, act: int = 0) -> Tensor:
+    """Segmented max over the pool groups (mesh_pool.py:88-89); act = 1: of sin(x) (fused activation, csrc/pool.cu)."""
     x = _f32c(x, "pool input")
     B, Cc, Nin = x.shape
     out = torch.empty((B, Cc, n_out), dtype=torch.float32, device=x.device)
-    C.check(C.lib().qc_segmax_fwd(C.ptr(x), C.ptr(grp_ptr), C.ptr(grp_mem), B * Cc, Nin, n_out, C.ptr(out),
-                                  C.stream()), "qc_segmax_fwd")
+    C.check(C.lib().qc_segmax_act_fwd(C.ptr(x), C.ptr(grp_ptr), C.ptr(grp_mem), B * Cc, Nin, n_out, act, C.ptr(out),
+                                      C.stream()), "qc_segmax_act_fwd")
     return out
 
 
 @segmax.register_fake
-def _(x, group, grp_ptr, grp_mem, n_out):
+def _(x, group, grp_ptr, grp_mem, n_out, act=0):
     return x.new_empty((x.shape[0], x.shape[1], n_out))
 
 
 @torch.library.custom_op("quadconv_b200::segmax_bwd", mutates_args=())
 @_on_device
-def segmax_bwd(x: Tensor, out: Tensor, grad_out: Tensor, group: Tensor, grp_ptr: Tensor, grp_mem: Tensor) -> Tensor:
+def segmax_bwd(x: Tensor, out: Tensor, grad_out: Tensor, group: Tensor, grp_ptr: Tensor, grp_mem: Tensor,
+               act: int = 0) -> Tensor:
     x, out, grad_out = _f32c(x, "x"), _f32c(out, "out"), _f32c(grad_out, "grad")
     B, Cc, Nin = x.shape
     gx = torch.empty_like(x)
-    C.check(C.lib().qc_segmax_bwd(C.ptr(x), C.ptr(out), C.ptr(grad_out), C.ptr(group), C.ptr(grp_ptr),
-                                  C.ptr(grp_mem), B * Cc, Nin, out.shape[2], C.ptr(gx), C.stream()), "qc_segmax_bwd")
+    C.check(C.lib().qc_segmax_act_bwd(C.ptr(x), C.ptr(out), C.ptr(grad_out), C.ptr(group), C.ptr(grp_ptr),
+                                      C.ptr(grp_mem), B * Cc, Nin, out.shape[2], act, C.ptr(gx), C.stream()),
+            "qc_segmax_act_bwd")
     return gx
 
 
 @segmax_bwd.register_fake
-def _(x, out, grad_out, group, grp_ptr, grp_mem):
+def _(x, out, grad_out, group, grp_ptr, grp_mem, act=0):
     return torch.empty_like(x)
 
 
 @torch.library.custom_op("quadconv_b200::gather_pool", mutates_args=())
 @_on_device
-def gather_pool(x: Tensor, index: Tensor) -> Tensor:
+def gather_pool(x: Tensor, index: Tensor, act: int = 0) -> Tensor:
     x = _f32c(x, "pool input")
     B, Cc, Nin = x.shape
     n_out = index.numel()
     out = torch.empty((B, Cc, n_out), dtype=torch.float32, device=x.device)
-    C.check(C.lib().qc_gather_fwd(C.ptr(x), C.ptr(index), B * Cc, Nin, n_out, C.ptr(out), C.stream()), "qc_gather_fwd")
+    C.check(C.lib().qc_gather_act_fwd(C.ptr(x), C.ptr(index), B * Cc, Nin, n_out, act, C.ptr(out), C.stream()),
+            "qc_gather_act_fwd")
     return out
 
 
 @gather_pool.register_fake
-def _(x, index):
+def _(x, index, act=0):
     return x.new_empty((x.shape[0], x.shape[1], index.numel()))
 
 
 @torch.library.custom_op("quadconv_b200::gather_pool_bwd", mutates_args=())
 @_on_device
-def gather_pool_bwd(grad_out: Tensor, grp_ptr: Tensor, grp_mem: Tensor, n_coarse: int) -> Tensor:
+def gather_pool_bwd(grad_out: Tensor, grp_ptr: Tensor, grp_mem: Tensor, n_coarse: int, x: Optional[Tensor] = None,
+                    act: int = 0) -> Tensor:
     grad_out = _f32c(grad_out, "grad")
     B, Cc, Nf = grad_out.shape
     gx = torch.empty((B, Cc, n_coarse), dtype=torch.float32, device=grad_out.device)
-    C.check(C.lib().qc_gather_bwd(C.ptr(grad_out), C.ptr(grp_ptr), C.ptr(grp_mem), B * Cc, Nf, n_coarse,
-                                  C.ptr(gx), C.stream()), "qc_gather_bwd")
+    xp = C.ptr(_f32c(x, "pool input")) if (act and x is not None) else None
+    C.check(C.lib().qc_gather_act_bwd(C.ptr(grad_out), xp, C.ptr(grp_ptr), C.ptr(grp_mem), B * Cc, Nf, n_coarse, act,
+                                      C.ptr(gx), C.stream()), "qc_gather_act_bwd")
     return gx
 
 
 @gather_pool_bwd.register_fake
-def _(grad_out, grp_ptr, grp_mem, n_coarse):
+def _(grad_out, grp_ptr, grp_mem, n_coarse, x=None, act=0):
     return grad_out.new_empty((grad_out.shape[0], grad_out.shape[1], n_coarse))
 
 
 def _segmax_setup(ctx, inputs, output):
-    x, group, grp_ptr, grp_mem, n_out = inputs
+    x, group, grp_ptr, grp_mem, n_out, act = inputs
     ctx.save_for_backward(x, output, group, grp_ptr, grp_mem)
+    ctx.act = act
 
 
 def _segmax_backward(ctx, grad):
     x, out, group, grp_ptr, grp_mem = ctx.saved_tensors
-    return segmax_bwd(x, out, grad, group, grp_ptr, grp_mem), None, None, None, None
+    return segmax_bwd(x, out, grad, group, grp_ptr, grp_mem, ctx.act), None, None, None, None, None
 
 
 segmax.register_autograd(_segmax_backward, setup_context=_segmax_setup)
@@ -847,16 +857,19 @@ segmax.register_autograd(_segmax_backward, setup_context=_segmax_setup)
 
 class _GatherPoolFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, index, grp_ptr, grp_mem):
-        ctx.save_for_backward(grp_ptr, grp_mem)
-        ctx.n_coarse = x.shape[2]
-        return gather_pool(x, index)
+    def forward(ctx, x, index, grp_ptr, grp_mem, act):
+        if act:
+            ctx.save_for_backward(grp_ptr, grp_mem, x)
+        else:
+            ctx.save_for_backward(grp_ptr, grp_mem)
+        ctx.n_coarse, ctx.act = x.shape[2], act
+        return gather_pool(x, index, act)
 
     @staticmethod
     def backward(ctx, grad):
-        grp_ptr, grp_mem = ctx.saved_tensors
-        return gather_pool_bwd(grad, grp_ptr, grp_mem, ctx.n_coarse), None, None, None
+        grp_ptr, grp_mem, *rest = ctx.saved_tensors
+        return gather_pool_bwd(grad, grp_ptr, grp_mem, ctx.n_coarse, rest[0] if rest else None, ctx.act), None, None, None, None
 
 
-def gather_pool_apply(x, index, grp_ptr, grp_mem):
-    return _GatherPoolFn.apply(x, index, grp_ptr, grp_mem)
+def gather_pool_apply(x, index, grp_ptr, grp_mem, act=0):
+    return _GatherPoolFn.apply(x, index, grp_ptr, grp_mem, act)

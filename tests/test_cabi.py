@@ -41,8 +41,9 @@ def test_host_side_shape_queries():
     assert L.qc_dphi_num_slices(100000, 32, 32, 8, 32) == 4   # C3: one slice per channel chunk
     assert L.qc_dphi_num_slices(1000, 64, 128, 32, 8) == 1    # not served by the fused kernels
     ws = L.qc_contract_workspace_bytes(32, 8, 8, 32, 100000, 32)
-    # C3 backward: 148 CTAs x 85 slots x 4 chunks x 64 x 32 floats + one counter per CTA
-    assert ws == 148 * 85 * 4 * 64 * 32 * 4 + 148 * 4
+    # C3 backward: 85 tiles per CTA x 2 row blocks x 4 chunks = 680 uses of the operand buffer, one slot per 16 uses ->
+    # 148 CTAs x 43 slots x 4 chunks x 64 x 32 floats + one counter per CTA
+    assert ws == 148 * 43 * 4 * 64 * 32 * 4 + 148 * 4
     assert L.qc_contract_workspace_bytes(64, 32, 32, 128, 10000, 8) == 0   # wide shapes: no tcgen05 dW variant
 
 

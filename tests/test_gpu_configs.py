@@ -90,7 +90,7 @@ def test_c4_wide_layer_full_size_vs_float64(cuda_lib):
     assert 150 * N < P < 210 * N
 
 
-def _autoencoder(B, seed=0):
+def _autoencoder(B, seed=0, fused=True):
     import pytorch_quadconv_b200 as q
     from bench import QuadConvAutoencoder
     torch.manual_seed(seed)
@@ -98,16 +98,18 @@ def _autoencoder(B, seed=0):
     pts = torch.rand(N, 2)
     x = torch.randn(B, 4, N)
     mesh = q.MeshHandler(pts).construct([N, 0, 0, 0, 0], mirror=True, quad_map="mfnus")
-    model = QuadConvAutoencoder(mesh, [4, 8, 16, 32, 32], [8, 8]).cuda()
+    model = QuadConvAutoencoder(mesh, [4, 8, 16, 32, 32], [8, 8], fuse_activation=fused).cuda()
     return model, x.cuda()
 
 
-def test_c2_autoencoder_full_size_vs_float64(cuda_lib):
+@pytest.mark.parametrize("fused", [False, True])
+def test_c2_autoencoder_full_size_vs_float64(cuda_lib, fused):
     """configs[1]: the 10k-point autoencoder (8 QuadConv + 4 pool + 4 adjoint-pool layers, sin activations, MSE) at full
-    size, batch 2, against the same composition evaluated in float64 by the oracle on the CPU."""
+    size, batch 2, against the same composition evaluated in float64 by the oracle on the CPU.  fused: the sin
+    activations evaluated inside the pool kernels (Mesh_MaxPool(activation='sin')) instead of torch.sin launches."""
     import ref64
     from oracle import quadconv_oracle as O
-    model, x = _autoencoder(2)
+    model, x = _autoencoder(2, fused=fused)
     mesh = model.mesh
     x.requires_grad_()
     y = model(x)

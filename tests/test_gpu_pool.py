@@ -163,3 +163,31 @@ def test_pool_nan_propagates_like_torch_amax(cuda_lib):
     assert torch.equal(y.detach().cpu()[0, 0, 1:], yr.detach()[0, 0, 1:])
     assert torch.equal(torch.isnan(x.grad.cpu()), torch.isnan(xr.grad))
     assert torch.equal(torch.nan_to_num(x.grad.cpu()), torch.nan_to_num(xr.grad))
+
+
+@pytest.mark.parametrize("adjoint", [False, True])
+def test_pool_fused_sin_matches_composition(cuda_lib, adjoint):
+    """Mesh_MaxPool(activation='sin') == pool(torch.sin(x)) forward (bit-exact: the same sinf) and backward (<= 1e-6:
+    torch multiplies by cos after routing, the kernel while routing), including tied maxima, on the golden pool chain."""
+    import pytorch_quadconv_b200 as q
+    A = load_golden("autoencoder")
+    mesh = q.MeshHandler(torch.from_numpy(A["pts"])).construct([400, 0], mirror=True, quad_map="mfnus").cuda()
+    n0, n1 = mesh.point_seq
+    torch.manual_seed(3)
+    x = torch.randn(3, 5, n1 if adjoint else n0, device="cuda")
+    if not adjoint:
+        idx = torch.arange(0, x.shape[2] - 1, 7, device="cuda")
+        x[:, :, idx] = x[:, :, idx + 1]                                     # equal inputs -> equal sines -> ties inside groups
+    outs = []
+    for act in (None, 'sin'):
+        pool = q.Mesh_MaxPool(adjoint=adjoint, activation=act)
+        xi = x.clone().requires_grad_()
+        mesh.reset()
+        if adjoint:
+            mesh.step()                                                     # cursor on the coarse level
+        y = pool(mesh, xi if act else torch.sin(xi))
+        g = torch.cos(torch.arange(y.numel(), device="cuda", dtype=torch.float32)).view_as(y)
+        (y * g).sum().backward()
+        outs.append((y.detach(), xi.grad))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert relerr(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy()) < 1e-6
