@@ -499,15 +499,17 @@ def run_ours(args, w, rank, local_rank, world, dev, sub=False, tc_table=False):
             ach = alg[dom] / (tc_k[dom] * 1e-3) / 1e12
             gather_bytes = None
             try:
-                gather_bytes = json.load(open(os.path.join(ROOT, "profiles", "r02_tc_traffic.json"))).get(dom)
+                gather_bytes = json.load(open(os.path.join(ROOT, "profiles", "r02_tc_traffic.json"))).get(args.workload, {}).get(dom)
             except Exception:
                 pass
             roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
                     "traffic": gather_bytes,
                     "note": f"bf16 tensor peak of {'measured (MEASURED_PEAKS.json)' if peaks else 'fallback'}; numerator = "
                             f"factorised-formulation FLOPs of this launch ({alg[dom] / 1e9:.1f} GFLOP) / CUDA-event time "
-                            f"{tc_k[dom]:.3f} ms.  The kernel is bound by the L2->SM gather of the union rows (2.6 GB per "
-                            f"launch at ~3 TB/s, profiles/), not by the tensor pipe (20 % active)"}
+                            f"{tc_k[dom]:.3f} ms; traffic = DRAM bytes of this launch (ncu).  The kernel is bound by the "
+                            f"L2->SM gather of the union rows (2.6-2.8 GB per launch = 12 bytes/clk/SM through per-lane "
+                            f"cp.async; the TMA gather4 variant is 2.4x slower), not by the tensor pipe (16-25 % active, "
+                            f"profiles/r02_c3_bf16_tensor_core_kernels.md)"}
     if rank == 0 and not is_ae and not sub:
         table, calls_per_step = time_kernels(w, mesh, layer, x)
         peaks = {}
@@ -534,8 +536,12 @@ def run_ours(args, w, rank, local_rank, world, dev, sub=False, tc_table=False):
         ach = alg / (dom_ms * 1e-3) / 1e12
         traffic = None
         try:   # dram__bytes_read+write of this kernel from the committed `ncu --set full` capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
-            traffic = tr.get(args.workload, {}).get(dom)
+            for f in ("r02_dram_traffic.json", "r01_dram_traffic.json"):
+                fp = os.path.join(ROOT, "profiles", f)
+                if os.path.exists(fp):
+                    traffic = json.load(open(fp)).get(args.workload, {}).get(dom)
+                    if traffic is not None:
+                        break
         except Exception:
             pass
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
