@@ -10,10 +10,14 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer owned by the caller (torch allocates), except where a
- *     parameter is documented as host; kernels never allocate or free;
+ *     parameter is documented as host.  Steady-state entry points allocate nothing; two setup-time exceptions use
+ *     stream-ordered scratch (cudaMallocAsync/cudaFreeAsync on the caller's stream): the scan / sort scratch of
+ *     qc_search_* and qc_balance_order, and qc_contract's dW mode when it is handed no workspace
+ *     (qc_contract_workspace_bytes; the modules always pass one, so captured CUDA graphs never allocate);
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
  *   - return value: 0 on success, a positive cudaError_t, or a negative QC_E* code; no exceptions;
- *   - re-entrant, no global state apart from one-time cudaFuncSetAttribute calls.
+ *   - re-entrant, no global state apart from per-process caches of launch-invariant host state (SM count,
+ *     cudaFuncSetAttribute done once per kernel and device, environment switches read once).
  *
  * Internal data layouts (DESIGN.md "Data layout in HBM")
  *   packed features  Xp[nblk][N][CP4/4][Bp][4] fp32; CP4 = C rounded up to 4, Bp = min(32, pow2ceil(B)) lanes,
