@@ -191,6 +191,16 @@ int qc_gather_dot(const float* Xp, int Nsrc, int Cx, const float* dT, const int*
 int qc_gemm_nt_tf32x3(const float* A, const float* B, float* D, long long M, int N, int K,
                       long long rows_per_batch, void* stream);
 
+/* The fourth GEMM of the wide path, dW_last: the reduction runs over the ROW index of the big operand.
+ *     D[n][m] = sum_{b,kk} X[b][n][kk] * T[b*Kb + kk][m]
+ * T [nb*Kb x M] row-major fp32 (read exactly once: the kernel is HBM bound), X [nb][N][Kb] (the reference's
+ * [B, C, N] feature layout, quadconv.py:238), D [N x M] row-major; 3xTF32 on tcgen05 with T as the TMEM operand
+ * (csrc/gemm_tc.cu).  K is split over CTAs; the partial results live in `ws` (qc_gemm_tn_workspace_bytes, may be 0)
+ * and are summed in a fixed order (bit-reproducible). */
+size_t qc_gemm_tn_workspace_bytes(int nb, int Kb, int M, int N);
+int qc_gemm_tn_tf32x3(const float* T, const float* X, float* D, int nb, int Kb, int M, int N,
+                      void* ws, size_t ws_bytes, void* stream);
+
 /* Repack the last Linear weight W_last [Ci*Co][H] (filter.{2L}.weight, quadconv.py:143):
  *   mode 0: W2[(i*H+h)*CoP + j]  (forward)        mode 1: W2[(j*H+h)*CiP + i]  (d features)
  *   mode 2: W3[(j*Ci+i)*HP + h]  (d phi)

@@ -73,6 +73,8 @@ _SIGNATURES = {
     "qc_gather_dot": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                               c_int, c_int64, c_void_p, c_void_p]),
     "qc_gemm_nt_tf32x3": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, ctypes.c_longlong, c_void_p]),
+    "qc_gemm_tn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "qc_gemm_tn_tf32x3": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "qc_repack_wlast": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qc_unpack_dwlast": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "qc_segmax_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -158,7 +160,9 @@ def ptr(t) -> int | None:
 
 
 def stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of the current stream of the current device (what torch.cuda.current_stream().cuda_stream returns,
+    without building a Stream object: this runs once per op call on a host-bound path)."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def make_mlp(d: int, hidden_ws, operand_bf16: bool = False) -> QcMlp:

@@ -79,7 +79,7 @@ class Mesh_MaxPool(nn.Module):
         self.output_shape = (x.shape[0], x.shape[1], self.output_shape[2])
 
         if not self.adjoint:
-            output = ops.segmax(x, group32, grp_ptr, grp_mem, n_groups, act)  # mesh_pool.py:88-89
+            output = ops.segmax_apply(x, group32, grp_ptr, grp_mem, n_groups, act)  # mesh_pool.py:88-89
         else:
             output = ops.gather_pool_apply(x, group32, grp_ptr, grp_mem, act)  # mesh_pool.py:93
 

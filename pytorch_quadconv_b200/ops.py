@@ -13,6 +13,7 @@ FLOP of the path runs in libquadconv_b200.so.  Ops (namespace `quadconv_b200`):
 from __future__ import annotations
 
 import functools
+import math
 import os
 
 from typing import List, Optional, Sequence, Tuple
@@ -34,10 +35,22 @@ def _on_device(fn):
             if isinstance(a, torch.Tensor):
                 if not a.is_cuda:
                     raise RuntimeError("pytorch_quadconv_b200 kernels need CUDA tensors (there is no CPU path)")
+                if a.device.index == torch.cuda.current_device():     # the usual case: no context switch needed
+                    return fn(*args, **kwargs)
                 with torch.cuda.device(a.device):
                     return fn(*args, **kwargs)
         return fn(*args, **kwargs)
     return wrapper
+
+
+def _call(op, *args):
+    """Run a quadconv_b200:: op from the autograd glue.  Eager mode calls the op's Python body directly: the
+    torch.library dispatcher costs 20-25 us per call on the host, a tenth of a small-mesh layer step, and adds nothing
+    here (autograd is handled by the enclosing Function, the body is CUDA-only).  Under torch.compile the registered op
+    (torch.ops.quadconv_b200.*, with its fake kernel) is what gets traced."""
+    if torch.compiler.is_compiling():
+        return op(*args)
+    return op._init_fn(*args)
 
 
 def _hp(h: int) -> int:
@@ -188,7 +201,7 @@ def _(eval_indices, n_out, n_in):
 
 def _flat_layout(shapes):
     """Offsets of tensors of the given shapes inside one flat fp32 buffer (16-byte aligned pieces)."""
-    sizes = [int(np.prod(sh)) if len(sh) else 1 for sh in shapes]
+    sizes = [math.prod(sh) for sh in shapes]
     offs, total = [], 0
     for n in sizes:
         offs.append(total)
@@ -243,10 +256,11 @@ def _gemm_nt(A: Tensor, Bm: Tensor, rows_per_batch: int = 0) -> Tensor:
     rows_per_batch = R > 0 returns [M/R, N, R] (each block of R rows transposed), else [M, N]."""
     M, K = A.shape
     N = Bm.shape[0]
+    if K % 4 != 0:      # 128-bit row pieces: pad the reduction dimension with zeros (odd channel counts only)
+        A = torch.nn.functional.pad(A, (0, 4 - K % 4))
+        Bm = torch.nn.functional.pad(Bm, (0, 4 - K % 4))
+        K = A.shape[1]
     A, Bm = A.contiguous(), Bm.contiguous()
-    if K % 4 != 0:      # 128-bit row pieces; not reachable with H % 4 == 0
-        D = torch.matmul(A, Bm.t())
-        return D.reshape(M // rows_per_batch, rows_per_batch, N).transpose(1, 2).contiguous() if rows_per_batch else D
     shape = (M // rows_per_batch, N, rows_per_batch) if rows_per_batch else (M, N)
     D = torch.empty(shape, dtype=torch.float32, device=A.device)
     C.check(C.lib().qc_gemm_nt_tf32x3(C.ptr(A), C.ptr(Bm), C.ptr(D), M, N, K, rows_per_batch, C.stream()),
@@ -254,15 +268,19 @@ def _gemm_nt(A: Tensor, Bm: Tensor, rows_per_batch: int = 0) -> Tensor:
     return D
 
 
-class _fp32_matmul:
-    """The dense stage of the wide path must be a true fp32 GEMM (1e-5 parity bound)."""
-
-    def __enter__(self):
-        self.prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = False
-
-    def __exit__(self, *exc):
-        torch.backends.cuda.matmul.allow_tf32 = self.prev
+def _gemm_tn(T: Tensor, X: Tensor) -> Tensor:
+    """D[n][m] = sum_{b,k} X[b][n][k] * T[b*Kb + k][m] for T [nb*Kb, M] row-major and X [nb, N, Kb] (the [B, C, N]
+    feature layout) on the tensor cores in 3xTF32 -- the GEMM that reduces over the row index of T (csrc/gemm_tc.cu)."""
+    nb, N, Kb = X.shape
+    M = T.shape[1]
+    T, X = T.contiguous(), X.contiguous()
+    L = C.lib()
+    wsb = L.qc_gemm_tn_workspace_bytes(nb, Kb, M, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=T.device) if wsb else None
+    D = torch.empty((N, M), dtype=torch.float32, device=T.device)
+    C.check(L.qc_gemm_tn_tf32x3(C.ptr(T), C.ptr(X), C.ptr(D), nb, Kb, M, N, C.ptr(ws), wsb, C.stream()),
+            "qc_gemm_tn_tf32x3")
+    return D
 
 
 @torch.library.custom_op("quadconv_b200::qc_forward", mutates_args=())
@@ -303,8 +321,7 @@ def qc_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor
         C.check(L.qc_gather_accumulate(C.ptr(xp), Ni, Ci, C.ptr(row_ptr), C.ptr(pair_col), None, C.ptr(phi), H, HP,
                                        C.ptr(order_out), No, B, C.ptr(T), st), "qc_gather_accumulate")
         W2T = w_last.view(Ci, Co, H).permute(1, 0, 2).reshape(Co, Ci * H)     # [j, (i,h)]
-        with _fp32_matmul():
-            out = _gemm_nt(T.view(B * No, Ci * H), W2T, No)                   # [B, Co, No]
+        out = _gemm_nt(T.view(B * No, Ci * H), W2T, No)                       # [B, Co, No]
         if bias is not None:
             out = out + _f32c(bias, "bias").reshape(1, Co, No)
         return out, phi, xp
@@ -568,33 +585,32 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
 
     if P > 0 and _use_wide(Ci, Co, H, HP, B, max(No, Ni)):
         wl = w_last.view(Ci, Co, H)
-        with _fp32_matmul():
-            # d phi: dT = G * W2^T as a GEMM, then the per-pair dots against the gathered features
-            W2 = wl.permute(0, 2, 1).reshape(Ci * H, Co)                       # [(i,h), j]
-            dT = _gemm_nt(grad_out.transpose(1, 2).reshape(B * No, Co), W2)    # [B*No, Ci*H]
-            nsl = L.qc_gather_dot_num_slices(Ci, HP, B)
-            dphi = torch.empty((nsl, P, HP), **f32)
-            C.check(L.qc_gather_dot(C.ptr(xp), Ni, Ci, C.ptr(dT), C.ptr(row_ptr), C.ptr(pair_col), H, HP,
-                                    C.ptr(order_out), No, B, P, C.ptr(dphi), st), "qc_gather_dot")
-            del dT
-            d_hidden = [torch.zeros_like(w) for w in hidden_ws]
-            d_quad_w = torch.zeros(Ni, **f32)
-            mlp = C.make_mlp(d, hidden_ws, mlp_bf16)
-            import ctypes
-            dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
-            C.check(L.qc_pair_phi_bwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row),
-                                      C.ptr(pair_col), P, d, mlp, HP, C.ptr(dphi), nsl, dptrs, C.ptr(d_quad_w), st),
-                    "qc_pair_phi_bwd")
-            del dphi
-            # d features and d W_last from T'[b][n][(j,h)] = sum_p phi[p][h] G[out(p)][b][j] (CSC view)
-            Tp = torch.empty((B, Ni, Co * H), **f32)
-            C.check(L.qc_gather_accumulate(C.ptr(gp), No, Co, C.ptr(csc_ptr), C.ptr(csc_row), C.ptr(csc_pair),
-                                           C.ptr(phi), H, HP, C.ptr(order_in), Ni, B, C.ptr(Tp), st),
-                    "qc_gather_accumulate (backward)")
-            d_features = _gemm_nt(Tp.view(B * Ni, Co * H), wl.reshape(Ci, Co * H), Ni)   # [B, Ci, Ni]
-            x = _unpack(xp, B, Ci, Ni, None)
-            dWt = torch.matmul(x.permute(1, 0, 2).reshape(Ci, B * Ni), Tp.reshape(B * Ni, Co * H))   # [i, (j,h)]
-            d_w_last = dWt.reshape(Ci * Co, H)
+        # d phi: dT = G * W2^T as a GEMM, then the per-pair dots against the gathered features
+        W2 = wl.permute(0, 2, 1).reshape(Ci * H, Co)                       # [(i,h), j]
+        dT = _gemm_nt(grad_out.transpose(1, 2).reshape(B * No, Co), W2)    # [B*No, Ci*H]
+        nsl = L.qc_gather_dot_num_slices(Ci, HP, B)
+        dphi = torch.empty((nsl, P, HP), **f32)
+        C.check(L.qc_gather_dot(C.ptr(xp), Ni, Ci, C.ptr(dT), C.ptr(row_ptr), C.ptr(pair_col), H, HP,
+                                C.ptr(order_out), No, B, P, C.ptr(dphi), st), "qc_gather_dot")
+        del dT
+        d_hidden = [torch.zeros_like(w) for w in hidden_ws]
+        d_quad_w = torch.zeros(Ni, **f32)
+        mlp = C.make_mlp(d, hidden_ws, mlp_bf16)
+        import ctypes
+        dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
+        C.check(L.qc_pair_phi_bwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row),
+                                  C.ptr(pair_col), P, d, mlp, HP, C.ptr(dphi), nsl, dptrs, C.ptr(d_quad_w), st),
+                "qc_pair_phi_bwd")
+        del dphi
+        # d features and d W_last from T'[b][n][(j,h)] = sum_p phi[p][h] G[out(p)][b][j] (CSC view)
+        Tp = torch.empty((B, Ni, Co * H), **f32)
+        C.check(L.qc_gather_accumulate(C.ptr(gp), No, Co, C.ptr(csc_ptr), C.ptr(csc_row), C.ptr(csc_pair),
+                                       C.ptr(phi), H, HP, C.ptr(order_in), Ni, B, C.ptr(Tp), st),
+                "qc_gather_accumulate (backward)")
+        d_features = _gemm_nt(Tp.view(B * Ni, Co * H), wl.reshape(Ci, Co * H), Ni)   # [B, Ci, Ni]
+        x = _unpack(xp, B, Ci, Ni, None)
+        dWt = _gemm_tn(Tp.view(B * Ni, Co * H), x)                                    # [i, (j,h)]
+        d_w_last = dWt.reshape(Ci * Co, H)
         shapes = _grad_shapes(hidden_ws, Ni, Ci, Co, H)
         flat = torch.empty(_flat_layout(shapes)[2], **f32)
         for dst, src in zip(_carve(flat, shapes), d_hidden + [d_quad_w, d_w_last]):
@@ -645,6 +661,126 @@ def _(grad_out, xp, phi, out_pts, in_pts, quad_w, hidden_ws, w_last, pair_row, p
     return [e((batch, in_channels, Ni)), e((1, out_channels, No)) if has_bias else e(0), e(_flat_layout(shapes)[2])]
 
 
+# ---- the whole layer in ONE C call per direction (csrc/layer.cu) ------------------------------
+# Small meshes are bound by the host: the composed ops above make ~6 + ~11 C calls and a dozen allocations per layer
+# step.  qc_layer_forward / qc_layer_backward run the same kernels behind one call with one workspace, which also
+# carries the saved activations (packed features, phi) to the backward call.  The workspace holds the backward's
+# scratch too, so this path is taken only while it stays below SINGLE_CALL_MAX_BYTES; larger layers (where the host
+# cost is noise) keep the composed ops and their tighter allocation lifetimes.
+
+SINGLE_CALL_MAX_BYTES = 64 << 20
+
+
+def _layer_desc(out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair_col, row_ptr, csc_ptr, csc_pair,
+                csc_row, order_out, order_in, Ci, Co) -> C.QcLayer:
+    d = C.QcLayer()
+    d.d, d.Ni, d.No, d.Ci, d.Co, d.H = out_pts.shape[1], in_pts.shape[0], out_pts.shape[0], Ci, Co, w_last.shape[1]
+    d.P = pair_row.numel()
+    d.out_pts, d.in_pts, d.quad_w = C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w)
+    d.mlp = C.make_mlp(out_pts.shape[1], hidden_ws, False)
+    d.w_last, d.bias = C.ptr(w_last), C.ptr(bias)
+    d.pair_row, d.pair_col, d.row_ptr = C.ptr(pair_row), C.ptr(pair_col), C.ptr(row_ptr)
+    d.csc_ptr, d.csc_pair, d.csc_row = C.ptr(csc_ptr), C.ptr(csc_pair), C.ptr(csc_row)
+    d.order_out, d.order_in = C.ptr(order_out), C.ptr(order_in)
+    return d
+
+
+@functools.lru_cache(maxsize=256)
+def single_call_workspace_bytes(B, Ci, Co, H, Ni, No, P, d=2) -> int:
+    """Workspace of qc_layer_forward/backward for a layer of this shape (only the sizes of the descriptor are read)."""
+    desc = C.QcLayer()
+    desc.d, desc.Ni, desc.No, desc.Ci, desc.Co, desc.H, desc.P = d, Ni, No, Ci, Co, H, P
+    import ctypes
+    return int(C.lib().qc_layer_workspace_bytes(ctypes.byref(desc), B))
+
+
+@torch.library.custom_op("quadconv_b200::layer_forward", mutates_args=())
+@_on_device
+def layer_forward(features: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor, hidden_ws: Sequence[Tensor],
+                  w_last: Tensor, bias: Optional[Tensor], pair_row: Tensor, pair_col: Tensor, row_ptr: Tensor,
+                  csc_ptr: Tensor, csc_pair: Tensor, csc_row: Tensor, order_out: Optional[Tensor],
+                  order_in: Optional[Tensor], in_channels: int, out_channels: int) -> Tuple[Tensor, Tensor]:
+    """QuadConv.forward + _integrate (quadconv.py:238-265, :213-227) as ONE C call.  Returns (out [B,Co,No], ws): the
+    workspace carries the saved activations and must reach layer_backward untouched."""
+    import ctypes
+    features = _f32c(features, "features")
+    out_pts, in_pts, quad_w = _f32c(out_pts, "points"), _f32c(in_pts, "points"), _f32c(quad_w, "weights")
+    hidden_ws = [_f32c(w, "filter weight") for w in hidden_ws]
+    w_last = _f32c(w_last, "filter weight")
+    B, Ci, Ni = features.shape
+    if Ci != in_channels or in_pts.shape[0] != Ni:
+        raise RuntimeError(f"features {tuple(features.shape)} do not match in_channels={in_channels}, in_points={in_pts.shape[0]}")
+    if w_last.shape[0] != Ci * out_channels:
+        raise RuntimeError("last filter layer must have in_channels*out_channels outputs")
+    _hp(w_last.shape[1])
+    b2 = _f32c(bias, "bias").reshape(out_channels, out_pts.shape[0]) if bias is not None else None
+    desc = _layer_desc(out_pts, in_pts, quad_w, hidden_ws, w_last, b2, pair_row, pair_col, row_ptr, csc_ptr, csc_pair,
+                       csc_row, order_out, order_in, Ci, out_channels)
+    L = C.lib()
+    ref = ctypes.byref(desc)
+    wsb = L.qc_layer_workspace_bytes(ref, B)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=features.device)
+    out = torch.empty((B, out_channels, out_pts.shape[0]), dtype=torch.float32, device=features.device)
+    C.check(L.qc_layer_forward(ref, C.ptr(features), B, C.ptr(out), C.ptr(ws), wsb, C.stream()), "qc_layer_forward")
+    return out, ws
+
+
+@layer_forward.register_fake
+def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair_col, row_ptr, csc_ptr, csc_pair,
+      csc_row, order_out, order_in, in_channels, out_channels):
+    B, Ci, Ni = features.shape
+    No = out_pts.shape[0]
+    wsb = single_call_workspace_bytes(B, Ci, out_channels, w_last.shape[1], Ni, No, pair_row.shape[0], out_pts.shape[1])
+    return features.new_empty((B, out_channels, No)), features.new_empty(wsb, dtype=torch.uint8)
+
+
+@torch.library.custom_op("quadconv_b200::layer_backward", mutates_args=())
+@_on_device
+def layer_backward(grad_out: Tensor, ws: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor,
+                   hidden_ws: Sequence[Tensor], w_last: Tensor, pair_row: Tensor, pair_col: Tensor, row_ptr: Tensor,
+                   csc_ptr: Tensor, csc_pair: Tensor, csc_row: Tensor, order_out: Optional[Tensor],
+                   order_in: Optional[Tensor], in_channels: int, out_channels: int, has_bias: bool) -> List[Tensor]:
+    """Autograd of layer_forward as ONE C call.  Returns [d_features, d_bias (or empty), flat] like qc_backward."""
+    import ctypes
+    grad_out = _f32c(grad_out, "grad_out")
+    hidden_ws = [_f32c(w, "filter weight") for w in hidden_ws]
+    w_last = _f32c(w_last, "filter weight")
+    B, Co, No = grad_out.shape
+    Ci, Ni = in_channels, in_pts.shape[0]
+    dev = grad_out.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    desc = _layer_desc(out_pts, in_pts, quad_w, hidden_ws, w_last, None, pair_row, pair_col, row_ptr, csc_ptr, csc_pair,
+                       csc_row, order_out, order_in, Ci, Co)
+    shapes = _grad_shapes(hidden_ws, Ni, Ci, Co, w_last.shape[1])
+    flat = torch.empty(_flat_layout(shapes)[2], **f32)          # every piece is overwritten by the C call
+    *d_hidden, d_quad_w, d_w_last = _carve(flat, shapes)
+    d_features = torch.empty((B, Ci, Ni), **f32)
+    d_bias = torch.empty((1, Co, No), **f32) if has_bias else torch.empty(0, **f32)
+    dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
+    C.check(C.lib().qc_layer_backward(ctypes.byref(desc), C.ptr(grad_out), B, C.ptr(d_features), C.ptr(d_quad_w),
+                                      C.ptr(d_w_last), dptrs, C.ptr(d_bias) if has_bias else None, C.ptr(ws),
+                                      ws.numel(), C.stream()), "qc_layer_backward")
+    return [d_features, d_bias, flat]
+
+
+@layer_backward.register_fake
+def _(grad_out, ws, out_pts, in_pts, quad_w, hidden_ws, w_last, pair_row, pair_col, row_ptr, csc_ptr, csc_pair,
+      csc_row, order_out, order_in, in_channels, out_channels, has_bias):
+    Ni, No = in_pts.shape[0], out_pts.shape[0]
+    e = grad_out.new_empty
+    shapes = _grad_shapes(hidden_ws, Ni, in_channels, out_channels, w_last.shape[1])
+    return [e((grad_out.shape[0], in_channels, Ni)), e((1, out_channels, No)) if has_bias else e(0),
+            e(_flat_layout(shapes)[2])]
+
+
+def _single_call_ok(B, Ci, Co, H, Ni, No, P, d, mlp_bf16) -> bool:
+    if mlp_bf16 or P <= 0 or SINGLE_CALL_MAX_BYTES <= 0 or H > 32:
+        return False
+    if _use_wide(Ci, Co, H, _hp(H), B, max(No, Ni)):
+        return False
+    return single_call_workspace_bytes(B, Ci, Co, H, Ni, No, P, d) <= SINGLE_CALL_MAX_BYTES
+
+
 class _QuadConvFn(torch.autograd.Function):
     """Autograd glue: forward/backward are the custom ops above."""
 
@@ -654,12 +790,18 @@ class _QuadConvFn(torch.autograd.Function):
         Ci, Co, mlp_bf16, tc = dims
         if tc is not None:
             tile_ent, tile_pptr, tile_uptr, union_idx, max_ku = tc["fwd"]
-            out, phi, xh = qc_forward_tc(features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
+            out, phi, xh = _call(qc_forward_tc, features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
                                          pair_col, tc["order_out"], tile_ent, tile_pptr, tile_uptr, union_idx, max_ku, Ci, Co)
             # the tensor-core backward reads the bf16 packed features; shapes it does not serve re-pack the fp32 input
             ctx.save_for_backward(xh if tc.get("bwd") is not None else features, phi, quad_w, w_last, *hidden_ws)
+        elif _single_call_ok(features.shape[0], Ci, Co, w_last.shape[1], in_pts.shape[0], out_pts.shape[0],
+                             pair_row.numel(), out_pts.shape[1], mlp_bf16):
+            out, ws = _call(layer_forward, features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row, pair_col,
+                                    row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in, Ci, Co)
+            ctx.save_for_backward(ws, quad_w, w_last, *hidden_ws)
+            ctx.single = True
         else:
-            out, phi, xp = qc_forward(features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
+            out, phi, xp = _call(qc_forward, features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row,
                                       pair_col, row_ptr, order_out, Ci, Co, mlp_bf16)
             ctx.save_for_backward(xp, phi, quad_w, w_last, *hidden_ws)
         ctx.tables = tables
@@ -669,18 +811,23 @@ class _QuadConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        xp, phi, quad_w, w_last, *hidden_ws = ctx.saved_tensors
         out_pts, in_pts, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = ctx.tables[:10]
         B, Ci, Co, has_bias, mlp_bf16 = ctx.dims
+        if getattr(ctx, "single", False):
+            ws, quad_w, w_last, *hidden_ws = ctx.saved_tensors
+            res = _call(layer_backward, grad_out, ws, out_pts, in_pts, quad_w, list(hidden_ws), w_last, pair_row, pair_col,
+                                 row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in, Ci, Co, has_bias)
+            return _QuadConvFn._unpack_grads(res, hidden_ws, in_pts.shape[0], Ci, Co, w_last.shape[1], has_bias)
+        xp, phi, quad_w, w_last, *hidden_ws = ctx.saved_tensors
         if ctx.tc is not None and ctx.tc.get("bwd") is not None:
             tc = ctx.tc
-            res = qc_backward_tc(grad_out, xp, phi, out_pts, in_pts, quad_w, list(hidden_ws), w_last, pair_row, pair_col,
+            res = _call(qc_backward_tc, grad_out, xp, phi, out_pts, in_pts, quad_w, list(hidden_ws), w_last, pair_row, pair_col,
                                  tc["order_out"], tc["order_in"], *tc["fwd"], *tc["bwd"], B, Ci, Co, has_bias)
             return _QuadConvFn._unpack_grads(res, hidden_ws, in_pts.shape[0], Ci, Co, w_last.shape[1], has_bias)
         if ctx.tc is not None:
             with torch.cuda.device(xp.device):
                 xp = _pack(_f32c(xp, "features"))
-        res = qc_backward(grad_out, xp, phi, out_pts, in_pts, quad_w, list(hidden_ws), w_last, pair_row, pair_col,
+        res = _call(qc_backward, grad_out, xp, phi, out_pts, in_pts, quad_w, list(hidden_ws), w_last, pair_row, pair_col,
                           row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in, B, Ci, Co, has_bias, mlp_bf16)
         return _QuadConvFn._unpack_grads(res, hidden_ws, in_pts.shape[0], Ci, Co, w_last.shape[1], has_bias)
 
@@ -752,14 +899,14 @@ class _WeightMapFn(torch.autograd.Function):
     def forward(ctx, on_backward, points, adj32, inc_ptr, inc_idx, *params):
         ctx.save_for_backward(points, adj32, *params)
         ctx.on_backward = on_backward
-        return weight_map(points, adj32, inc_ptr, inc_idx, list(params))
+        return _call(weight_map, points, adj32, inc_ptr, inc_idx, list(params))
 
     @staticmethod
     def backward(ctx, grad_w):
         points, adj32, *params = ctx.saved_tensors
         if ctx.on_backward is not None:
             ctx.on_backward()          # the graph behind the memoised weights is being consumed (MeshHandler.weight_map)
-        flat = weight_map_bwd(grad_w, points, adj32, list(params))
+        flat = _call(weight_map_bwd, grad_w, points, adj32, list(params))
         return (None, None, None, None, None, *_carve(flat, [tuple(p.shape) for p in params]))
 
 
@@ -855,6 +1002,26 @@ def _segmax_backward(ctx, grad):
 segmax.register_autograd(_segmax_backward, setup_context=_segmax_setup)
 
 
+class _SegmaxFn(torch.autograd.Function):
+    """Same autograd as the registered one above, with the op bodies called directly in eager mode (_call)."""
+
+    @staticmethod
+    def forward(ctx, x, group, grp_ptr, grp_mem, n_out, act):
+        out = _call(segmax, x, group, grp_ptr, grp_mem, n_out, act)
+        ctx.save_for_backward(x, out, group, grp_ptr, grp_mem)
+        ctx.act = act
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, out, group, grp_ptr, grp_mem = ctx.saved_tensors
+        return _call(segmax_bwd, x, out, grad, group, grp_ptr, grp_mem, ctx.act), None, None, None, None, None
+
+
+def segmax_apply(x, group, grp_ptr, grp_mem, n_out, act=0):
+    return _SegmaxFn.apply(x, group, grp_ptr, grp_mem, n_out, act)
+
+
 class _GatherPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, index, grp_ptr, grp_mem, act):
@@ -863,12 +1030,12 @@ class _GatherPoolFn(torch.autograd.Function):
         else:
             ctx.save_for_backward(grp_ptr, grp_mem)
         ctx.n_coarse, ctx.act = x.shape[2], act
-        return gather_pool(x, index, act)
+        return _call(gather_pool, x, index, act)
 
     @staticmethod
     def backward(ctx, grad):
         grp_ptr, grp_mem, *rest = ctx.saved_tensors
-        return gather_pool_bwd(grad, grp_ptr, grp_mem, ctx.n_coarse, rest[0] if rest else None, ctx.act), None, None, None, None
+        return _call(gather_pool_bwd, grad, grp_ptr, grp_mem, ctx.n_coarse, rest[0] if rest else None, ctx.act), None, None, None, None
 
 
 def gather_pool_apply(x, index, grp_ptr, grp_mem, act=0):

@@ -455,3 +455,42 @@ def test_graphed_step_matches_eager(cuda_lib):
     assert relerr(y_g.cpu().numpy(), y_e.detach().cpu().numpy()) < 1e-6
     for a, p in zip(grads_g, params):
         assert relerr(a.cpu().numpy(), p.grad.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bias,same", [(True, True), (False, False)])
+def test_single_call_path_matches_composed_ops(bias, same):
+    """Small layers run as ONE C call per direction (ops.layer_forward / layer_backward -> csrc/layer.cu); the same
+    kernels as the composed ops: identical output and feature gradient, parameter gradients equal up to the
+    summation order of the per-pair backward's atomics."""
+    import pytorch_quadconv_b200 as q
+    from pytorch_quadconv_b200 import ops
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    n0 = 900
+    pts = torch.rand(n0, 2)
+    mesh = q.MeshHandler(pts).construct([n0, 0], mirror=True, quad_map="mfnus").to(dev)
+    n1 = mesh.point_seq[1]
+    layer = q.QuadConv(spatial_dim=2, in_points=n0, out_points=n0 if same else n1, in_channels=6, out_channels=10,
+                       filter_seq=[8, 8], output_same=same, bias=bias, decay_param=0.12).to(dev)
+    x = torch.randn(5, 6, n0, device=dev)
+    res = []
+    for limit in (64 << 20, 0):
+        ops.SINGLE_CALL_MAX_BYTES, saved = limit, ops.SINGLE_CALL_MAX_BYTES
+        try:
+            mesh.reset()
+            for p in list(layer.parameters()) + list(mesh.parameters()):
+                p.grad = None
+            xi = x.clone().requires_grad_()
+            y = layer(mesh, xi)
+            (y * torch.linspace(-1, 1, y.shape[2], device=dev)).sum().backward()
+            torch.cuda.synchronize()
+            res.append((y.detach().clone(), xi.grad.clone(),
+                        [p.grad.clone() for p in list(layer.parameters()) + list(mesh.parameters()) if p.grad is not None]))
+        finally:
+            ops.SINGLE_CALL_MAX_BYTES = saved
+    (y1, dx1, g1), (y0, dx0, g0) = res
+    assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
+    assert len(g1) == len(g0) and len(g1) >= 4
+    for a, b in zip(g1, g0):
+        assert float((a - b).norm()) <= 1e-6 * float(b.norm()) + 1e-12

@@ -49,6 +49,31 @@ def test_tcgen05_gemm_nt_3xtf32(cuda_lib, M, N, K, rpb):
     assert err < 2e-6, err
 
 
+@pytest.mark.parametrize("nb,Kb,M,N", [(3, 100, 200, 40), (8, 1000, 512, 64), (2, 77, 130, 70), (1, 5000, 1024, 64),
+                                        (5, 3922, 256, 7), (1, 1, 128, 1)])
+def test_tcgen05_gemm_tn_3xtf32(cuda_lib, nb, Kb, M, N):
+    """dW_last of the wide path (csrc/gemm_tc.cu, k_gemm_tn_tf32x3): D[n][m] = sum_{b,k} X[b][n][k] T[b*Kb+k][m] in
+    3xTF32 with T as the TMEM operand; ragged tiles, chunks that end inside a batch block, K splits, bounded
+    accumulation chains (Kb = 5000: 79 chunks per CTA set), and run-to-run bit reproducibility."""
+    from pytorch_quadconv_b200 import _cabi as C
+    g = torch.Generator().manual_seed(nb + Kb + M + N)
+    T = torch.randn(nb * Kb, M, generator=g).cuda()
+    X = torch.randn(nb, N, Kb, generator=g).cuda()
+    wsb = cuda_lib.qc_gemm_tn_workspace_bytes(nb, Kb, M, N)
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device="cuda")
+    outs = []
+    for _ in range(2):
+        D = torch.full((N, M), float("nan"), device="cuda")
+        C.check(cuda_lib.qc_gemm_tn_tf32x3(C.ptr(T), C.ptr(X), C.ptr(D), nb, Kb, M, N, C.ptr(ws), wsb, C.stream()),
+                "qc_gemm_tn_tf32x3")
+        torch.cuda.synchronize()
+        outs.append(D)
+    ref = X.double().permute(1, 0, 2).reshape(N, nb * Kb) @ T.double()
+    err = float((outs[0].double() - ref).norm() / ref.norm())
+    assert err < 2e-6, err
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_tcgen05_bf16_operand_majorness(cuda_lib):
     """Building block for a reduced-precision gather stage: with bf16 operands (kind::f16) the shared-memory
     operands may be MN-major (contiguous along M / N -- the order in which gathered feature rows arrive) as well
