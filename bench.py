@@ -105,9 +105,13 @@ def cpu_sample_config(w):
     return s
 
 
-def run_cpu_reference(w, steps, warmup):
+def run_cpu_reference(w, steps, warmup, gpu_twin=False):
     """`y = layer(mesh, x); y.sum().backward()` with the oracle's torch-CPU restatement of
-    quadconv.py:238-265 (same ATen ops and association order as the reference), all host threads."""
+    quadconv.py:238-265 (same ATen ops and association order as the reference), all host threads.
+    gpu_twin=True also times the SAME ATen composition on the SAME sample with the tensors on cuda:0 -- what a user
+    of the reference gets by calling `.cuda()` on it -- and reports it inside the record (`same_sample_aten_on_gpu`):
+    the like-for-like number next to the CPU one (the reference's formulation cannot run the full C3/C4 sizes on
+    either device: its [P,Ci,Co] filter tensor and [B,C,P] gathers are tens of GB)."""
     from oracle import quadconv_oracle as O
     s = cpu_sample_config(w)
     cores = os.cpu_count() or 1
@@ -134,7 +138,31 @@ def run_cpu_reference(w, steps, warmup):
     t = sum(times) / len(times)
     sample = (f"oracle port of quadconv.py:238-265 (+autograd) on N={s['N']} pts (same channels/batch/filter, "
               f"radius rescaled to keep ~{P / s['N']:.0f} neighbours/pt), P={P} pairs, {t:.2f} s/step")
-    return dict(value=P / t / 1e6, unit=UNIT, cores=cores, kind="port", sample=sample), t, P
+    rec = dict(value=P / t / 1e6, unit=UNIT, cores=cores, kind="port", sample=sample)
+    if gpu_twin and torch.cuda.is_available():
+        dev = torch.device("cuda:0")
+        g = lambda v: v.detach().to(dev).requires_grad_(v.requires_grad)
+        pts_g, x_g, qw_g, pairs_g = pts.to(dev), g(x), g(qw), pairs.to(dev)
+        ws_g = [g(v) for v in ws]
+
+        def gstep():
+            x_g.grad = None
+            O.quadconv_forward(pts_g, pts_g, qw_g, ws_g, x_g, pairs_g, s["ci"], s["co"], None, block_pairs=1 << 16).sum().backward()
+        for _ in range(3):
+            gstep()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            gstep()
+        e1.record()
+        torch.cuda.synchronize()
+        tg = e0.elapsed_time(e1) / 10 * 1e-3
+        rec["same_sample_aten_on_gpu"] = dict(value=P / tg / 1e6, unit=UNIT, ms_per_step=tg * 1e3,
+                                              note="the oracle's ATen composition (the reference's formulation: materialised "
+                                                   "[P,Ci,Co] filters, gather, bmm, scatter_add_) with its tensors on the B200, "
+                                                   "same sample; cuBLAS/ATen kernels, TF32 off")
+    return rec, t, P
 
 
 # --------------------------------------------------------------------------------------------
@@ -278,7 +306,7 @@ def time_kernels(w, mesh, layer, x, reps=5):
     from pytorch_quadconv_b200 import _cabi as C, ops
     L = C.lib()
     names = ["qc_pair_phi_fwd", "qc_pack_features", "qc_repack_wlast", "qc_contract", "qc_unpack_features",
-             "qc_batch_sum", "qc_dphi", "qc_pair_phi_bwd", "qc_unpack_dwlast", "qc_gather_accumulate", "qc_gather_dot", "qc_contract_mma", "qc_pack_features_bf16", "qc_dphi_mma", "qc_dw_mma"]
+             "qc_batch_sum", "qc_dphi", "qc_pair_phi_bwd", "qc_unpack_dwlast", "qc_gather_accumulate", "qc_gather_dot", "qc_contract_mma", "qc_pack_features_bf16", "qc_dphi_mma", "qc_dw_mma", "qc_gemm_nt_tf32x3", "qc_gemm_tn_tf32x3"]
     acc = {}
     orig = {n: getattr(L, n) for n in names}
     phase = {"bwd": False}
@@ -560,7 +588,7 @@ def run_ours(args, w, rank, local_rank, world, dev, sub=False, tc_table=False):
             json.dump({"workload": w["name"], "P": P, "ms_per_step": ms, "kernels_ms": table},
                       open(args.kernel_table, "w"), indent=1)
         if world == 1 and not args.no_cpu_baseline:
-            cb, _, _ = run_cpu_reference(w, 1, 1)
+            cb, _, _ = run_cpu_reference(w, 1, 1, gpu_twin=True)
 
     if rank == 0:
         launches = 0

@@ -23,6 +23,7 @@
 #include <cstdint>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -223,6 +224,213 @@ k_gemm_tf32x3(const GemmArgs g)
     if (warp == 0) tc::tmem_dealloc(tmem, 2 * BN);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// TMA-fed, warp-specialised version of the same GEMM (the default; the cp.async kernel above stays as the fallback
+// for hosts whose driver refuses the tensor maps and as the A/B baseline, QC_GEMM_NO_TMA=1).
+//
+// The loader above is per-thread: every thread copies its pieces, waits for them, derives the lo tile, and the CTA
+// meets at a __syncthreads per K chunk -- copy, split and MMA take turns (ncu: 1.2 TB/s of DRAM, tensor pipe 22 %).
+// Here the three roles run decoupled, handing stages over through mbarriers only:
+//     warp 8  (one lane)  TMA producer: cp.async.bulk.tensor.2d of the A box (128 rows x 32 k) and the B box (BN x 32 k)
+//                         per chunk into a TS-stage ring; the copy engine writes the 128-byte-swizzled K-major
+//                         layout the MMA descriptors expect and zero-fills ragged M / N / K edges
+//     warps 0-7           lo makers: lo = v - trunc_tf32(v) of the landed stage into a 2-stage lo ring (the raw tile IS
+//                         the hi operand); they also fold finished TMEM accumulation groups into fp32 registers
+//                         (bounded chains, see the truncation note at the top) and write the epilogue
+//     warp 9  (one lane)  MMA issuer: 12 kind::tf32 MMAs per chunk, tcgen05.commit frees the raw and lo stages
+constexpr int TS = 4;             // raw (= hi) stages filled by TMA
+constexpr int TL = 2;             // lo stages
+constexpr int TMA_THREADS = 320;  // 8 lo/epilogue warps + producer warp + MMA warp
+
+template <int BN>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+k_gemm_tf32x3_tma(const GemmArgs g, const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap)
+{
+    constexpr int A_TILE = 128 * GK;
+    constexpr int B_TILE = BN * GK;
+    constexpr int TILE = A_TILE + B_TILE;
+    constexpr int HN = BN / 2;
+    extern __shared__ __align__(1024) float smem_raw[];
+    float* raw_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* lo_s = raw_s + (size_t)TS * TILE;
+    __shared__ __align__(8) uint64_t full[TS], raw_free[TS], lo_full[TL], lo_free[TL], acc_full[2], acc_free[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const long long m0 = (long long)blockIdx.x * 128;
+    const int n0 = blockIdx.y * BN;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 2 * BN);
+    if (tid == 0) {
+        for (int i = 0; i < TS; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&raw_free[i], 1);
+        for (int i = 0; i < TL; ++i) tc::mbar_init(&lo_full[i], 256), tc::mbar_init(&lo_free[i], 1);
+        for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_free[i], 256);
+        tc::mbar_fence_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const int nk = (g.K + GK - 1) / GK;
+    const int ngroups = (nk + GROUP - 1) / GROUP;
+
+    if (warp == 8) {
+        // ---- TMA producer ------------------------------------------------------------------------------------
+        if (lane == 0) {
+            tma::prefetch_map(&amap);
+            tma::prefetch_map(&bmap);
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % TS;
+                if (kc >= TS) tc::mbar_wait(&raw_free[s], ((kc / TS) - 1) & 1);
+                tma::mbar_arrive_expect_tx(&full[s], TILE * 4);
+                const uint32_t dst = tc::smem_u32(raw_s + (size_t)s * TILE);
+                tma::load_2d(dst, &amap, &full[s], kc * GK, (int)m0);
+                tma::load_2d(dst + A_TILE * 4, &bmap, &full[s], kc * GK, n0);
+            }
+        }
+    } else if (warp == 9) {
+        // ---- MMA issuer ----------------------------------------------------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_tf32(128, BN);
+            constexpr uint32_t SBO = 1024;
+            constexpr uint64_t SW128 = (uint64_t)2 << 61;
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % TS, l = kc % TL, gi = kc / GROUP;
+                if (kc % GROUP == 0 && gi >= 2) tc::mbar_wait(&acc_free[gi & 1], ((gi >> 1) - 1) & 1);   // group gi-2 has been read out
+                tc::mbar_wait(&full[s], (kc / TS) & 1);
+                tc::mbar_wait(&lo_full[l], (kc / TL) & 1);
+                tc::fence_after_sync();
+                const uint32_t ahi = tc::smem_u32(raw_s + (size_t)s * TILE), bhi = ahi + A_TILE * 4;
+                const uint32_t alo = tc::smem_u32(lo_s + (size_t)l * TILE), blo = alo + A_TILE * 4;
+                const uint32_t d = tmem + (gi & 1) * BN;
+#pragma unroll
+                for (int ks = 0; ks < GK / 8; ++ks) {
+                    const uint64_t dah = tc::make_smem_desc(ahi + ks * 32, 16, SBO) | SW128;
+                    const uint64_t dal = tc::make_smem_desc(alo + ks * 32, 16, SBO) | SW128;
+                    const uint64_t dbh = tc::make_smem_desc(bhi + ks * 32, 16, SBO) | SW128;
+                    const uint64_t dbl = tc::make_smem_desc(blo + ks * 32, 16, SBO) | SW128;
+                    tc::mma_tf32_ss(d, dah, dbh, idesc, !(kc % GROUP == 0 && ks == 0));
+                    tc::mma_tf32_ss(d, dal, dbh, idesc, true);
+                    tc::mma_tf32_ss(d, dah, dbl, idesc, true);
+                }
+                tc::mma_commit(&raw_free[s]);
+                tc::mma_commit(&lo_free[l]);
+                if (kc % GROUP == GROUP - 1 || kc == nk - 1) tc::mma_commit(&acc_full[gi & 1]);
+            }
+        }
+    } else {
+        // ---- lo makers + accumulation + epilogue (warps 0-7) -------------------------------------------------------
+        const int wq = warp & 3, wh = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+        float acc[HN];
+#pragma unroll
+        for (int j = 0; j < HN; ++j) acc[j] = 0.f;
+        auto take_group = [&](int gi) {
+            tc::mbar_wait(&acc_full[gi & 1], (gi >> 1) & 1);
+            tc::fence_after_sync();
+#pragma unroll
+            for (int c = 0; c < HN / 16; ++c) {
+                uint32_t r[16];
+                tc::tmem_ld16(lane_base + tmem + (gi & 1) * BN + wh * HN + c * 16, r);
+                tc::wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[c * 16 + j] += __uint_as_float(r[j]);
+            }
+            tc::fence_before_sync();
+            tc::mbar_arrive(&acc_free[gi & 1]);
+        };
+        int gread = 0;
+        for (int kc = 0; kc < nk; ++kc) {
+            const int s = kc % TS, l = kc % TL;
+            tc::mbar_wait(&full[s], (kc / TS) & 1);
+            if (kc >= TL) tc::mbar_wait(&lo_free[l], ((kc / TL) - 1) & 1);
+            const float4* rs = reinterpret_cast<const float4*>(raw_s + (size_t)s * TILE);
+            float4* ls = reinterpret_cast<float4*>(lo_s + (size_t)l * TILE);
+#pragma unroll
+            for (int j = 0; j < TILE / 4 / 256; ++j) {        // elementwise on the landed bytes: the swizzle does not matter
+                const float4 v = rs[tid + 256 * j];
+                float4 o;
+                o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                ls[tid + 256 * j] = o;
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(&lo_full[l]);
+            // a finished group moves to registers two chunks into the next one (its MMAs retired long ago)
+            const int gi = kc / GROUP;
+            if (kc % GROUP == GROUP / 2 && gi >= 1) {
+                take_group(gi - 1);
+                gread = gi;
+            }
+        }
+        for (int gi = gread; gi < ngroups; ++gi) take_group(gi);
+
+        const long long m = m0 + wq * 32 + lane;
+        const int nb = n0 + wh * HN;
+        if (m < g.M) {
+            if (g.rows_per_batch > 0) {
+                const long long bb = m / g.rows_per_batch, o = m % g.rows_per_batch;
+                float* dst = g.D + bb * g.N * g.rows_per_batch + o;
+#pragma unroll
+                for (int j = 0; j < HN; ++j)
+                    if (nb + j < g.N) dst[(long long)(nb + j) * g.rows_per_batch] = acc[j];
+            }
+        }
+        if (g.rows_per_batch == 0) {
+            // row-major output: a thread holds HN columns of ONE row, so direct stores would put 16 bytes into each of
+            // 32 rows per instruction.  The tile goes through shared memory (the operand ring is free: every MMA has
+            // retired) and leaves as whole rows, 512 contiguous bytes per warp instruction.
+            constexpr int LD = BN + 4;                 // row pitch in floats: quarter-warps hit distinct banks
+            float* stg = raw_s;
+            float* srow = stg + (size_t)(wq * 32 + lane) * LD + wh * HN;
+#pragma unroll
+            for (int q4 = 0; q4 < HN / 4; ++q4)
+                *reinterpret_cast<float4*>(srow + 4 * q4) = make_float4(acc[4 * q4], acc[4 * q4 + 1], acc[4 * q4 + 2], acc[4 * q4 + 3]);
+            tc::named_bar_sync(1, 256);
+            constexpr int LPR = BN / 4;                // lanes per row (float4 each)
+            constexpr int RPI = 32 / LPR;              // rows per warp instruction
+            const int c4 = (lane % LPR) * 4, rsub = lane / LPR;
+            const bool vec = (g.N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.D) & 15) == 0;
+            for (int r = warp * RPI + rsub; r < 128; r += 8 * RPI) {
+                const long long mr = m0 + r;
+                if (mr >= g.M || n0 + c4 >= g.N) continue;
+                const float4 v = *reinterpret_cast<const float4*>(stg + (size_t)r * LD + c4);
+                float* dst = g.D + mr * g.N + n0 + c4;
+                if (vec) {
+                    *reinterpret_cast<float4*>(dst) = v;
+                } else {
+                    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (n0 + c4 + k < g.N) dst[k] = e[k];
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 2 * BN);
+}
+
+template <int BN>
+int launch_gemm_tma(const GemmArgs& g, cudaStream_t st)
+{
+    if (g.M > 2147483647LL) return QC_EUNSUP;
+    CUtensorMap amap, bmap;
+    if (!tma::make_map_2d(&amap, g.A, 4, (uint64_t)g.M, (uint64_t)g.K, GK, 128)) return QC_EUNSUP;
+    if (!tma::make_map_2d(&bmap, g.B, 4, (uint64_t)g.N, (uint64_t)g.K, GK, BN)) return QC_EUNSUP;
+    const size_t smem = (size_t)(TS + TL) * (128 * GK + BN * GK) * 4 + 1024;
+    QC_CUDA((qc_set_max_smem<k_gemm_tf32x3_tma<BN>>((int)smem)));
+    const long long mt = (g.M + 127) / 128;
+    const int nt = (g.N + BN - 1) / BN;
+    if (nt > 65535) return QC_EUNSUP;
+    k_gemm_tf32x3_tma<BN><<<dim3((unsigned)mt, (unsigned)nt), TMA_THREADS, smem, st>>>(g, amap, bmap);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
 template <int BN>
 int launch_gemm(const GemmArgs& g, cudaStream_t st)
 {
@@ -247,6 +455,10 @@ extern "C" int qc_gemm_nt_tf32x3(const float* A, const float* B, float* D, long 
     if (rows_per_batch > 0 && M % rows_per_batch != 0) return QC_EINVAL;
     GemmArgs g{A, B, D, M, N, K, rows_per_batch};
     cudaStream_t st = (cudaStream_t)stream;
+    if (getenv("QC_GEMM_NO_TMA") == nullptr) {   // read per call: the tests toggle it (these are large launches)
+        const int rc = N <= 64 ? launch_gemm_tma<64>(g, st) : launch_gemm_tma<128>(g, st);
+        if (rc != QC_EUNSUP) return rc;       // tensor map refused (driver / stride): the cp.async kernel serves it
+    }
     return N <= 64 ? launch_gemm<64>(g, st) : launch_gemm<128>(g, st);
 }
 
@@ -433,6 +645,211 @@ k_gemm_tn_tf32x3(const TnArgs g)
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+// TMA-staged version of the TN GEMM (the default when M % 4 == 0; the kernel above is the fallback).  The register
+// loads above leave ~40 KB in flight per SM and make each set wait out the full DRAM latency per chunk (1.8 TB/s
+// measured).  Here a producer lane keeps TST chunks of T (32 KB each: four 32-column x 64-row boxes, 128-byte swizzle)
+// in flight with cp.async.bulk.tensor.2d, and the two consumer sets (chunks alternate between them, as above) read
+// their column of the landed stage from shared memory (lane = column: every warp instruction is one 128-byte line,
+// conflict free).  X arrives in 16-byte pieces when Kb % 4 == 0 (X16), 4-byte pieces otherwise.
+constexpr int TST = 3;             // T stages in flight
+constexpr int TN2_THREADS = 288;   // 2 consumer sets of 4 warps + the producer warp
+
+template <bool X16>
+__global__ void __launch_bounds__(TN2_THREADS, 1)
+k_gemm_tn_tf32x3_tma(const TnArgs g, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(1024) float smem_raw[];
+    float* ts = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // [TST][4 boxes][64 x 32]
+    float* xs = ts + (size_t)TST * TK * 128;                                                                   // [set][stage][hi, lo][XS_TILE]
+    __shared__ __align__(8) uint64_t t_full[TST], t_free[TST], bars[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.z * TBN;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        for (int i = 0; i < TST; ++i) tc::mbar_init(&t_full[i], 1), tc::mbar_init(&t_free[i], 128);
+        tc::mbar_init(&bars[0], 1);
+        tc::mbar_init(&bars[1], 1);
+        tc::mbar_fence_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const int cbeg = blockIdx.y * g.cps, cend = min(cbeg + g.cps, g.nchunks);
+    const int ntot = max(cend - cbeg, 0);
+    float* red = xs;                       // [TBN][128] hand-off of set 1's sums (after every MMA has retired)
+    float acc[TBN];
+    const int set = (warp >> 2) & 1, wq = warp & 3;
+    const int m = m0 + wq * 32 + lane;
+    const bool mvalid = m < g.M;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            tma::prefetch_map(&tmap);
+            for (int it = 0; it < ntot; ++it) {
+                const int s = it % TST, c = cbeg + it;
+                const int b = c / g.cpb, kk0 = (c % g.cpb) * TK;
+                if (it >= TST) tc::mbar_wait(&t_free[s], ((it / TST) - 1) & 1);
+                tma::mbar_arrive_expect_tx(&t_full[s], TK * 128 * 4);
+                const uint32_t dst = tc::smem_u32(ts + (size_t)s * TK * 128);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tma::load_2d(dst + q * (TK * 128), &tmap, &t_full[s], m0 + 32 * q, b * g.Kb + kk0);
+            }
+        }
+    } else {
+        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+        const uint32_t a_hi = tmem + set * 192, a_lo = a_hi + TK, d_acc = a_hi + 2 * TK;
+        const uint32_t idesc = tc::make_idesc_tf32(128, TBN);
+        constexpr uint64_t SW128 = (uint64_t)2 << 61;
+        const int nit = (ntot - set + 1) / 2;                  // this set's chunks: cbeg + set + 2 i
+        float* xset = xs + (size_t)set * 4 * XS_TILE;
+        const int ts_tid = wq * 32 + lane;                     // thread index inside the set
+
+        // X tile of this set's chunk i: 64 rows x 64 k, K-major, 128-byte swizzle (two 32-k sub-tiles)
+        auto issue_x = [&](int i) {
+            const int c = cbeg + set + 2 * i;
+            const int b = c / g.cpb, kk0 = (c % g.cpb) * TK;
+            const uint32_t st = tc::smem_u32(xset + (size_t)(i & 1) * 2 * XS_TILE);
+            const float* xb = g.X + ((long long)b * g.N + n0) * g.Kb + kk0;
+            if (X16) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int p = ts_tid + 128 * j, nl = p >> 4, q16 = p & 15, kt = q16 >> 3, q = q16 & 7;
+                    const bool v = n0 + nl < g.N && kk0 + 4 * q16 < g.Kb;
+                    const uint32_t off = (uint32_t)(kt * (TBN * 128) + (nl >> 3) * 1024 + (nl & 7) * 128 + ((q ^ (nl & 7)) << 4));
+                    tc::cp_async16_zfill(st + off, v ? xb + (long long)nl * g.Kb + 4 * q16 : g.X, v);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int nl = wq * 16 + (j >> 1), kt = j & 1, k = kt * 32 + lane;
+                    const bool v = n0 + nl < g.N && kk0 + k < g.Kb;
+                    const uint32_t off = (uint32_t)(kt * (TBN * 128) + (nl >> 3) * 1024 + (nl & 7) * 128 + (((lane >> 2) ^ (nl & 7)) * 16) + (lane & 3) * 4);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(st + off), "l"(v ? xb + (long long)nl * g.Kb + k : g.X), "r"(v ? 4 : 0) : "memory");
+                }
+            }
+        };
+        auto make_lo = [&](int i) {          // every thread splits exactly the pieces it copied
+            float* hs = xset + (size_t)(i & 1) * 2 * XS_TILE;
+            float* ls = hs + XS_TILE;
+            if (X16) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int p = ts_tid + 128 * j, nl = p >> 4, q16 = p & 15, kt = q16 >> 3, q = q16 & 7;
+                    const uint32_t o = (uint32_t)(kt * (TBN * 128) + (nl >> 3) * 1024 + (nl & 7) * 128 + ((q ^ (nl & 7)) << 4)) / 4;
+                    const float4 v = *reinterpret_cast<const float4*>(hs + o);
+                    float4 l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                    *reinterpret_cast<float4*>(ls + o) = l;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int nl = wq * 16 + (j >> 1), kt = j & 1;
+                    const uint32_t o = (uint32_t)(kt * (TBN * 128) + (nl >> 3) * 1024 + (nl & 7) * 128 + (((lane >> 2) ^ (nl & 7)) * 16) + (lane & 3) * 4) / 4;
+                    const float v = hs[o];
+                    ls[o] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                }
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < TBN; ++j) acc[j] = 0.f;
+        auto take = [&]() {            // acc += D (the chain's MMAs have finished)
+            tc::fence_after_sync();
+#pragma unroll
+            for (int c = 0; c < TBN / 16; ++c) {
+                uint32_t r[16];
+                tc::tmem_ld16(lane_base + d_acc + c * 16, r);
+                tc::wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[c * 16 + j] += __uint_as_float(r[j]);
+            }
+        };
+
+        if (nit > 0) issue_x(0);
+        tc::cp_async_commit();
+        for (int i = 0; i < nit; ++i) {
+            const int it = set + 2 * i, s = it % TST;
+            const int kk0 = ((cbeg + it) % g.cpb) * TK;
+            tc::mbar_wait(&t_full[s], (it / TST) & 1);
+            // this thread's column of the landed chunk: 64 rows, swizzled 128-byte lines
+            float v[TK];
+            const float* col = ts + (size_t)s * TK * 128 + wq * (TK * 32);
+            const bool full = mvalid && kk0 + TK <= g.Kb;
+#pragma unroll
+            for (int t = 0; t < TK; ++t) {
+                const float x = col[t * 32 + ((((lane >> 2) ^ (t & 7)) << 2) | (lane & 3))];
+                v[t] = (full || (mvalid && kk0 + t < g.Kb)) ? x : 0.f;
+            }
+            // the previous chunk's MMAs of this set have read the A operand in TMEM and X stage (i+1)&1
+            if (i > 0) tc::mbar_wait(&bars[set], (i - 1) & 1);
+            if (i > 0 && i % TN_GROUP == 0) take();
+            if (i + 1 < nit) issue_x(i + 1);
+            tc::cp_async_commit();
+            tc::cp_async_wait<1>();
+            make_lo(i);
+#pragma unroll
+            for (int cc = 0; cc < TK / 16; ++cc) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float x = v[cc * 16 + j];
+                    const float hv = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+                    hi[j] = __float_as_uint(hv);
+                    lo[j] = __float_as_uint(x - hv);
+                }
+                tc::tmem_st16(lane_base + a_hi + cc * 16, hi);
+                tc::tmem_st16(lane_base + a_lo + cc * 16, lo);
+            }
+            tc::wait_st();
+            tc::mbar_arrive(&t_free[s]);                   // this thread's column of the stage has left shared memory
+            tc::fence_proxy_async();
+            tc::fence_before_sync();
+            tc::named_bar_sync(1 + set, 128);
+            if (wq == 0 && lane == 0) {
+                tc::fence_after_sync();
+                const uint32_t bhi = tc::smem_u32(xset + (size_t)(i & 1) * 2 * XS_TILE), blo = bhi + XS_TILE * 4;
+#pragma unroll
+                for (int ks = 0; ks < TK / 8; ++ks) {
+                    const uint32_t o = (uint32_t)((ks >> 2) * (TBN * 128) + (ks & 3) * 32);
+                    const uint64_t dh = tc::make_smem_desc(bhi + o, 16, 1024) | SW128;
+                    const uint64_t dl = tc::make_smem_desc(blo + o, 16, 1024) | SW128;
+                    tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dh, idesc, !(i % TN_GROUP == 0 && ks == 0));
+                    tc::mma_tf32_ts(d_acc, a_lo + ks * 8, dh, idesc, true);
+                    tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dl, idesc, true);
+                }
+                tc::mma_commit(&bars[set]);
+            }
+        }
+        if (nit > 0) {
+            tc::mbar_wait(&bars[set], (nit - 1) & 1);
+            take();
+        }
+    }
+    // set 1 hands its sums to set 0 through shared memory (every MMA has retired: the X tiles are free)
+    tc::fence_before_sync();
+    __syncthreads();
+    const int row = wq * 32 + lane;
+    if (warp >= 4 && warp < 8) {
+#pragma unroll
+        for (int j = 0; j < TBN; ++j) red[j * 128 + row] = acc[j];
+    }
+    __syncthreads();
+    if (warp < 4 && mvalid) {
+        float* dst = g.out + (size_t)blockIdx.y * g.N * g.M + m;
+#pragma unroll
+        for (int j = 0; j < TBN; ++j)
+            if (n0 + j < g.N) dst[(size_t)(n0 + j) * g.M] = acc[j] + red[j * 128 + row];
+    }
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 __global__ void k_sum_slices(const float* __restrict__ part, int S, long long n, float* __restrict__ D)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -448,7 +865,7 @@ int tn_splits(int tiles, int nchunks)
     const int sms = qc_num_sms();
     int best = 1;
     double best_eff = 0.0;
-    for (int S = 1; S <= 64 && (S == 1 || nchunks / S >= 8); ++S) {
+    for (int S = 1; S <= 160 && (S == 1 || nchunks / S >= 8); ++S) {
         const int ctas = tiles * S;
         const double eff = (double)ctas / ((double)((ctas + sms - 1) / sms) * sms);
         if (eff > best_eff + 1e-9) { best_eff = eff; best = S; }
@@ -481,7 +898,21 @@ extern "C" int qc_gemm_tn_tf32x3(const float* T, const float* X, float* D, int n
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)2 * 2 * 2 * XS_TILE * 4 + 1024;
     QC_CUDA((qc_set_max_smem<k_gemm_tn_tf32x3>((int)smem)));
-    k_gemm_tn_tf32x3<<<dim3((unsigned)mt, (unsigned)S, (unsigned)nt), TN_THREADS, smem, st>>>(g);
+    CUtensorMap tmap;
+    if (getenv("QC_GEMM_NO_TMA") == nullptr && (M & 3) == 0 && (reinterpret_cast<uintptr_t>(T) & 15) == 0 &&
+        (long long)nb * Kb <= 2147483647LL && tma::make_map_2d(&tmap, T, 4, (uint64_t)nb * Kb, (uint64_t)M, 32, TK)) {
+        const size_t smem2 = (size_t)TST * TK * 128 * 4 + (size_t)2 * 2 * 2 * XS_TILE * 4 + 1024;
+        const bool x16 = (Kb & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+        if (x16) {
+            QC_CUDA((qc_set_max_smem<k_gemm_tn_tf32x3_tma<true>>((int)smem2)));
+            k_gemm_tn_tf32x3_tma<true><<<dim3((unsigned)mt, (unsigned)S, (unsigned)nt), TN2_THREADS, smem2, st>>>(g, tmap);
+        } else {
+            QC_CUDA((qc_set_max_smem<k_gemm_tn_tf32x3_tma<false>>((int)smem2)));
+            k_gemm_tn_tf32x3_tma<false><<<dim3((unsigned)mt, (unsigned)S, (unsigned)nt), TN2_THREADS, smem2, st>>>(g, tmap);
+        }
+    } else {
+        k_gemm_tn_tf32x3<<<dim3((unsigned)mt, (unsigned)S, (unsigned)nt), TN_THREADS, smem, st>>>(g);
+    }
     QC_CHECK_LAUNCH();
     if (S > 1) {
         const long long n = (long long)N * M;

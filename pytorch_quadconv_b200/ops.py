@@ -838,8 +838,53 @@ class _QuadConvFn(torch.autograd.Function):
         return (d_features, d_quad_w, d_w_last, d_bias if has_bias else None, None, None, *d_hidden)
 
 
+# ---- batch folding for layers with few channels ------------------------------------------------
+# The per-pair overhead of the fused kernels (pair index, phi row, gather address, loop control) is paid once per
+# (pair, batch lane) and amortised over the channels a lane owns: a 4 -> 8 channel layer runs at a quarter of the
+# per-FLOP rate of a 32 -> 32 one, and with batch 256 it walks the pair list eight times (one pass per block of 32
+# lanes).  A layer with few channels and a large batch is therefore evaluated as the EQUIVALENT layer with `s` batch
+# entries folded into the channel axis:
+#     x [B, Ci, N] viewed as [B/s, s*Ci, N]  (free),   W_last' = I_s (x) W_last  (block diagonal, [(s,i),(s',j),h]),
+#     out' [B/s, s*Co, N] viewed as [B, Co, N]  (free).
+# Stage B (the gather, 60 % of the work) does exactly the same sums per (batch entry, channel) with s times fewer lanes;
+# the dense stages multiply by the zero blocks as well, which the tensor cores absorb.  Values are unchanged up to the
+# summation order of d W_last over the s diagonal blocks.  FOLD_MIN_BATCH = the smallest folded batch (lanes per point).
+FOLD_MAX_CHANNELS = 32
+FOLD_MIN_BATCH = 32
+_EYES = {}
+
+
+def fold_factor(B: int, Ci: int, Co: int, H: int) -> int:
+    if H > 8 or FOLD_MIN_BATCH <= 0:
+        return 1
+    f = 1
+    while 2 * f * max(Ci, Co) <= FOLD_MAX_CHANNELS and B % (2 * f) == 0 and B // (2 * f) >= FOLD_MIN_BATCH:
+        f *= 2
+    return f
+
+
+def _eye(f: int, device) -> Tensor:
+    key = (f, str(device))
+    e = _EYES.get(key)
+    if e is None:
+        e = _EYES[key] = torch.eye(f, device=device, dtype=torch.float32).view(f, 1, f, 1, 1)
+    return e
+
+
 def quadconv_apply(features, quad_w, hidden_ws, w_last, bias, tables, in_channels, out_channels, mlp_bf16=False,
                    tc=None):
+    B, Ci, Co, H = features.shape[0], in_channels, out_channels, w_last.shape[1]
+    f = 1
+    if tc is None and not mlp_bf16 and features.dim() == 3 and features.shape[1] == Ci and features.dtype == torch.float32:
+        f = fold_factor(B, Ci, Co, H)
+    if f > 1:
+        N = features.shape[2]
+        No = tables[0].shape[0]
+        xf = features.contiguous().view(B // f, f * Ci, N)
+        wf = (_eye(f, w_last.device) * w_last.view(1, Ci, 1, Co, H)).view(f * Ci * f * Co, H)
+        bf = bias.repeat(1, f, 1) if bias is not None else None
+        out = _QuadConvFn.apply(xf, quad_w, wf, bf, tables, (f * Ci, f * Co, False, None), *hidden_ws)
+        return out.view(B, Co, No)
     return _QuadConvFn.apply(features, quad_w, w_last, bias, tables,
                              (in_channels, out_channels, bool(mlp_bf16), tc), *hidden_ws)
 

@@ -493,4 +493,46 @@ def test_single_call_path_matches_composed_ops(bias, same):
     assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
     assert len(g1) == len(g0) and len(g1) >= 4
     for a, b in zip(g1, g0):
-        assert float((a - b).norm()) <= 1e-6 * float(b.norm()) + 1e-12
+        assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-12   # float atomics in the per-pair backward: order-dependent rounding
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,ci,co,min_batch,expect", [(64, 4, 8, 32, 2), (64, 4, 8, 8, 4), (96, 3, 5, 8, 4), (32, 16, 16, 8, 2),
+                                                      (48, 32, 8, 8, 1)])
+def test_batch_folding_matches_unfolded_layer(B, ci, co, min_batch, expect):
+    """Few-channel layers with a large batch are evaluated with batch entries folded into the channel axis
+    (ops.quadconv_apply: x viewed as [B/s, s*Ci, N], W_last' = I_s (x) W_last).  Same layer: output, feature gradient and
+    every parameter gradient agree with the unfolded evaluation to rounding."""
+    import pytorch_quadconv_b200 as q
+    from pytorch_quadconv_b200 import ops
+    torch.manual_seed(11)
+    dev = torch.device("cuda:0")
+    n = 700
+    pts = torch.rand(n, 2)
+    mesh = q.MeshHandler(pts).construct([n]).to(dev)
+    layer = q.QuadConv(spatial_dim=2, in_points=n, out_points=n, in_channels=ci, out_channels=co, filter_seq=[8, 8],
+                       output_same=True, bias=True, decay_param=0.1).to(dev)
+    x = torch.randn(B, ci, n, device=dev)
+    wgt = torch.randn(B, co, n, device=dev)
+    saved = ops.FOLD_MIN_BATCH
+    res = []
+    try:
+        for mb in (min_batch, 0):
+            ops.FOLD_MIN_BATCH = mb
+            assert ops.fold_factor(B, ci, co, 8) == (expect if mb else 1)
+            mesh.reset()
+            ps = list(layer.parameters()) + list(mesh.parameters())
+            for p in ps:
+                p.grad = None
+            xi = x.clone().requires_grad_()
+            y = layer(mesh, xi)
+            (y * wgt).sum().backward()
+            torch.cuda.synchronize()
+            res.append((y.detach().clone(), xi.grad.clone(), [p.grad.clone() for p in ps if p.grad is not None]))
+    finally:
+        ops.FOLD_MIN_BATCH = saved
+    (y1, dx1, g1), (y0, dx0, g0) = res
+    assert relerr(y1.cpu(), y0.cpu()) < 1e-6 and relerr(dx1.cpu(), dx0.cpu()) < 1e-6
+    assert len(g1) == len(g0) >= 4
+    for a, b in zip(g1, g0):
+        assert a.shape == b.shape and relerr(a.cpu(), b.cpu()) < 2e-6

@@ -31,11 +31,16 @@ def test_tcgen05_3xtf32_gemm(cuda_lib):
 
 
 @pytest.mark.parametrize("M,N,K,rpb", [(1000, 40, 68, 0), (1000, 40, 68, 250), (384, 128, 2048, 128), (700, 200, 128, 0),
-                                       (130, 64, 36, 65), (50, 7, 4, 0)])
-def test_tcgen05_gemm_nt_3xtf32(cuda_lib, M, N, K, rpb):
+                                       (130, 64, 36, 65), (50, 7, 4, 0), (4000, 128, 1024, 0)])
+@pytest.mark.parametrize("loader", ["tma", "cp_async"])
+def test_tcgen05_gemm_nt_3xtf32(cuda_lib, M, N, K, rpb, loader, monkeypatch):
     """Dense stage of the wide path (csrc/gemm_tc.cu): D = A * B^T in 3xTF32, row-major or per-batch transposed
-    output, ragged M / N / K tiles."""
+    output, ragged M / N / K tiles; the TMA-fed warp-specialised kernel (default) and the cp.async kernel (fallback)."""
     from pytorch_quadconv_b200 import _cabi as C
+    if loader == "cp_async":
+        monkeypatch.setenv("QC_GEMM_NO_TMA", "1")
+    else:
+        monkeypatch.delenv("QC_GEMM_NO_TMA", raising=False)
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g).cuda()
     B = torch.randn(N, K, generator=g).cuda()
@@ -51,11 +56,16 @@ def test_tcgen05_gemm_nt_3xtf32(cuda_lib, M, N, K, rpb):
 
 @pytest.mark.parametrize("nb,Kb,M,N", [(3, 100, 200, 40), (8, 1000, 512, 64), (2, 77, 130, 70), (1, 5000, 1024, 64),
                                         (5, 3922, 256, 7), (1, 1, 128, 1)])
-def test_tcgen05_gemm_tn_3xtf32(cuda_lib, nb, Kb, M, N):
+@pytest.mark.parametrize("loader", ["tma", "registers"])
+def test_tcgen05_gemm_tn_3xtf32(cuda_lib, nb, Kb, M, N, loader, monkeypatch):
     """dW_last of the wide path (csrc/gemm_tc.cu, k_gemm_tn_tf32x3): D[n][m] = sum_{b,k} X[b][n][k] T[b*Kb+k][m] in
     3xTF32 with T as the TMEM operand; ragged tiles, chunks that end inside a batch block, K splits, bounded
     accumulation chains (Kb = 5000: 79 chunks per CTA set), and run-to-run bit reproducibility."""
     from pytorch_quadconv_b200 import _cabi as C
+    if loader == "registers":
+        monkeypatch.setenv("QC_GEMM_NO_TMA", "1")       # the register-loading kernel (also the fallback for M % 4 != 0)
+    else:
+        monkeypatch.delenv("QC_GEMM_NO_TMA", raising=False)
     g = torch.Generator().manual_seed(nb + Kb + M + N)
     T = torch.randn(nb * Kb, M, generator=g).cuda()
     X = torch.randn(nb, N, Kb, generator=g).cuda()
