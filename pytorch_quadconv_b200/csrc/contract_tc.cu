@@ -260,11 +260,21 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_nslots, const in
                 tc::cp_async_wait<D - 1>();
                 load(cur, 0, 0);
                 for (int it = 0; it < cmax; it += D) {
+                    // the source indices of the D pairs issued in this round: ONE 128-bit load a whole round ahead of
+                    // their use (the shared-memory pipe is ~50 % busy; a per-pair LDS.32 issued one FMA block ahead of
+                    // its address computation was the top stall of the kernel)
+                    unsigned unv[D];
+                    if constexpr (D == 4) {
+                        const uint4 q4 = tc::lds_u128_early(my_idx_sa + (it + D) * 4);      // past the list they are unused
+                        unv[0] = q4.x, unv[1] = q4.y, unv[2] = q4.z, unv[3] = q4.w;
+                    }
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
                         tc::cp_async_wait<D - 2>();       // the group of pair it+d+1 (slot d+1) has landed
                         load(nxt, (d + 1) % D, it + d + 1);
-                        const unsigned un = tc::lds_u32_early(my_idx_sa + (it + d + D) * 4);   // past the list it is unused
+                        unsigned un;
+                        if constexpr (D == 4) un = unv[d];
+                        else un = tc::lds_u32_early(my_idx_sa + (it + d + D) * 4);   // past the list it is unused
                         if (it + d < clen) {
                             fma(cur);
                             if (it + d + D < clen) issue_u(d, un);
@@ -743,6 +753,11 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                     const float* own_p = my_ring_p + up * (NG * 128);
                     const float* oth_p = my_ring_p + (1 - up) * (NG * 128);
                     for (int it = 0; it < cmax; it += D) {
+                        unsigned unv[D];                          // source indices of this round's issues, one LDS.128 (see k_contract_tc)
+                        if constexpr (D == 4) {
+                            const uint4 q4 = tc::lds_u128_early(my_idx_sa + (it + D) * 4);
+                            unv[0] = q4.x, unv[1] = q4.y, unv[2] = q4.z, unv[3] = q4.w;
+                        }
 #pragma unroll
                         for (int d = 0; d < D; d += 2) {
                             tc::cp_async_wait<D - 2>();       // slots d and d+1 have landed
@@ -754,7 +769,12 @@ k_dphi_tc(const DphiArgs a, const int nkc, const size_t slice_stride)
                                     xa[q] = *reinterpret_cast<const float4*>(own_p + (d * NG + q) * 128);
                                     xb[q] = *reinterpret_cast<const float4*>(oth_p + (d * NG + q) * 128);
                                 }
-                                const unsigned u0 = tc::lds_u32_early(my_idx_sa + (it + d + D) * 4), u1 = tc::lds_u32_early(my_idx_sa + (it + d + 1 + D) * 4);
+                                unsigned u0, u1;
+                                if constexpr (D == 4) {
+                                    u0 = unv[d], u1 = unv[d + 1];
+                                } else {
+                                    u0 = tc::lds_u32_early(my_idx_sa + (it + d + D) * 4), u1 = tc::lds_u32_early(my_idx_sa + (it + d + 1 + D) * 4);
+                                }
                                 float acc0[HP], acc1[HP];
 #pragma unroll
                                 for (int h = 0; h < HP; ++h) acc0[h] = 0.f, acc1[h] = 0.f;

@@ -219,6 +219,14 @@ __device__ __forceinline__ uint32_t lds_u32_early(uint32_t saddr)
     return v;
 }
 
+// four consecutive 32-bit words with one LDS.128 (16-byte aligned address), same no-sinking property
+__device__ __forceinline__ uint4 lds_u128_early(uint32_t saddr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");

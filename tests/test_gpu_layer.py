@@ -532,7 +532,9 @@ def test_batch_folding_matches_unfolded_layer(B, ci, co, min_batch, expect):
     finally:
         ops.FOLD_MIN_BATCH = saved
     (y1, dx1, g1), (y0, dx0, g0) = res
-    assert relerr(y1.cpu(), y0.cpu()) < 1e-6 and relerr(dx1.cpu(), dx0.cpu()) < 1e-6
+    # (a folded shape may be served by another kernel family -- 3xTF32 dense stage vs the FP32-pipe one: ~1e-6 apart)
+    assert relerr(y1.cpu(), y0.cpu()) < 5e-6 and relerr(dx1.cpu(), dx0.cpu()) < 5e-6
     assert len(g1) == len(g0) >= 4
     for a, b in zip(g1, g0):
-        assert a.shape == b.shape and relerr(a.cpu(), b.cpu()) < 2e-6
+        # d W_last accumulates in TMEM (truncating adds, bounded chains: ~2-4e-6 each way): parity bound
+        assert a.shape == b.shape and relerr(a.cpu(), b.cpu()) < 1e-5
