@@ -11,6 +11,7 @@
 // registers.  sinf/cosf are the accurate versions (no fast-math) to hold the 1e-5 fp32 bound.
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -82,6 +83,140 @@ k_pair_phi_fwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
             if (h < HP) dst[h] = h < H ? wq * a[h] : 0.f;
         // HP may exceed WMAX only when H <= WMAX < HP, which the host never configures
     }
+}
+
+// Tensor-core forward for wide filter MLPs (hidden width 16 or 32, two or more hidden layers; BASELINE config 4).
+// One thread per pair cannot feed the FP32 pipe here: a 32 x 32 Linear is 1024 dependent-free FMAs whose weight
+// operands all come from shared memory.  The hidden Linears l >= 1 are therefore run as dense layers on tcgen05 over
+// tiles of 128 pairs:  D[128 pairs][W] = A[128][W] * W_l^T  with the tile's activations as the A operand in TMEM
+// (thread = pair = TMEM lane: written straight from registers, split into tf32 hi / lo) and the weights (hi, lo) as
+// K-major shared-memory operands, three kind::tf32 MMAs per product (A_hi B_hi + A_lo B_hi + A_hi B_lo: ~1e-6, the
+// fp32 parity bound is 1e-5).  Layer 0 (spatial_dim <= 3 inputs) and the sines stay on the FP32 / SFU pipes.
+template <int W>
+__global__ void __launch_bounds__(128, 4)
+k_pair_phi_fwd_tc(const float* __restrict__ out_pts, const float* __restrict__ in_pts,
+                  const float* __restrict__ quad_w, const int* __restrict__ pair_row,
+                  const int* __restrict__ pair_col, int64_t P, int d, MlpDev m, int HP, float* __restrict__ phi)
+{
+    extern __shared__ __align__(128) float smem[];
+    float* W0s = smem;                          // [W][4] layer 0, zero padded
+    float* Bs = smem + W * 4;                   // [n_hidden - 1][hi, lo][W * W] canonical K-major tiles
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    constexpr int TCOLS = W == 32 ? 128 : 64;   // A_hi, A_lo, D: 3 W columns
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int L = m.n_hidden;
+    for (int t = tid; t < W * 4; t += 128) {
+        const int o = t >> 2, k = t & 3;
+        W0s[t] = (o < m.dims[1] && k < m.dims[0]) ? rnd_operand(m.w[0][o * m.dims[0] + k], m.bf16) : 0.f;
+    }
+    for (int l = 1; l < L; ++l) {
+        const int nin = m.dims[l], nout = m.dims[l + 1];
+        char* hi = reinterpret_cast<char*>(Bs + (size_t)(l - 1) * 2 * W * W);
+        char* lo = hi + W * W * 4;
+        for (int t = tid; t < W * W; t += 128) {
+            const int o = t / W, k = t % W;
+            const float v = (o < nout && k < nin) ? rnd_operand(m.w[l][o * nin + k], m.bf16) : 0.f;
+            const float hv = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            const uint32_t off = tc::kmajor_off_bytes(o, k, W);
+            *reinterpret_cast<float*>(hi + off) = hv;
+            *reinterpret_cast<float*>(lo + off) = v - hv;
+        }
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, TCOLS);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_fence_init();
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t a_hi = tmem, a_lo = tmem + W, d_acc = tmem + 2 * W;
+    const uint32_t idesc = tc::make_idesc_tf32(128, W);
+    constexpr uint32_t SBO = (W / 4) * 128;
+    const int H = m.dims[L];
+    uint32_t phase = 0;
+
+    for (int64_t base = (int64_t)blockIdx.x * 128; base < P; base += (int64_t)gridDim.x * 128) {
+        const int64_t p = base + tid;
+        const bool valid = p < P;
+        int r = 0, c = 0;
+        if (valid) r = pair_row[p], c = pair_col[p];
+        float z[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < d) z[k] = rnd_operand(__fsub_rn(out_pts[(size_t)r * d + k], in_pts[(size_t)c * d + k]), m.bf16);
+        }
+        float a[W];
+#pragma unroll
+        for (int o = 0; o < W; ++o) {
+            const float4 w4 = *reinterpret_cast<const float4*>(W0s + o * 4);
+            // same association order as the scalar kernel: ((w0 z0 + 0) + w1 z1) + w2 z2
+            float acc = fmaf(w4.x, z[0], 0.f);
+            acc = fmaf(w4.y, z[1], acc);
+            acc = fmaf(w4.z, z[2], acc);
+            a[o] = rnd_operand(sinf(acc), m.bf16);
+        }
+        for (int l = 1; l < L; ++l) {
+#pragma unroll
+            for (int cc = 0; cc < W / 16; ++cc) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float x = a[cc * 16 + j];
+                    const float hv = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+                    hi[j] = __float_as_uint(hv);
+                    lo[j] = __float_as_uint(x - hv);
+                }
+                tc::tmem_st16(lane_base + a_hi + cc * 16, hi);
+                tc::tmem_st16(lane_base + a_lo + cc * 16, lo);
+            }
+            tc::wait_st();
+            tc::fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc::fence_after_sync();
+                const uint32_t bhi = tc::smem_u32(Bs + (size_t)(l - 1) * 2 * W * W), blo = bhi + W * W * 4;
+#pragma unroll
+                for (int ks = 0; ks < W / 8; ++ks) {
+                    const uint64_t dhi = tc::make_smem_desc(bhi + ks * 256, 128, SBO);
+                    const uint64_t dlo = tc::make_smem_desc(blo + ks * 256, 128, SBO);
+                    tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dhi, idesc, ks != 0);
+                    tc::mma_tf32_ts(d_acc, a_lo + ks * 8, dhi, idesc, true);
+                    tc::mma_tf32_ts(d_acc, a_hi + ks * 8, dlo, idesc, true);
+                }
+                tc::mma_commit(&bar);
+            }
+            tc::mbar_wait(&bar, phase);
+            phase ^= 1u;
+            tc::fence_after_sync();
+#pragma unroll
+            for (int cc = 0; cc < W / 16; ++cc) {
+                uint32_t rr[16];
+                tc::tmem_ld16(lane_base + d_acc + cc * 16, rr);
+                tc::wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) a[cc * 16 + j] = rnd_operand(sinf(__uint_as_float(rr[j])), m.bf16);
+            }
+        }
+        if (valid) {
+            const float wq = quad_w ? quad_w[c] : 1.f;
+            float4* dst = reinterpret_cast<float4*>(phi + (size_t)p * HP);
+#pragma unroll
+            for (int q = 0; q < W / 4; ++q)
+                if (4 * q < HP)
+                    dst[q] = make_float4(4 * q < H ? wq * a[4 * q] : 0.f, 4 * q + 1 < H ? wq * a[4 * q + 1] : 0.f,
+                                         4 * q + 2 < H ? wq * a[4 * q + 2] : 0.f, 4 * q + 3 < H ? wq * a[4 * q + 3] : 0.f);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
 }
 
 // Backward.  Block = 128 pairs per sweep.  Per layer the block stages (da, x) of its pairs in
@@ -242,6 +377,260 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
     }
 }
 
+// Tensor-core backward for wide filter MLPs with exactly two hidden layers (d -> h1 -> h2, widths <= W = 16 or 32:
+// BASELINE config 4).  Per tile of 128 pairs (thread = pair = TMEM lane) four dense products run on tcgen05 in 3xTF32:
+//   F  pre1 = x1 W1^T                      recompute of the hidden-to-hidden Linear        A = x1 in TMEM, B = W1
+//   X  dx1  = da1 W1                       gradient w.r.t. its input                       A = da1 in TMEM, B = W1^T
+//   G  dW1 += da1^T x1   (sum over pairs)  both operands staged K-major (K = pair) in one 128-byte-swizzled
+//   H  dW0 += da0^T z                      shared-memory tile: rows [0, W) = da, rows [W, 2W) = x1 / z
+// G and H put da in the first rows of the tile and the layer input right behind it, so the B operand is a row offset
+// into the A tile (M = 64 rows are multiplied, the rows past W yield products nobody reads).  Their accumulators are
+// read out after every tile (48-MMA chains, see the truncation note in DESIGN.md) and carried in fp32 registers by
+// the lanes that own those rows (an M = 64 accumulator keeps rows 16 w .. 16 w + 15 in lanes 0..15 of lane quadrant w); one
+// atomicAdd per entry per CTA at the end, as in the scalar kernel.
+// Sines / cosines, layer 0 and the quadrature-weight gradient stay on the FP32 / SFU pipes.
+template <int W>
+__global__ void __launch_bounds__(128, 2)
+k_pair_phi_bwd_tc(const float* __restrict__ out_pts, const float* __restrict__ in_pts,
+                  const float* __restrict__ quad_w, const int* __restrict__ pair_row,
+                  const int* __restrict__ pair_col, int64_t P, int d, MlpDev m, int HP,
+                  const float* __restrict__ dphi, int nslices, float* __restrict__ d_quad_w)
+{
+    extern __shared__ __align__(1024) float smem_raw[];
+    float* S_hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // [4][64 rows][32]
+    float* S_lo = S_hi + 4 * 64 * 32;
+    float* B1 = S_lo + 4 * 64 * 32;              // [hi, lo][W*W]  W1   as [N = o][K = k], canonical K-major
+    float* B1T = B1 + 2 * W * W;                 // [hi, lo][W*W]  W1^T as [N = k][K = o]
+    float* W0s = B1T + 2 * W * W;                // [W][4]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    constexpr int TCOLS = W == 32 ? 128 : 64;    // A_hi, A_lo, D (F / X), D (G / H)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int n0 = m.dims[0], n1 = m.dims[1], n2 = m.dims[2];
+    for (int t = tid; t < 2 * 4 * 64 * 32; t += 128) S_hi[t] = 0.f;      // S_hi and S_lo: rows nobody writes must stay finite
+    for (int t = tid; t < W * 4; t += 128) {
+        const int o = t >> 2, k = t & 3;
+        W0s[t] = (o < n1 && k < n0) ? rnd_operand(m.w[0][o * n0 + k], m.bf16) : 0.f;
+    }
+    for (int t = tid; t < W * W; t += 128) {
+        const int o = t / W, k = t % W;
+        const float v = (o < n2 && k < n1) ? rnd_operand(m.w[1][o * n1 + k], m.bf16) : 0.f;
+        const float hv = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const uint32_t off = tc::kmajor_off_bytes(o, k, W) / 4, offT = tc::kmajor_off_bytes(k, o, W) / 4;
+        B1[off] = hv, B1[W * W + off] = v - hv;
+        B1T[offT] = hv, B1T[W * W + offT] = v - hv;
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, TCOLS);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_fence_init();
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t a_hi = tmem, a_lo = tmem + W, d_fx = tmem + 2 * W, d_gh = tmem + 3 * W;
+    const uint32_t idesc_fx = tc::make_idesc_tf32(128, W), idesc_g = tc::make_idesc_tf32(64, W), idesc_h = tc::make_idesc_tf32(64, 8);
+    constexpr uint32_t SBO = (W / 4) * 128;
+    constexpr uint64_t SW128 = (uint64_t)2 << 61;
+    uint32_t phase = 0;
+    float dW1acc[W], dW0acc[8];          // lanes 0..15 of warps 0 (and 1): one row of dW1 / dW0 summed over this CTA's tiles
+#pragma unroll
+    for (int k = 0; k < W; ++k) dW1acc[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dW0acc[k] = 0.f;
+
+    auto put_a = [&](const float (&v)[W]) {              // this pair's row of the TMEM A operand (hi, lo)
+#pragma unroll
+        for (int cc = 0; cc < W / 16; ++cc) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float x = v[cc * 16 + j];
+                const float hv = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+                hi[j] = __float_as_uint(hv);
+                lo[j] = __float_as_uint(x - hv);
+            }
+            tc::tmem_st16(lane_base + a_hi + cc * 16, hi);
+            tc::tmem_st16(lane_base + a_lo + cc * 16, lo);
+        }
+        tc::wait_st();
+    };
+    // element (row, pair = this thread) of the staged tile: K-major over the 128 pairs, 128-byte swizzle, four 32-pair sub-tiles
+    const uint32_t s_col = (uint32_t)((tid >> 5) * (64 * 32));
+    auto put_s = [&](int row, float x) {
+        const uint32_t o = s_col + (uint32_t)((row >> 3) * 256 + (row & 7) * 32 + ((((lane >> 2) ^ (row & 7)) << 2) | (lane & 3)));
+        const float hv = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        S_hi[o] = hv;
+        S_lo[o] = x - hv;
+    };
+    auto mma_ts = [&](uint32_t dcol, const float* Bt, uint32_t idesc) {     // D[128][W] = A(TMEM) * Bt^T, fresh accumulator
+        const uint32_t bhi = tc::smem_u32(Bt), blo = bhi + W * W * 4;
+#pragma unroll
+        for (int ks = 0; ks < W / 8; ++ks) {
+            const uint64_t dhi = tc::make_smem_desc(bhi + ks * 256, 128, SBO);
+            const uint64_t dlo = tc::make_smem_desc(blo + ks * 256, 128, SBO);
+            tc::mma_tf32_ts(dcol, a_hi + ks * 8, dhi, idesc, ks != 0);
+            tc::mma_tf32_ts(dcol, a_lo + ks * 8, dhi, idesc, true);
+            tc::mma_tf32_ts(dcol, a_hi + ks * 8, dlo, idesc, true);
+        }
+    };
+    auto mma_ss = [&](uint32_t idesc) {                  // D[64][N] = S[rows 0..63] * S[rows W..W+N)^T over the 128 pairs
+        const uint32_t shi = tc::smem_u32(S_hi), slo = tc::smem_u32(S_lo);
+        constexpr uint32_t BOFF = (W >> 3) * 1024;       // byte offset of row W inside a sub-tile
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+            const uint32_t o = (uint32_t)((ks >> 2) * (64 * 128) + (ks & 3) * 32);
+            const uint64_t ah = tc::make_smem_desc(shi + o, 16, 1024) | SW128, al = tc::make_smem_desc(slo + o, 16, 1024) | SW128;
+            const uint64_t bh = tc::make_smem_desc(shi + o + BOFF, 16, 1024) | SW128, bl = tc::make_smem_desc(slo + o + BOFF, 16, 1024) | SW128;
+            tc::mma_tf32_ss(d_gh, ah, bh, idesc, ks != 0);
+            tc::mma_tf32_ss(d_gh, al, bh, idesc, true);
+            tc::mma_tf32_ss(d_gh, ah, bl, idesc, true);
+        }
+    };
+    auto wait_mma = [&]() {
+        tc::mbar_wait(&bar, phase);
+        phase ^= 1u;
+        tc::fence_after_sync();
+    };
+    auto get_d = [&](uint32_t dcol, float (&v)[W]) {
+#pragma unroll
+        for (int cc = 0; cc < W / 16; ++cc) {
+            uint32_t rr[16];
+            tc::tmem_ld16(lane_base + dcol + cc * 16, rr);
+            tc::wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[cc * 16 + j] = __uint_as_float(rr[j]);
+        }
+    };
+
+    for (int64_t base = (int64_t)blockIdx.x * 128; base < P; base += (int64_t)gridDim.x * 128) {
+        const int64_t p = base + tid;
+        const bool valid = p < P;
+        int r = 0, c = 0;
+        if (valid) r = pair_row[p], c = pair_col[p];
+        float z[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < d) z[k] = rnd_operand(__fsub_rn(out_pts[(size_t)r * d + k], in_pts[(size_t)c * d + k]), m.bf16);
+        }
+        // layer 0 on the FP32 pipe; x1 = sin, c0 = cos of its pre-activation
+        float x1[W], c0[W];
+#pragma unroll
+        for (int o = 0; o < W; ++o) {
+            const float4 w4 = *reinterpret_cast<const float4*>(W0s + o * 4);
+            float acc = fmaf(w4.x, z[0], 0.f);
+            acc = fmaf(w4.y, z[1], acc);
+            acc = fmaf(w4.z, z[2], acc);
+            float sv, cv;
+            sincosf(acc, &sv, &cv);
+            x1[o] = rnd_operand(sv, m.bf16);
+            c0[o] = cv;
+        }
+        // F: pre1 = x1 W1^T
+        put_a(x1);
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            mma_ts(d_fx, B1, idesc_fx);
+            tc::mma_commit(&bar);
+        }
+        wait_mma();
+        float da[W];                      // pre1, then da1 = d loss / d pre1
+        get_d(d_fx, da);
+        // d loss / d phi of this pair (slices summed in a fixed order), d quadrature weight, da1
+        const float wq = (valid && quad_w) ? quad_w[c] : 1.f;
+        float dwq = 0.f;
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q) {
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && 4 * q < HP)
+                for (int sl = 0; sl < nslices; ++sl) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(dphi + ((size_t)sl * P + p) * HP) + q);
+                    g4.x += v.x, g4.y += v.y, g4.z += v.z, g4.w += v.w;
+                }
+            const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int h = 4 * q + e;
+                float sv, cv;
+                sincosf(da[h], &sv, &cv);
+                const float gh = h < n2 ? g[e] : 0.f;
+                dwq = fmaf(gh, rnd_operand(sv, m.bf16), dwq);
+                da[h] = wq * gh * cv;
+            }
+        }
+        if (valid && d_quad_w) atomicAdd(&d_quad_w[c], dwq);
+        // G: dW1 += da1^T x1 (staged tile) and X: dx1 = da1 W1 (TMEM operand), issued together
+#pragma unroll
+        for (int o = 0; o < W; ++o) put_s(o, da[o]);
+#pragma unroll
+        for (int k = 0; k < W; ++k) put_s(W + k, x1[k]);
+        put_a(da);
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            mma_ss(idesc_g);
+            mma_ts(d_fx, B1T, idesc_fx);
+            tc::mma_commit(&bar);
+        }
+        wait_mma();
+        if (warp * 16 < W) {               // M = 64 accumulators: rows 16 w .. 16 w + 15 sit in lanes 0..15 of warp w's quadrant
+            float t[W];
+            get_d(d_gh, t);
+#pragma unroll
+            for (int k = 0; k < W; ++k) dW1acc[k] += t[k];
+        }
+        get_d(d_fx, da);                  // dx1
+        // H: dW0 += da0^T z
+#pragma unroll
+        for (int o = 0; o < W; ++o) put_s(o, da[o] * c0[o]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) put_s(W + k, k < 3 ? z[k < 3 ? k : 0] : 0.f);
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            mma_ss(idesc_h);
+            tc::mma_commit(&bar);
+        }
+        wait_mma();
+        if (warp * 16 < W) {
+            uint32_t rr[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7])
+                         : "r"(lane_base + d_gh) : "memory");
+            tc::wait_ld();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dW0acc[k] += __uint_as_float(rr[k]);
+        }
+        tc::fence_before_sync();          // the next tile's MMAs overwrite what was just read
+    }
+    // flush: lane l < 16 of warp w owns row 16 w + l
+    if (warp * 16 < W && lane < 16) {
+        const int o = warp * 16 + lane;
+        if (o < n2)
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                if (k < n1) atomicAdd(&m.dw[1][o * n1 + k], dW1acc[k]);
+        if (o < n1)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < n0) atomicAdd(&m.dw[0][o * n0 + k], dW0acc[k]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
+}
+
 int pick_wmax(const qc_mlp_t* mlp, int d)
 {
     int mx = d;
@@ -279,6 +668,31 @@ int launch_fwd(const float* out_pts, const float* in_pts, const float* quad_w, c
     return 0;
 }
 
+template <int W>
+int launch_fwd_tc(const float* out_pts, const float* in_pts, const float* quad_w, const int* pair_row,
+                  const int* pair_col, int64_t P, int d, const MlpDev& m, int HP, float* phi, cudaStream_t st)
+{
+    const size_t smem = ((size_t)W * 4 + (size_t)(m.n_hidden - 1) * 2 * W * W) * 4;
+    QC_CUDA((qc_set_max_smem<k_pair_phi_fwd_tc<W>>((int)smem)));
+    const int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 4);     // 4 CTAs per SM share the 512 TMEM columns
+    k_pair_phi_fwd_tc<W><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, phi);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int W>
+int launch_bwd_tc(const float* out_pts, const float* in_pts, const float* quad_w, const int* pair_row,
+                  const int* pair_col, int64_t P, int d, const MlpDev& m, int HP, const float* dphi,
+                  int nslices, float* d_quad_w, cudaStream_t st)
+{
+    const size_t smem = ((size_t)2 * 4 * 64 * 32 + 4 * W * W + W * 4) * 4 + 1024;
+    QC_CUDA((qc_set_max_smem<k_pair_phi_bwd_tc<W>>((int)smem)));
+    const int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 2);
+    k_pair_phi_bwd_tc<W><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
 template <int WMAX, int LT>
 int launch_bwd(const float* out_pts, const float* in_pts, const float* quad_w, const int* pair_row,
                const int* pair_col, int64_t P, int d, const MlpDev& m, int HP, const float* dphi,
@@ -310,6 +724,12 @@ int qc_pair_phi_fwd(const float* out_pts, const float* in_pts, const float* quad
     if (wmax < 0 || HP < H || HP > 32 || (HP & 3)) return QC_EUNSUP;
     cudaStream_t st = (cudaStream_t)stream;
     const int wsel = wmax > HP ? wmax : HP;  // the phi row (HP wide) is written from registers
+    // wide MLPs with at least one hidden-to-hidden Linear: those layers run on the tensor cores
+    if (wsel >= 16 && m.n_hidden >= 2 && (HP & 3) == 0 && getenv("QC_MLP_NO_TC") == nullptr &&
+        (size_t)(m.n_hidden - 1) * 2 * wsel * wsel * 4 <= 48 * 1024) {
+        if (wsel == 16) return launch_fwd_tc<16>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, phi, st);
+        return launch_fwd_tc<32>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, phi, st);
+    }
     switch (wsel) {
         case 4: return launch_fwd<4>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, phi, st);
         case 8: return launch_fwd<8>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, phi, st);
@@ -335,6 +755,11 @@ int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad
     if (wmax < 0 || HP < H || HP > 32 || (HP & 3)) return QC_EUNSUP;
     cudaStream_t st = (cudaStream_t)stream;
     const int wsel = wmax > HP ? wmax : HP;
+    // wide MLPs with exactly two hidden layers: the 32 x 32 products run on the tensor cores
+    if (wsel >= 16 && m.n_hidden == 2 && getenv("QC_MLP_NO_TC") == nullptr) {
+        if (wsel == 16) return launch_bwd_tc<16>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
+        return launch_bwd_tc<32>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
+    }
 #define QC_BWD(W, LTV) return launch_bwd<W, LTV>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st)
     const int L = m.n_hidden;
     switch (wsel) {   // register-resident activations when (2L+1)*W floats fit comfortably, else the general kernel

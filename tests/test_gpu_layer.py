@@ -538,3 +538,44 @@ def test_batch_folding_matches_unfolded_layer(B, ci, co, min_batch, expect):
     for a, b in zip(g1, g0):
         # d W_last accumulates in TMEM (truncating adds, bounded chains: ~2-4e-6 each way): parity bound
         assert a.shape == b.shape and relerr(a.cpu(), b.cpu()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,fs,ci,co", [(2, [32, 32], 8, 8), (3, [12, 20], 6, 4), (2, [16, 16], 4, 8), (3, [32, 24], 5, 7)])
+def test_tensor_core_filter_mlp_matches_scalar_kernels(d, fs, ci, co, monkeypatch):
+    """Wide filter MLPs (hidden width 16 / 32, two hidden layers) evaluate their hidden-to-hidden Linear -- forward,
+    input gradient and both weight gradients -- as dense 3xTF32 layers on tcgen05 over 128-pair tiles
+    (csrc/pair_mlp.cu: k_pair_phi_fwd_tc / k_pair_phi_bwd_tc).  Same layer as the one-thread-per-pair FP32 kernels
+    (QC_MLP_NO_TC=1) within the fp32 parity bound, ragged widths and a pair count that is not a multiple of 128."""
+    import pytorch_quadconv_b200 as q
+    torch.manual_seed(5)
+    dev = torch.device("cuda:0")
+    n = 777
+    pts = torch.rand(n, d)
+    wa = {"element_size": d + 1, "dimension": d, "const": False}
+    mesh = q.MeshHandler(pts).construct([n], quad_args={"point_args": {}, "weight_args": wa}).to(dev)
+    layer = q.QuadConv(spatial_dim=d, in_points=n, out_points=n, in_channels=ci, out_channels=co, filter_seq=fs,
+                       output_same=True, bias=False, decay_param=0.11 if d == 2 else 0.2).to(dev)
+    x = torch.randn(8, ci, n, device=dev)
+    wgt = torch.randn(8, co, n, device=dev)
+    res = []
+    for no_tc in (False, True):
+        if no_tc:
+            monkeypatch.setenv("QC_MLP_NO_TC", "1")
+        else:
+            monkeypatch.delenv("QC_MLP_NO_TC", raising=False)
+        mesh.reset()
+        ps = list(layer.parameters()) + list(mesh.parameters())
+        for p in ps:
+            p.grad = None
+        xi = x.clone().requires_grad_()
+        y = layer(mesh, xi)
+        (y * wgt).sum().backward()
+        torch.cuda.synchronize()
+        res.append((y.detach().cpu(), xi.grad.cpu(), [p.grad.cpu() for p in ps if p.grad is not None]))
+    (y1, dx1, g1), (y0, dx0, g0) = res
+    assert int(layer.eval_indices.shape[0]) % 128 != 0
+    assert relerr(y1, y0) < 5e-6 and relerr(dx1, dx0) < 5e-6
+    assert len(g1) == len(g0) >= 4
+    for a, b in zip(g1, g0):
+        assert a.shape == b.shape and relerr(a, b) < 1e-5
