@@ -85,6 +85,17 @@ k_pair_phi_fwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
     }
 }
 
+// Accurate sine / cosine as real calls: the tensor-core kernels below evaluate 64 of them per pair in fully unrolled
+// register code, and 64 inlined copies of sincosf (fast path + Payne-Hanek fallback) overflow the instruction cache
+// (ncu: 37 % of the backward kernel's stall samples were `no_instruction` on those lines).
+__device__ __noinline__ float2 sincos_call(float x)
+{
+    float s, c;
+    sincosf(x, &s, &c);
+    return make_float2(s, c);
+}
+__device__ __noinline__ float sin_call(float x) { return sinf(x); }
+
 // Tensor-core forward for wide filter MLPs (hidden width 16 or 32, two or more hidden layers; BASELINE config 4).
 // One thread per pair cannot feed the FP32 pipe here: a 32 x 32 Linear is 1024 dependent-free FMAs whose weight
 // operands all come from shared memory.  The hidden Linears l >= 1 are therefore run as dense layers on tcgen05 over
@@ -160,7 +171,7 @@ k_pair_phi_fwd_tc(const float* __restrict__ out_pts, const float* __restrict__ i
             float acc = fmaf(w4.x, z[0], 0.f);
             acc = fmaf(w4.y, z[1], acc);
             acc = fmaf(w4.z, z[2], acc);
-            a[o] = rnd_operand(sinf(acc), m.bf16);
+            a[o] = rnd_operand(sin_call(acc), m.bf16);
         }
         for (int l = 1; l < L; ++l) {
 #pragma unroll
@@ -201,7 +212,7 @@ k_pair_phi_fwd_tc(const float* __restrict__ out_pts, const float* __restrict__ i
                 tc::tmem_ld16(lane_base + d_acc + cc * 16, rr);
                 tc::wait_ld();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) a[cc * 16 + j] = rnd_operand(sinf(__uint_as_float(rr[j])), m.bf16);
+                for (int j = 0; j < 16; ++j) a[cc * 16 + j] = rnd_operand(sin_call(__uint_as_float(rr[j])), m.bf16);
             }
         }
         if (valid) {
@@ -526,10 +537,9 @@ k_pair_phi_bwd_tc(const float* __restrict__ out_pts, const float* __restrict__ i
             float acc = fmaf(w4.x, z[0], 0.f);
             acc = fmaf(w4.y, z[1], acc);
             acc = fmaf(w4.z, z[2], acc);
-            float sv, cv;
-            sincosf(acc, &sv, &cv);
-            x1[o] = rnd_operand(sv, m.bf16);
-            c0[o] = cv;
+            const float2 sc = sincos_call(acc);
+            x1[o] = rnd_operand(sc.x, m.bf16);
+            c0[o] = sc.y;
         }
         // F: pre1 = x1 W1^T
         put_a(x1);
@@ -558,11 +568,10 @@ k_pair_phi_bwd_tc(const float* __restrict__ out_pts, const float* __restrict__ i
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int h = 4 * q + e;
-                float sv, cv;
-                sincosf(da[h], &sv, &cv);
+                const float2 sc = sincos_call(da[h]);
                 const float gh = h < n2 ? g[e] : 0.f;
-                dwq = fmaf(gh, rnd_operand(sv, m.bf16), dwq);
-                da[h] = wq * gh * cv;
+                dwq = fmaf(gh, rnd_operand(sc.x, m.bf16), dwq);
+                da[h] = wq * gh * sc.y;
             }
         }
         if (valid && d_quad_w) atomicAdd(&d_quad_w[c], dwq);
