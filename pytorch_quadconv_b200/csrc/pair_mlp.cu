@@ -41,6 +41,26 @@ __device__ __forceinline__ void load_weights(const MlpDev& m, float* Wsm)
     }
 }
 
+// Accurate sine / cosine as real calls: the tensor-core kernels below evaluate 64 of them per pair in fully unrolled
+// register code, and 64 inlined copies of sincosf (fast path + Payne-Hanek fallback) overflow the instruction cache
+// (ncu: 37 % of the backward kernel's stall samples were `no_instruction` on those lines).
+__device__ __noinline__ float2 sincos_call(float x)
+{
+    float s, c;
+    sincosf(x, &s, &c);
+    return make_float2(s, c);
+}
+__device__ __noinline__ float sin_call(float x) { return sinf(x); }
+
+// scalar kernels: inlined by default (QC_MLP_CALLS=1 at compile time switches them to the calls for experiments)
+#ifdef QC_MLP_CALLS
+#define QC_SCALAR_SIN(v) sin_call(v)
+#define QC_SCALAR_SINCOS(v, sv_, cv_) do { const float2 sc__ = sincos_call(v); sv_ = sc__.x; cv_ = sc__.y; } while (0)
+#else
+#define QC_SCALAR_SIN(v) sinf(v)
+#define QC_SCALAR_SINCOS(v, sv_, cv_) sincosf(v, &sv_, &cv_)
+#endif
+
 template <int WMAX>
 __global__ void __launch_bounds__(128)
 k_pair_phi_fwd(const float* __restrict__ out_pts, const float* __restrict__ in_pts,
@@ -71,7 +91,7 @@ k_pair_phi_fwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
                 float acc = 0.f;
 #pragma unroll
                 for (int k = 0; k < WMAX; ++k) acc = fmaf(W[o * WMAX + k], a[k], acc);
-                t[o] = rnd_operand(sinf(acc), m.bf16);
+                t[o] = rnd_operand(QC_SCALAR_SIN(acc), m.bf16);
             }
 #pragma unroll
             for (int o = 0; o < WMAX; ++o) a[o] = t[o];
@@ -84,17 +104,6 @@ k_pair_phi_fwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
         // HP may exceed WMAX only when H <= WMAX < HP, which the host never configures
     }
 }
-
-// Accurate sine / cosine as real calls: the tensor-core kernels below evaluate 64 of them per pair in fully unrolled
-// register code, and 64 inlined copies of sincosf (fast path + Payne-Hanek fallback) overflow the instruction cache
-// (ncu: 37 % of the backward kernel's stall samples were `no_instruction` on those lines).
-__device__ __noinline__ float2 sincos_call(float x)
-{
-    float s, c;
-    sincosf(x, &s, &c);
-    return make_float2(s, c);
-}
-__device__ __noinline__ float sin_call(float x) { return sinf(x); }
 
 // Tensor-core forward for wide filter MLPs (hidden width 16 or 32, two or more hidden layers; BASELINE config 4).
 // One thread per pair cannot feed the FP32 pipe here: a 32 x 32 Linear is 1024 dependent-free FMAs whose weight
@@ -285,7 +294,7 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
 #pragma unroll
                 for (int k = 0; k < WMAX; ++k) acc = fmaf(W[o * WMAX + k], xs[l][k], acc);
                 float sv, cv;
-                sincosf(acc, &sv, &cv);
+                QC_SCALAR_SINCOS(acc, sv, cv);
                 xs[l + 1][o] = rnd_operand(sv, m.bf16);   // straight-through: the derivative ignores the rounding
                 cs[l][o] = cv;
             }
