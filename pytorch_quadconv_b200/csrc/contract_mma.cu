@@ -732,26 +732,46 @@ __global__ void __launch_bounds__(256) k_pack_bf16(const TIn* __restrict__ x, in
     const int n0 = blockIdx.x * PTB, c = blockIdx.y, blk = blockIdx.z, nch = gridDim.y;
     const int rows = CC * Bp;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = w; r < rows; r += 8) {
-        const int il = r / Bp, bl = r % Bp;
-        const int ch = c * CC + il, b = blk * 32 + bl;
+    if (sizeof(TIn) == 4 && (N & 3) == 0) {
+        // fp32 source with 16-byte aligned rows: half-warp per row, one 128-bit load per lane (like k_pack)
+        const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
+        const int n = n0 + hl * 4;
+        for (int r = hw; r < rows; r += 16) {
+            const int il = r / Bp, bl = r % Bp;
+            const int ch = c * CC + il, b = blk * 32 + bl;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ch < C && b < B && n < N) v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + ((size_t)b * C + ch) * N + n));
+            float* t = tile + r * RSB + hl * 4;
+            t[0] = v.x, t[1] = v.y, t[2] = v.z, t[3] = v.w;
+        }
+    } else {
+        for (int r = w; r < rows; r += 8) {
+            const int il = r / Bp, bl = r % Bp;
+            const int ch = c * CC + il, b = blk * 32 + bl;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int n = n0 + half * 32 + lane;
-            float v = 0.f;
-            if (ch < C && b < B && n < N) v = to_f32(x[((size_t)b * C + ch) * N + n]);
-            tile[r * RSB + half * 32 + lane] = v;
+            for (int half = 0; half < 2; ++half) {
+                const int n = n0 + half * 32 + lane;
+                float v = 0.f;
+                if (ch < C && b < B && n < N) v = to_f32(x[((size_t)b * C + ch) * N + n]);
+                tile[r * RSB + half * 32 + lane] = v;
+            }
         }
     }
     __syncthreads();
     const int per_pt = rows / 2;           // bf16x2 words per point and chunk
-    for (int idx = threadIdx.x; idx < PTB * per_pt; idx += 256) {
-        const int nl = idx / per_pt, wd = idx % per_pt;
+    const int per_pt4 = rows / 8;          // 16-byte pieces (8 bf16) per point and chunk
+    for (int idx = threadIdx.x; idx < PTB * per_pt4; idx += 256) {
+        const int nl = idx / per_pt4, w4 = idx % per_pt4;
         const int n = n0 + nl;
         if (n < N) {
-            const int bl = (2 * wd) / CC, il = (2 * wd) % CC;
-            const uint32_t v = pack_bf16(tile[(il * Bp + bl) * RSB + nl], tile[((il + 1) * Bp + bl) * RSB + nl]);
-            reinterpret_cast<uint32_t*>(xp)[(((size_t)blk * N + n) * nch + c) * per_pt + wd] = v;
+            uint32_t v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = 8 * w4 + 2 * j, bl = e / CC, il = e % CC;
+                v[j] = pack_bf16(tile[(il * Bp + bl) * RSB + nl], tile[((il + 1) * Bp + bl) * RSB + nl]);
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(xp) + (((size_t)blk * N + n) * nch + c) * per_pt + 4 * w4) =
+                make_uint4(v[0], v[1], v[2], v[3]);
         }
     }
 }
