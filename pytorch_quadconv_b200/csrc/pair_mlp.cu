@@ -265,25 +265,62 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
     constexpr int LMAX = LT > 0 ? LT : QC_MAX_MLP_LAYERS;
     const int L = LT > 0 ? LT : m.n_hidden;
 
-    for (int64_t base = (int64_t)blockIdx.x * NT; base < P; base += (int64_t)gridDim.x * NT) {
-        const int64_t p = base + threadIdx.x;
-        const bool valid = p < P;
-        // forward recompute, keeping every layer input and the cosine of every pre-activation
-        float xs[LMAX + 1][WMAX];
-        float cs[LMAX][WMAX];
-        int r = 0, c = 0;
-        if (valid) {
-            r = pair_row[p];
-            c = pair_col[p];
-        }
+    // Two-stage software pipeline over the block's sweeps: the pair indices are loaded two sweeps ahead, the data they
+    // address (points, quadrature weight) and the pair's d(phi) row one sweep ahead, so the two dependent global-memory
+    // latencies of a sweep are paid under the arithmetic of the previous ones instead of at its start.
+    struct PairIn { int c; float z[3]; float wq; float g[WMAX]; };
+    const int64_t stride = (int64_t)gridDim.x * NT;
+    auto load_idx = [&](int64_t base_, int& r_, int& c_) {
+        const int64_t p_ = base_ + threadIdx.x;
+        r_ = 0, c_ = 0;
+        if (p_ < P) r_ = pair_row[p_], c_ = pair_col[p_];
+    };
+    auto load_in = [&](int64_t base_, int r_, int c_, PairIn& in) {
+        const int64_t p_ = base_ + threadIdx.x;
+        const bool v_ = p_ < P;
+        in.c = c_;
 #pragma unroll
-        for (int k = 0; k < WMAX; ++k) xs[0][k] = 0.f;
-        if (valid) {
+        for (int k = 0; k < 3; ++k) in.z[k] = 0.f;
+#pragma unroll
+        for (int h = 0; h < WMAX; ++h) in.g[h] = 0.f;
+        in.wq = 1.f;
+        if (v_) {
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 if (k < d && k < WMAX)
-                    xs[0][k] = rnd_operand(__fsub_rn(out_pts[(size_t)r * d + k], in_pts[(size_t)c * d + k]), m.bf16);
+                    in.z[k] = rnd_operand(__fsub_rn(out_pts[(size_t)r_ * d + k], in_pts[(size_t)c_ * d + k]), m.bf16);
+            if (quad_w) in.wq = quad_w[c_];
+            // d loss / d phi of this pair: the slices are summed in a fixed order, 128 bits at a time
+            for (int sl = 0; sl < nslices; ++sl) {
+                const float4* src = reinterpret_cast<const float4*>(dphi + ((size_t)sl * P + p_) * HP);
+#pragma unroll
+                for (int q = 0; q < WMAX / 4; ++q)
+                    if (4 * q < HP) {
+                        const float4 v = __ldg(src + q);
+                        in.g[4 * q] += v.x, in.g[4 * q + 1] += v.y, in.g[4 * q + 2] += v.z, in.g[4 * q + 3] += v.w;
+                    }
+            }
         }
+    };
+    const int64_t base0 = (int64_t)blockIdx.x * NT;
+    int r1, c1, r2 = 0, c2 = 0;
+    PairIn nxt;
+    load_idx(base0, r1, c1);
+    load_in(base0, r1, c1, nxt);
+    load_idx(base0 + stride, r1, c1);
+    for (int64_t base = base0; base < P; base += stride) {
+        const int64_t p = base + threadIdx.x;
+        const bool valid = p < P;
+        const PairIn cur = nxt;
+        load_idx(base + 2 * stride, r2, c2);                 // indices two sweeps ahead
+        if (base + stride < P) load_in(base + stride, r1, c1, nxt);   // data one sweep ahead (its indices arrived a sweep ago)
+        r1 = r2, c1 = c2;
+        const int c = cur.c;
+        // forward recompute, keeping every layer input and the cosine of every pre-activation
+        float xs[LMAX + 1][WMAX];
+        float cs[LMAX][WMAX];
+#pragma unroll
+        for (int k = 0; k < WMAX; ++k) xs[0][k] = (k < 3 && valid) ? cur.z[k < 3 ? k : 0] : 0.f;
 #pragma unroll(LT > 0 ? LMAX : 1)
         for (int l = 0; l < LMAX; ++l) {
             if (l >= L) break;
@@ -299,26 +336,12 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
                 cs[l][o] = cv;
             }
         }
-        const float wq = (valid && quad_w) ? quad_w[c] : 1.f;
+        const float wq = cur.wq;
         float dx[WMAX];
         float dwq = 0.f;
-        float gs[WMAX];   // d loss / d phi of this pair: the slices are summed in a fixed order, 128 bits at a time
-#pragma unroll
-        for (int h = 0; h < WMAX; ++h) gs[h] = 0.f;
-        if (valid) {
-            for (int sl = 0; sl < nslices; ++sl) {
-                const float4* src = reinterpret_cast<const float4*>(dphi + ((size_t)sl * P + p) * HP);
-#pragma unroll
-                for (int q = 0; q < WMAX / 4; ++q)
-                    if (4 * q < HP) {
-                        const float4 v = __ldg(src + q);
-                        gs[4 * q] += v.x, gs[4 * q + 1] += v.y, gs[4 * q + 2] += v.z, gs[4 * q + 3] += v.w;
-                    }
-            }
-        }
 #pragma unroll
         for (int h = 0; h < WMAX; ++h) {
-            const float g = h < H ? gs[h] : 0.f;
+            const float g = h < H ? cur.g[h] : 0.f;
             dwq = fmaf(g, LT > 0 ? xs[LT][h] : xs[L][h], dwq);
             dx[h] = wq * g;
         }
