@@ -734,7 +734,7 @@ def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair
     return features.new_empty((B, out_channels, No)), features.new_empty(wsb, dtype=torch.uint8)
 
 
-@torch.library.custom_op("quadconv_b200::layer_backward", mutates_args=())
+@torch.library.custom_op("quadconv_b200::layer_backward", mutates_args=("ws",))   # the workspace's scratch regions are rewritten
 @_on_device
 def layer_backward(grad_out: Tensor, ws: Tensor, out_pts: Tensor, in_pts: Tensor, quad_w: Tensor,
                    hidden_ws: Sequence[Tensor], w_last: Tensor, pair_row: Tensor, pair_col: Tensor, row_ptr: Tensor,

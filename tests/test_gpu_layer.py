@@ -579,3 +579,56 @@ def test_tensor_core_filter_mlp_matches_scalar_kernels(d, fs, ci, co, monkeypatc
     assert len(g1) == len(g0) >= 4
     for a, b in zip(g1, g0):
         assert a.shape == b.shape and relerr(a, b) < 1e-5
+
+
+@pytest.mark.gpu
+def test_custom_ops_pass_opcheck():
+    """The quadconv_b200:: ops are registered torch.library custom ops with fake (meta) kernels: schema and
+    FakeTensor checks of torch.library.opcheck on the ops the modules call (what torch.compile traces)."""
+    import pytorch_quadconv_b200 as q
+    from pytorch_quadconv_b200 import ops
+    torch.manual_seed(2)
+    dev = torch.device("cuda:0")
+    n = 300
+    pts = torch.rand(n, 2)
+    mesh = q.MeshHandler(pts).construct([n, 0], mirror=True, quad_map="mfnus").to(dev)
+    layer = q.QuadConv(spatial_dim=2, in_points=n, out_points=n, in_channels=4, out_channels=8, filter_seq=[8, 8],
+                       output_same=True, bias=True, decay_param=0.15).to(dev)
+    pool = q.Mesh_MaxPool()
+    x = torch.randn(8, 4, n, device=dev)
+    mesh.reset()
+    y = layer(mesh, x)
+    pool(mesh, y)
+    pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in = layer._tables[:8]
+    mesh.reset()
+    p = mesh.input_points().detach()          # level 0 (the pool call above stepped the cursor)
+    lin = [m for m in layer.filter if isinstance(m, torch.nn.Linear)]
+    hidden = [m.weight.detach() for m in lin[:-1]]
+    w_last = lin[-1].weight.detach()
+    qw = torch.rand(n, device=dev)
+    utils = ("test_schema", "test_faketensor")
+    torch.library.opcheck(ops.qc_forward, (x, p, p, qw, hidden, w_last, layer.bias.detach(), pair_row, pair_col, row_ptr,
+                                           order_out, 4, 8), test_utils=utils)
+    torch.library.opcheck(ops.layer_forward, (x, p, p, qw, hidden, w_last, layer.bias.detach(), pair_row, pair_col, row_ptr,
+                                              csc_ptr, csc_pair, csc_row, order_out, order_in, 4, 8), test_utils=utils)
+    out, ws = ops.layer_forward(x, p, p, qw, hidden, w_last, None, pair_row, pair_col, row_ptr, csc_ptr, csc_pair, csc_row,
+                                order_out, order_in, 4, 8)
+    torch.library.opcheck(ops.layer_backward, (torch.ones_like(out), ws, p, p, qw, hidden, w_last, pair_row, pair_col, row_ptr,
+                                               csc_ptr, csc_pair, csc_row, order_out, order_in, 4, 8, False), test_utils=utils)
+    group32, grp_ptr, grp_mem, n_groups = pool._tables
+    torch.library.opcheck(ops.segmax, (y.detach(), group32, grp_ptr, grp_mem, n_groups, 1), test_utils=utils)
+    torch.library.opcheck(ops.gather_pool, (torch.randn(8, 8, n_groups, device=dev), group32, 0), test_utils=utils)
+    # the composed backward, the pool backwards, the weight map both ways, tables from a given pair list
+    _, phi, xp = ops.qc_forward(x, p, p, qw, hidden, w_last, None, pair_row, pair_col, row_ptr, order_out, 4, 8)
+    torch.library.opcheck(ops.qc_backward, (torch.ones_like(out), xp, phi, p, p, qw, hidden, w_last, pair_row, pair_col, row_ptr,
+                                            csc_ptr, csc_pair, csc_row, order_out, order_in, 8, 4, 8, True), test_utils=utils)
+    pooled = ops.segmax(y.detach(), group32, grp_ptr, grp_mem, n_groups, 1)
+    torch.library.opcheck(ops.segmax_bwd, (y.detach(), pooled, torch.ones_like(pooled), group32, grp_ptr, grp_mem, 1), test_utils=utils)
+    torch.library.opcheck(ops.gather_pool_bwd, (torch.ones(8, 8, n, device=dev), grp_ptr, grp_mem, n_groups,
+                                                torch.randn(8, 8, n_groups, device=dev), 1), test_utils=utils)
+    adj32, inc_ptr, inc_idx = mesh._incidence(0, mesh._adjacency[0])
+    wm = [t.detach() for lin_ in (mesh._weight_network[0], mesh._weight_network[2], mesh._weight_network[4],
+                                  mesh._weight_network[6]) for t in (lin_.weight, lin_.bias)]
+    torch.library.opcheck(ops.weight_map, (p, adj32, inc_ptr, inc_idx, wm), test_utils=utils)
+    torch.library.opcheck(ops.weight_map_bwd, (torch.ones(n, device=dev), p, adj32, wm), test_utils=utils)
+    torch.library.opcheck(ops.pairs_to_tables, (layer.eval_indices.data, n, n), test_utils=utils)
