@@ -306,7 +306,7 @@ def time_kernels(w, mesh, layer, x, reps=5):
     from pytorch_quadconv_b200 import _cabi as C, ops
     L = C.lib()
     names = ["qc_pair_phi_fwd", "qc_pack_features", "qc_repack_wlast", "qc_contract", "qc_unpack_features",
-             "qc_batch_sum", "qc_dphi", "qc_pair_phi_bwd", "qc_unpack_dwlast", "qc_gather_accumulate", "qc_gather_dot", "qc_contract_mma", "qc_pack_features_bf16", "qc_dphi_mma", "qc_dw_mma", "qc_gemm_nt_tf32x3", "qc_gemm_tn_tf32x3"]
+             "qc_batch_sum", "qc_dphi", "qc_pair_phi_bwd", "qc_pair_phi_bwd_ws", "qc_unpack_dwlast", "qc_gather_accumulate", "qc_gather_dot", "qc_contract_mma", "qc_pack_features_bf16", "qc_dphi_mma", "qc_dw_mma", "qc_gemm_nt_tf32x3", "qc_gemm_tn_tf32x3"]
     acc = {}
     orig = {n: getattr(L, n) for n in names}
     phase = {"bwd": False}

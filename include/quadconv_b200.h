@@ -130,6 +130,16 @@ int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad
                     float* const* d_mlp_w /*host array of device ptrs*/, float* d_quad_w,
                     void* stream);
 
+/* Bit-reproducible variants (the plain ones combine per-block partial sums with float atomics, whose order varies run
+ * to run): per-block partial sums and per-pair terms go to a caller-owned workspace and are added in fixed orders
+ * (block order; the CSC order of each in-point for d_quad_w -- csc_ptr [Ni+1], csc_pair [P] from qc_csc_*). */
+size_t qc_pair_phi_bwd_workspace_bytes(int64_t P, int d, const qc_mlp_t* mlp, int HP);
+int qc_pair_phi_bwd_ws(const float* out_pts, const float* in_pts, const float* quad_w,
+                       const int* pair_row, const int* pair_col, int64_t P, int d,
+                       const qc_mlp_t* mlp, int HP, const float* dphi, int nslices,
+                       float* const* d_mlp_w, float* d_quad_w, const int* csc_ptr, const int* csc_pair, int Ni,
+                       void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K2b/K3  fused last-MLP-layer + gather-contract-segmented-reduce.
  * Replaces the last Linear of self.filter + reshape (quadconv.py:143,:91), the feature gather,
@@ -287,6 +297,10 @@ int qc_weight_map_fwd(const float* pts, const int* adj, int M, int E, int d, con
 int qc_vertex_sum(const float* el_w, const int* inc_ptr, const int* inc_idx, int N, float* w, void* stream);
 int qc_weight_map_bwd(const float* pts, const int* adj, int M, int E, int d, const float* const* wb,
                       const float* gw, float* const* dwb, void* stream);
+/* bit-reproducible variant: per-block partial sums in `ws`, added in block order */
+size_t qc_weight_map_bwd_workspace_bytes(int M);
+int qc_weight_map_bwd_ws(const float* pts, const int* adj, int M, int E, int d, const float* const* wb,
+                         const float* gw, float* const* dwb, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Reduced-precision tensor-core path (bf16 operands, fp32 accumulation; QuadConv(compute_dtype=torch.bfloat16)).

@@ -114,6 +114,13 @@ _SIGNATURES = {
     "qc_vertex_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "qc_weight_map_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p,
                                   ctypes.POINTER(c_void_p), c_void_p]),
+    "qc_weight_map_bwd_workspace_bytes": (c_size_t, [c_int]),
+    "qc_weight_map_bwd_ws": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p,
+                                     ctypes.POINTER(c_void_p), c_void_p, c_size_t, c_void_p]),
+    "qc_pair_phi_bwd_workspace_bytes": (c_size_t, [c_int64, c_int, ctypes.POINTER(QcMlp), c_int]),
+    "qc_pair_phi_bwd_ws": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, ctypes.POINTER(QcMlp), c_int,
+                                   c_void_p, c_int, ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int,
+                                   c_void_p, c_size_t, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

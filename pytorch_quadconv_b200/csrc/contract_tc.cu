@@ -445,19 +445,18 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_nslots, const in
     if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
 }
 
-// dW2[(c*H+h)][j] += sum over the slots written by every CTA (fp32, fixed order inside a CTA's slots).
-// grid (nkc*64*32 / 256, CTAs of the main kernel); entry e = (chunk, m, j).
+// dW2[(c*H+h)][j] += sum over the slots written by every CTA, in two passes with FIXED summation orders (the result
+// is bit-reproducible run to run): k_dw_reduce folds a CTA's slots into its slot 0 (grid (nkc*64*32 / 256, CTAs of the
+// main kernel); entry e = (chunk, m, j)), k_dw_sum_ctas adds the CTAs' slot 0 in CTA order.
 template <int HP>
 __global__ void __launch_bounds__(256)
-k_dw_reduce(const float* __restrict__ scratch, const int* __restrict__ counts, int nslots, int nkc, int Cx, int H,
-            int Cy, int CyP, float* __restrict__ dW2)
+k_dw_reduce(float* __restrict__ scratch, const int* __restrict__ counts, int nslots, int nkc)
 {
-    constexpr int CXC = 64 / HP;
     const int e = blockIdx.x * 256 + threadIdx.x, cta = blockIdx.y;
     const int per = nkc * 64 * 32;
     if (e >= per) return;
     const int n = counts[cta];
-    const float* p = scratch + (size_t)cta * nslots * per + e;
+    float* p = scratch + (size_t)cta * nslots * per + e;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int f = 0;
     for (; f + 4 <= n; f += 4) {
@@ -467,9 +466,32 @@ k_dw_reduce(const float* __restrict__ scratch, const int* __restrict__ counts, i
         s3 += p[(size_t)(f + 3) * per];
     }
     for (; f < n; ++f) s0 += p[(size_t)f * per];
+    p[0] = (s0 + s1) + (s2 + s3);            // only this thread touches element e of this CTA's slots
+}
+
+template <int HP>
+__global__ void __launch_bounds__(256)
+k_dw_sum_ctas(const float* __restrict__ scratch, int nctas, int nslots, int nkc, int Cx, int H, int Cy, int CyP,
+              float* __restrict__ dW2)
+{
+    constexpr int CXC = 64 / HP;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    const int per = nkc * 64 * 32;
+    if (e >= per) return;
     const int j = e & 31, m = (e >> 5) & 63, kc = e >> 11;
     const int cx = kc * CXC + m / HP, hh = m % HP;
-    if (n > 0 && cx < Cx && hh < H && j < Cy) atomicAdd(dW2 + ((size_t)cx * H + hh) * CyP + j, (s0 + s1) + (s2 + s3));
+    if (!(cx < Cx && hh < H && j < Cy)) return;
+    const size_t cstride = (size_t)nslots * per;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= nctas; c += 4) {
+        s0 += scratch[(size_t)c * cstride + e];
+        s1 += scratch[(size_t)(c + 1) * cstride + e];
+        s2 += scratch[(size_t)(c + 2) * cstride + e];
+        s3 += scratch[(size_t)(c + 3) * cstride + e];
+    }
+    for (; c < nctas; ++c) s0 += scratch[(size_t)c * cstride + e];
+    dW2[((size_t)cx * H + hh) * CyP + j] += (s0 + s1) + (s2 + s3);
 }
 
 template <int HP, int KCH, int LB, bool DW, int NW>
@@ -519,8 +541,11 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
         k_contract_tc<HP, KCH, LB, DW, NW><<<grid, NW * 32, smem, st>>>(a2, nkc, nslots, DW_FLUSH);
         cudaError_t le = cudaGetLastError();
         if (le == cudaSuccess) {
-            k_dw_reduce<HP><<<dim3(qc_ceil_div(per, 256), nctas), 256, 0, st>>>(a2.dW_scratch, a2.dW_counts, nslots, nkc,
-                                                                                 a.Cx, a.H, a.Cy, a.CyP, a.dW2);
+            k_dw_reduce<HP><<<dim3(qc_ceil_div(per, 256), nctas), 256, 0, st>>>(a2.dW_scratch, a2.dW_counts, nslots, nkc);
+            le = cudaGetLastError();
+        }
+        if (le == cudaSuccess) {
+            k_dw_sum_ctas<HP><<<qc_ceil_div(per, 256), 256, 0, st>>>(a2.dW_scratch, nctas, nslots, nkc, a.Cx, a.H, a.Cy, a.CyP, a.dW2);
             le = cudaGetLastError();
         }
         if (own) cudaFreeAsync(buf, st);

@@ -28,8 +28,8 @@ inline int hp_of(int H) { return H <= 4 ? 4 : (H <= 8 ? 8 : (H <= 16 ? 16 : 32))
 
 struct Plan {
     float *phi, *xp, *yp, *w2, *gp, *w3, *dphi, *w2t, *dw2, *dxp;
-    void* cws;
-    size_t cws_bytes, total;
+    void *cws, *mws;
+    size_t cws_bytes, mws_bytes, total;
     int HP, nsl;
 };
 
@@ -55,6 +55,8 @@ Plan make_plan(const qc_layer_t* L, int B, void* ws)
     pl.dxp = c.take<float>(xin);
     pl.cws_bytes = qc_contract_workspace_bytes(L->Co, H, HP, L->Ci, L->Ni, B);
     pl.cws = c.take<char>(pl.cws_bytes);
+    pl.mws_bytes = qc_pair_phi_bwd_workspace_bytes(L->P, L->d, &L->mlp, HP);   // partial sums of the per-pair backward
+    pl.mws = c.take<char>(pl.mws_bytes);
     pl.total = c.used;
     return pl;
 }
@@ -109,8 +111,9 @@ int qc_layer_backward(const qc_layer_t* L, const float* grad_out, int B, float* 
         QC_CUDA(cudaMemsetAsync(d_hidden[l], 0, (size_t)L->mlp.dims[l] * L->mlp.dims[l + 1] * sizeof(float), st));
     }
     if (d_quad_w != nullptr) QC_CUDA(cudaMemsetAsync(d_quad_w, 0, (size_t)L->Ni * sizeof(float), st));
-    if ((rc = qc_pair_phi_bwd(L->out_pts, L->in_pts, L->quad_w, L->pair_row, L->pair_col, L->P, L->d, &L->mlp, pl.HP, pl.dphi,
-                              pl.nsl, d_hidden, d_quad_w, stream)) != 0)
+    if (L->P > 0 &&
+        (rc = qc_pair_phi_bwd_ws(L->out_pts, L->in_pts, L->quad_w, L->pair_row, L->pair_col, L->P, L->d, &L->mlp, pl.HP, pl.dphi,
+                                 pl.nsl, d_hidden, d_quad_w, L->csc_ptr, L->csc_pair, L->Ni, pl.mws, pl.mws_bytes, stream)) != 0)
         return rc;
     // d features (CSC view) and d W_last in the same pass
     if ((rc = qc_repack_wlast(L->w_last, L->Ci, L->Co, L->H, pl.HP, 1, pl.w2t, stream)) != 0) return rc;

@@ -124,7 +124,7 @@ k_pair_phi_fwd_tc(const float* __restrict__ out_pts, const float* __restrict__ i
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     constexpr int TCOLS = W == 32 ? 128 : 64;   // A_hi, A_lo, D: 3 W columns
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int L = m.n_hidden;
     for (int t = tid; t < W * 4; t += 128) {
@@ -250,14 +250,19 @@ __global__ void __launch_bounds__(128)
 k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_pts,
                const float* __restrict__ quad_w, const int* __restrict__ pair_row,
                const int* __restrict__ pair_col, int64_t P, int d, MlpDev m, int HP,
-               const float* __restrict__ dphi, int nslices, float* __restrict__ d_quad_w)
+               const float* __restrict__ dphi, int nslices, float* __restrict__ d_quad_w,
+               float* __restrict__ part, float* __restrict__ dwq_out)
 {
+    // part / dwq_out != nullptr: deterministic mode (qc_pair_phi_bwd_ws) -- the block's weight-gradient sums go to its
+    // row of `part`, the per-pair quadrature-weight terms to dwq_out[p]; k_mlp_finish / k_dwq_segsum add them in fixed
+    // orders.  Otherwise one atomicAdd per entry per block / per pair.
     constexpr int NT = 128;
     extern __shared__ float smem[];
     float* Wsm = smem;                                  // [n_hidden][WMAX*WMAX]
     float* dWs = Wsm + m.n_hidden * WMAX * WMAX;        // [n_hidden][WMAX*WMAX]
     float* da_s = dWs + m.n_hidden * WMAX * WMAX;       // [NT][WMAX]
     float* x_s = da_s + NT * WMAX;                      // [NT][WMAX]
+    float* part_s = x_s + NT * WMAX;                    // [NQR][WMAX*WMAX] partial tiles of the block's q ranges
     load_weights<WMAX>(m, Wsm);
     for (int t = threadIdx.x; t < m.n_hidden * WMAX * WMAX; t += NT) dWs[t] = 0.f;
     __syncthreads();
@@ -345,7 +350,8 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
             dwq = fmaf(g, LT > 0 ? xs[LT][h] : xs[L][h], dwq);
             dx[h] = wq * g;
         }
-        if (valid && d_quad_w) atomicAdd(&d_quad_w[c], dwq);
+        if (valid && dwq_out) dwq_out[p] = dwq;
+        else if (valid && d_quad_w) atomicAdd(&d_quad_w[c], dwq);
 
 #pragma unroll(LT > 0 ? LMAX : 1)
         for (int l = LMAX - 1; l >= 0; --l) {
@@ -361,7 +367,7 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
             __syncthreads();
             // dW_l[o][k] += sum_q da[q][o] * x[q][k]: a register-tiled mini-GEMM over the block's 128 pairs.
             // Every thread owns a TL x TL tile of (o,k) and a range of q; vector loads of TL values feed
-            // TL*TL FMAs; the q ranges are combined with shared-memory atomics.
+            // TL*TL FMAs; the q ranges are combined in a fixed order (one shared-memory slice per range).
             {
                 constexpr int TL = WMAX >= 16 ? 4 : 2;
                 constexpr int TPR = WMAX / TL, NTILE = TPR * TPR;
@@ -395,8 +401,14 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
 #pragma unroll
                 for (int i = 0; i < TL; ++i)
 #pragma unroll
-                    for (int j = 0; j < TL; ++j)
-                        atomicAdd(&dWs[l * WMAX * WMAX + (o0 + i) * WMAX + k0 + j], acc[i][j]);
+                    for (int j = 0; j < TL; ++j) part_s[qr * WMAX * WMAX + (o0 + i) * WMAX + k0 + j] = acc[i][j];
+                __syncthreads();
+                for (int t = threadIdx.x; t < WMAX * WMAX; t += NT) {
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int q = 0; q < NQR; ++q) sacc += part_s[q * WMAX * WMAX + t];
+                    dWs[l * WMAX * WMAX + t] += sacc;
+                }
             }
             if (l > 0) {
 #pragma unroll
@@ -411,6 +423,12 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
         }
     }
     // flush
+    __syncthreads();
+    if (part != nullptr) {
+        float* row = part + (size_t)blockIdx.x * (L * WMAX * WMAX);
+        for (int t = threadIdx.x; t < L * WMAX * WMAX; t += NT) row[t] = dWs[t];
+        return;
+    }
     for (int l = 0; l < L; ++l) {
         const int nin = m.dims[l], nout = m.dims[l + 1];
         for (int t = threadIdx.x; t < WMAX * WMAX; t += NT) {
@@ -418,6 +436,34 @@ k_pair_phi_bwd(const float* __restrict__ out_pts, const float* __restrict__ in_p
             if (o < nout && k < nin) atomicAdd(&m.dw[l][o * nin + k], dWs[l * WMAX * WMAX + t]);
         }
     }
+}
+
+// Deterministic finish of qc_pair_phi_bwd_ws, one launch: blocks [0, nb_w) add the blocks' rows of `part`
+// ([nblocks][L][W*W]) into dw[l][o][k] -- one warp per entry, lane j adds rows j, j + 32, ... in sequence, then a fixed
+// shuffle tree; blocks [nb_w, ...) add the pairs' quadrature-weight terms into d_quad_w[k] in the order of the CSC list
+// of in-point k (one thread per in-point).
+__global__ void __launch_bounds__(128)
+k_mlp_finish(const float* __restrict__ part, int nblocks, int W, MlpDev m, int nb_w, const float* __restrict__ dwq,
+             const int* __restrict__ csc_ptr, const int* __restrict__ csc_pair, int Ni, float* __restrict__ d_quad_w)
+{
+    if ((int)blockIdx.x >= nb_w) {
+        const int k = ((int)blockIdx.x - nb_w) * 128 + threadIdx.x;
+        if (k >= Ni) return;
+        float s = 0.f;
+        for (int e = csc_ptr[k]; e < csc_ptr[k + 1]; ++e) s += dwq[csc_pair[e]];
+        d_quad_w[k] += s;
+        return;
+    }
+    const int e = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int L = m.n_hidden;
+    if (e >= L * W * W) return;
+    const int l = e / (W * W), o = (e % (W * W)) / W, k = e % W;
+    if (o >= m.dims[l + 1] || k >= m.dims[l]) return;
+    float v = 0.f;
+    for (int b = lane; b < nblocks; b += 32) v += part[(size_t)b * (L * W * W) + e];
+#pragma unroll
+    for (int mk = 16; mk >= 1; mk >>= 1) v += __shfl_xor_sync(0xffffffffu, v, mk);
+    if (lane == 0) m.dw[l][o * m.dims[l] + k] += v;
 }
 
 // Tensor-core backward for wide filter MLPs with exactly two hidden layers (d -> h1 -> h2, widths <= W = 16 or 32:
@@ -437,7 +483,8 @@ __global__ void __launch_bounds__(128, 2)
 k_pair_phi_bwd_tc(const float* __restrict__ out_pts, const float* __restrict__ in_pts,
                   const float* __restrict__ quad_w, const int* __restrict__ pair_row,
                   const int* __restrict__ pair_col, int64_t P, int d, MlpDev m, int HP,
-                  const float* __restrict__ dphi, int nslices, float* __restrict__ d_quad_w)
+                  const float* __restrict__ dphi, int nslices, float* __restrict__ d_quad_w,
+                  float* __restrict__ part, float* __restrict__ dwq_out)
 {
     extern __shared__ __align__(1024) float smem_raw[];
     float* S_hi = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // [4][64 rows][32]
@@ -606,7 +653,8 @@ k_pair_phi_bwd_tc(const float* __restrict__ out_pts, const float* __restrict__ i
                 da[h] = wq * gh * sc.y;
             }
         }
-        if (valid && d_quad_w) atomicAdd(&d_quad_w[c], dwq);
+        if (valid && dwq_out) dwq_out[p] = dwq;
+        else if (valid && d_quad_w) atomicAdd(&d_quad_w[c], dwq);
         // G: dW1 += da1^T x1 (staged tile) and X: dx1 = da1 W1 (TMEM operand), issued together
 #pragma unroll
         for (int o = 0; o < W; ++o) put_s(o, da[o]);
@@ -656,7 +704,15 @@ k_pair_phi_bwd_tc(const float* __restrict__ out_pts, const float* __restrict__ i
         tc::fence_before_sync();          // the next tile's MMAs overwrite what was just read
     }
     // flush: lane l < 16 of warp w owns row 16 w + l
-    if (warp * 16 < W && lane < 16) {
+    if (warp * 16 < W && lane < 16 && part != nullptr) {
+        // deterministic mode: this CTA's rows of `part` ([2][W*W], same layout as the scalar kernel's)
+        const int o = warp * 16 + lane;
+        float* row = part + (size_t)blockIdx.x * (2 * W * W);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) row[o * W + k] = dW0acc[k];
+#pragma unroll
+        for (int k = 0; k < W; ++k) row[W * W + o * W + k] = dW1acc[k];
+    } else if (warp * 16 < W && lane < 16) {
         const int o = warp * 16 + lane;
         if (o < n2)
 #pragma unroll
@@ -721,15 +777,20 @@ int launch_fwd_tc(const float* out_pts, const float* in_pts, const float* quad_w
     return 0;
 }
 
+// blocks of the backward kernels: one resident wave (the kernels sweep with a grid stride); the deterministic mode's
+// workspace has one row per block
+inline int bwd_blocks(int64_t P, bool tc) { return min(qc_ceil_div(P, 128), qc_num_sms() * (tc ? 2 : 4)); }
+
 template <int W>
 int launch_bwd_tc(const float* out_pts, const float* in_pts, const float* quad_w, const int* pair_row,
                   const int* pair_col, int64_t P, int d, const MlpDev& m, int HP, const float* dphi,
-                  int nslices, float* d_quad_w, cudaStream_t st)
+                  int nslices, float* d_quad_w, float* part, float* dwq_out, cudaStream_t st)
 {
     const size_t smem = ((size_t)2 * 4 * 64 * 32 + 4 * W * W + W * 4) * 4 + 1024;
     QC_CUDA((qc_set_max_smem<k_pair_phi_bwd_tc<W>>((int)smem)));
-    const int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 2);
-    k_pair_phi_bwd_tc<W><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w);
+    const int blocks = bwd_blocks(P, true);
+    k_pair_phi_bwd_tc<W><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w,
+                                                    part, dwq_out);
     QC_CHECK_LAUNCH();
     return 0;
 }
@@ -737,12 +798,14 @@ int launch_bwd_tc(const float* out_pts, const float* in_pts, const float* quad_w
 template <int WMAX, int LT>
 int launch_bwd(const float* out_pts, const float* in_pts, const float* quad_w, const int* pair_row,
                const int* pair_col, int64_t P, int d, const MlpDev& m, int HP, const float* dphi,
-               int nslices, float* d_quad_w, cudaStream_t st)
+               int nslices, float* d_quad_w, float* part, float* dwq_out, cudaStream_t st)
 {
-    size_t smem = ((size_t)2 * m.n_hidden * WMAX * WMAX + 2 * 128 * WMAX) * 4;
+    constexpr int TL = WMAX >= 16 ? 4 : 2, NQR = 128 / ((WMAX / TL) * (WMAX / TL));
+    size_t smem = ((size_t)2 * m.n_hidden * WMAX * WMAX + 2 * 128 * WMAX + NQR * WMAX * WMAX) * 4;
     QC_CUDA((qc_set_max_smem<k_pair_phi_bwd<WMAX, LT>>((int)smem)));
-    int blocks = min(qc_ceil_div(P, 128), qc_num_sms() * 16);
-    k_pair_phi_bwd<WMAX, LT><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w);
+    const int blocks = part ? bwd_blocks(P, false) : min(qc_ceil_div(P, 128), qc_num_sms() * 16);
+    k_pair_phi_bwd<WMAX, LT><<<blocks, 128, smem, st>>>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w,
+                                                        part, dwq_out);
     QC_CHECK_LAUNCH();
     return 0;
 }
@@ -780,10 +843,12 @@ int qc_pair_phi_fwd(const float* out_pts, const float* in_pts, const float* quad
     return QC_EUNSUP;
 }
 
-int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad_w,
-                    const int* pair_row, const int* pair_col, int64_t P, int d,
-                    const qc_mlp_t* mlp, int HP, const float* dphi, int nslices,
-                    float* const* d_mlp_w, float* d_quad_w, void* stream)
+static bool mlp_bwd_uses_tc(int wsel, int n_hidden) { return wsel >= 16 && n_hidden == 2 && getenv("QC_MLP_NO_TC") == nullptr; }
+
+static int pair_phi_bwd_impl(const float* out_pts, const float* in_pts, const float* quad_w,
+                             const int* pair_row, const int* pair_col, int64_t P, int d,
+                             const qc_mlp_t* mlp, int HP, const float* dphi, int nslices,
+                             float* const* d_mlp_w, float* d_quad_w, float* part, float* dwq_out, int* wsel_out, void* stream)
 {
     if (P <= 0) return 0;
     if (d < 1 || d > 3 || nslices < 1) return QC_EUNSUP;
@@ -796,12 +861,13 @@ int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad
     if (wmax < 0 || HP < H || HP > 32 || (HP & 3)) return QC_EUNSUP;
     cudaStream_t st = (cudaStream_t)stream;
     const int wsel = wmax > HP ? wmax : HP;
+    if (wsel_out) *wsel_out = wsel;
     // wide MLPs with exactly two hidden layers: the 32 x 32 products run on the tensor cores
-    if (wsel >= 16 && m.n_hidden == 2 && getenv("QC_MLP_NO_TC") == nullptr) {
-        if (wsel == 16) return launch_bwd_tc<16>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
-        return launch_bwd_tc<32>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st);
+    if (mlp_bwd_uses_tc(wsel, m.n_hidden)) {
+        if (wsel == 16) return launch_bwd_tc<16>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, part, dwq_out, st);
+        return launch_bwd_tc<32>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, part, dwq_out, st);
     }
-#define QC_BWD(W, LTV) return launch_bwd<W, LTV>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, st)
+#define QC_BWD(W, LTV) return launch_bwd<W, LTV>(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, m, HP, dphi, nslices, d_quad_w, part, dwq_out, st)
     const int L = m.n_hidden;
     switch (wsel) {   // register-resident activations when (2L+1)*W floats fit comfortably, else the general kernel
         case 4: if (L == 1) QC_BWD(4, 1); if (L == 2) QC_BWD(4, 2); if (L == 3) QC_BWD(4, 3); if (L == 4) QC_BWD(4, 4); QC_BWD(4, 0);
@@ -811,6 +877,63 @@ int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad
     }
 #undef QC_BWD
     return QC_EUNSUP;
+}
+
+int qc_pair_phi_bwd(const float* out_pts, const float* in_pts, const float* quad_w,
+                    const int* pair_row, const int* pair_col, int64_t P, int d,
+                    const qc_mlp_t* mlp, int HP, const float* dphi, int nslices,
+                    float* const* d_mlp_w, float* d_quad_w, void* stream)
+{
+    return pair_phi_bwd_impl(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, mlp, HP, dphi, nslices, d_mlp_w, d_quad_w,
+                             nullptr, nullptr, nullptr, stream);
+}
+
+// workspace layout of the deterministic variant: [blocks][n_hidden][W*W] partial weight gradients, then [P] pair terms
+static size_t mlp_ws_rows(int64_t P, int d, const qc_mlp_t* mlp, int HP, int* wsel_out, int* blocks_out)
+{
+    const int wmax = pick_wmax(mlp, d);
+    if (wmax < 0) return 0;
+    const int wsel = wmax > HP ? wmax : HP;
+    const int blocks = bwd_blocks(P, mlp_bwd_uses_tc(wsel, mlp->n_hidden));
+    if (wsel_out) *wsel_out = wsel;
+    if (blocks_out) *blocks_out = blocks;
+    return (size_t)blocks * (mlp->n_hidden > 0 ? mlp->n_hidden : 1) * wsel * wsel;
+}
+
+size_t qc_pair_phi_bwd_workspace_bytes(int64_t P, int d, const qc_mlp_t* mlp, int HP)
+{
+    if (P <= 0 || mlp == nullptr) return 0;
+    return (mlp_ws_rows(P, d, mlp, HP, nullptr, nullptr) + (size_t)P) * sizeof(float);
+}
+
+int qc_pair_phi_bwd_ws(const float* out_pts, const float* in_pts, const float* quad_w,
+                       const int* pair_row, const int* pair_col, int64_t P, int d,
+                       const qc_mlp_t* mlp, int HP, const float* dphi, int nslices,
+                       float* const* d_mlp_w, float* d_quad_w, const int* csc_ptr, const int* csc_pair, int Ni,
+                       void* ws, size_t ws_bytes, void* stream)
+{
+    if (P <= 0) return 0;
+    if (mlp == nullptr || (d_quad_w != nullptr && (csc_ptr == nullptr || csc_pair == nullptr || Ni <= 0))) return QC_EINVAL;
+    int wsel = 0, blocks = 0;
+    const size_t rows = mlp_ws_rows(P, d, mlp, HP, &wsel, &blocks);
+    if (rows == 0 && mlp->n_hidden > 0) return QC_EUNSUP;
+    if (ws == nullptr || ws_bytes < (rows + (size_t)P) * sizeof(float)) return QC_EWORKSPACE;
+    float* part = reinterpret_cast<float*>(ws);
+    float* dwq = part + rows;
+    int rc = pair_phi_bwd_impl(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, mlp, HP, dphi, nslices, d_mlp_w, d_quad_w,
+                               part, d_quad_w ? dwq : nullptr, nullptr, stream);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    MlpDev m;
+    rc = fill_dev(mlp, d, m);
+    if (rc) return rc;
+    for (int l = 0; l < m.n_hidden; ++l) m.dw[l] = d_mlp_w[l];
+    const int nb_w = qc_ceil_div((int64_t)m.n_hidden * wsel * wsel, 4), nb_q = d_quad_w ? qc_ceil_div(Ni, 128) : 0;
+    if (nb_w + nb_q > 0) {
+        k_mlp_finish<<<nb_w + nb_q, 128, 0, st>>>(part, blocks, wsel, m, nb_w, dwq, csc_ptr, csc_pair, Ni, d_quad_w);
+        QC_CHECK_LAUNCH();
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -13,6 +13,9 @@ namespace {
 constexpr int WM_HID = 8;    // hidden width (fixed by the reference)
 constexpr int WM_MAXIN = 12; // E*d <= 12 (tetrahedra in 3-D)
 constexpr int WM_MAXE = 4;
+constexpr int WM_NW = WM_HID * WM_MAXIN + 2 * WM_HID * WM_HID + WM_MAXE * WM_HID;   // per-block weight-gradient sums
+constexpr int WM_NB = 3 * WM_HID + WM_MAXE;                                        // ... and bias-gradient sums
+constexpr int WM_PART = WM_NW + WM_NB;
 
 struct WmParams {
     const float* W[4];
@@ -134,7 +137,7 @@ __global__ void k_vertex_sum(const float* __restrict__ el_w, const int* __restri
 // atomic-free; one atomicAdd per parameter entry per block at the end.
 __global__ void __launch_bounds__(128)
 k_wm_bwd(const float* __restrict__ pts, const int* __restrict__ adj, int M, int E, int dd, WmParams p,
-         const float* __restrict__ gw)
+         const float* __restrict__ gw, float* __restrict__ part)
 {
     constexpr int NT = 128;
     __shared__ WmSmem s;
@@ -240,6 +243,13 @@ k_wm_bwd(const float* __restrict__ pts, const int* __restrict__ adj, int M, int 
         reduce_layer(aW0, accb, WM_HID, F0, WM_MAXIN);
     }
     __syncthreads();
+    if (part != nullptr) {
+        // deterministic mode: this block's sums go to its own row of the workspace; k_wm_finish adds the rows in block order
+        float* row = part + (size_t)blockIdx.x * WM_PART;
+        for (int t = threadIdx.x; t < WM_NW; t += NT) row[t] = accW[t];
+        for (int t = threadIdx.x; t < WM_NB; t += NT) row[WM_NW + t] = accb[t];
+        return;
+    }
     for (int t = threadIdx.x; t < WM_HID * F0; t += NT) atomicAdd(&p.dW[0][t], aW0[(t / F0) * WM_MAXIN + t % F0]);
     for (int t = threadIdx.x; t < WM_HID * WM_HID; t += NT) {
         atomicAdd(&p.dW[1][t], aW1[t]);
@@ -252,6 +262,37 @@ k_wm_bwd(const float* __restrict__ pts, const int* __restrict__ adj, int M, int 
         atomicAdd(&p.db[2][t], accb[2 * WM_HID + t]);
     }
     for (int t = threadIdx.x; t < E; t += NT) atomicAdd(&p.db[3][t], accb[3 * WM_HID + t]);
+}
+
+// dW / db += the blocks' partial sums in a FIXED order (bit-reproducible): one warp per entry, lane j adds the rows
+// j, j + 32, ... in sequence, then a fixed xor-shuffle tree combines the 32 lanes
+__global__ void __launch_bounds__(128) k_wm_finish(const float* __restrict__ part, int nblocks, int E, int dd, WmParams p)
+{
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= WM_PART) return;
+    float v = 0.f;
+    for (int b = lane; b < nblocks; b += 32) v += part[(size_t)b * WM_PART + t];
+#pragma unroll
+    for (int mk = 16; mk >= 1; mk >>= 1) v += __shfl_xor_sync(0xffffffffu, v, mk);
+    if (lane != 0) return;
+    const int F0 = E * dd;
+    constexpr int O1 = WM_HID * WM_MAXIN, O2 = O1 + WM_HID * WM_HID, O3 = O2 + WM_HID * WM_HID;
+    if (t < O1) {
+        const int o = t / WM_MAXIN, k = t % WM_MAXIN;
+        if (k < F0) p.dW[0][o * F0 + k] += v;
+    } else if (t < O2) {
+        p.dW[1][t - O1] += v;
+    } else if (t < O3) {
+        p.dW[2][t - O2] += v;
+    } else if (t < WM_NW) {
+        if (t - O3 < E * WM_HID) p.dW[3][t - O3] += v;
+    } else {
+        const int u = t - WM_NW;
+        if (u < WM_HID) p.db[0][u] += v;
+        else if (u < 2 * WM_HID) p.db[1][u - WM_HID] += v;
+        else if (u < 3 * WM_HID) p.db[2][u - 2 * WM_HID] += v;
+        else if (u - 3 * WM_HID < E) p.db[3][u - 3 * WM_HID] += v;
+    }
 }
 
 int fill(WmParams& p, const float* const* wb, float* const* dwb)
@@ -294,7 +335,28 @@ int qc_weight_map_bwd(const float* pts, const int* adj, int M, int E, int dd, co
     if (M <= 0 || E < 2 || E > WM_MAXE || dd < 1 || dd > 3 || E * dd > WM_MAXIN) return QC_EUNSUP;
     WmParams p;
     fill(p, wb, dwb);
-    k_wm_bwd<<<min(qc_ceil_div(M, 128), qc_num_sms() * 8), 128, 0, (cudaStream_t)stream>>>(pts, adj, M, E, dd, p, gw);
+    k_wm_bwd<<<min(qc_ceil_div(M, 128), qc_num_sms() * 8), 128, 0, (cudaStream_t)stream>>>(pts, adj, M, E, dd, p, gw, nullptr);
+    QC_CHECK_LAUNCH();
+    return 0;
+}
+
+size_t qc_weight_map_bwd_workspace_bytes(int M)
+{
+    if (M <= 0) return 0;
+    return (size_t)min(qc_ceil_div(M, 128), qc_num_sms() * 8) * WM_PART * sizeof(float);
+}
+
+int qc_weight_map_bwd_ws(const float* pts, const int* adj, int M, int E, int dd, const float* const* wb,
+                         const float* gw, float* const* dwb, void* ws, size_t ws_bytes, void* stream)
+{
+    if (M <= 0 || E < 2 || E > WM_MAXE || dd < 1 || dd > 3 || E * dd > WM_MAXIN) return QC_EUNSUP;
+    const int blocks = min(qc_ceil_div(M, 128), qc_num_sms() * 8);
+    if (ws == nullptr || ws_bytes < (size_t)blocks * WM_PART * sizeof(float)) return QC_EWORKSPACE;
+    WmParams p;
+    fill(p, wb, dwb);
+    k_wm_bwd<<<blocks, 128, 0, (cudaStream_t)stream>>>(pts, adj, M, E, dd, p, gw, reinterpret_cast<float*>(ws));
+    QC_CHECK_LAUNCH();
+    k_wm_finish<<<qc_ceil_div(WM_PART, 4), 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(ws), blocks, E, dd, p);
     QC_CHECK_LAUNCH();
     return 0;
 }

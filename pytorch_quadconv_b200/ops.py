@@ -221,6 +221,20 @@ def _grad_shapes(hidden_ws, Ni, Ci, Co, H):
     return [tuple(w.shape) for w in hidden_ws] + [(Ni,), (Ci * Co, H)]
 
 
+def _pair_phi_bwd(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, mlp, HP, dphi, nsl, dptrs, d_quad_w, csc_ptr, csc_pair,
+                  Ni, st):
+    """Per-pair chain rule through the hidden filter layers (qc_pair_phi_bwd_ws): the block partial sums and the per-pair
+    quadrature-weight terms go through a workspace and are added in fixed orders, so the parameter gradients of the
+    fp32 path are bit-reproducible run to run."""
+    import ctypes
+    L = C.lib()
+    wsb = L.qc_pair_phi_bwd_workspace_bytes(P, d, ctypes.byref(mlp), HP)
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dphi.device)
+    C.check(L.qc_pair_phi_bwd_ws(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row), C.ptr(pair_col), P, d, mlp, HP,
+                                 C.ptr(dphi), nsl, dptrs, C.ptr(d_quad_w), C.ptr(csc_ptr), C.ptr(csc_pair), Ni, C.ptr(ws), wsb,
+                                 st), "qc_pair_phi_bwd_ws")
+
+
 def _pack(x: Tensor) -> Tensor:
     B, Cc, N = x.shape
     xp = torch.empty(_packed_shape(B, Cc, N), dtype=torch.float32, device=x.device)
@@ -598,9 +612,8 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
         mlp = C.make_mlp(d, hidden_ws, mlp_bf16)
         import ctypes
         dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
-        C.check(L.qc_pair_phi_bwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row),
-                                  C.ptr(pair_col), P, d, mlp, HP, C.ptr(dphi), nsl, dptrs, C.ptr(d_quad_w), st),
-                "qc_pair_phi_bwd")
+        _pair_phi_bwd(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, mlp, HP, dphi, nsl, dptrs, d_quad_w, csc_ptr, csc_pair,
+                      Ni, st)
         del dphi
         # d features and d W_last from T'[b][n][(j,h)] = sum_p phi[p][h] G[out(p)][b][j] (CSC view)
         Tp = torch.empty((B, Ni, Co * H), **f32)
@@ -632,8 +645,9 @@ def qc_backward(grad_out: Tensor, xp: Tensor, phi: Tensor, out_pts: Tensor, in_p
     mlp = C.make_mlp(d, hidden_ws, mlp_bf16)
     import ctypes
     dptrs = (ctypes.c_void_p * max(len(d_hidden), 1))(*[C.ptr(t) for t in d_hidden])
-    C.check(L.qc_pair_phi_bwd(C.ptr(out_pts), C.ptr(in_pts), C.ptr(quad_w), C.ptr(pair_row), C.ptr(pair_col),
-                              P, d, mlp, HP, C.ptr(dphi), nsl, dptrs, C.ptr(d_quad_w), st), "qc_pair_phi_bwd")
+    if P > 0:
+        _pair_phi_bwd(out_pts, in_pts, quad_w, pair_row, pair_col, P, d, mlp, HP, dphi, nsl, dptrs, d_quad_w, csc_ptr, csc_pair,
+                      Ni, st)
 
     # d features (grouped by in point through the CSC tables) + d W_last in the same pass
     W2t = torch.empty((Co * H, CiP), **f32)
@@ -686,10 +700,15 @@ def _layer_desc(out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair
 
 
 @functools.lru_cache(maxsize=256)
-def single_call_workspace_bytes(B, Ci, Co, H, Ni, No, P, d=2) -> int:
-    """Workspace of qc_layer_forward/backward for a layer of this shape (only the sizes of the descriptor are read)."""
+def single_call_workspace_bytes(B, Ci, Co, H, Ni, No, P, d=2, hidden=()) -> int:
+    """Workspace of qc_layer_forward/backward for a layer of this shape (only the sizes of the descriptor are read);
+    `hidden` = the hidden widths of the filter MLP (the last one is H)."""
     desc = C.QcLayer()
     desc.d, desc.Ni, desc.No, desc.Ci, desc.Co, desc.H, desc.P = d, Ni, No, Ci, Co, H, P
+    desc.mlp.n_hidden = len(hidden)
+    desc.mlp.dims[0] = d
+    for l, h in enumerate(hidden):
+        desc.mlp.dims[l + 1] = h
     import ctypes
     return int(C.lib().qc_layer_workspace_bytes(ctypes.byref(desc), B))
 
@@ -730,7 +749,8 @@ def _(features, out_pts, in_pts, quad_w, hidden_ws, w_last, bias, pair_row, pair
       csc_row, order_out, order_in, in_channels, out_channels):
     B, Ci, Ni = features.shape
     No = out_pts.shape[0]
-    wsb = single_call_workspace_bytes(B, Ci, out_channels, w_last.shape[1], Ni, No, pair_row.shape[0], out_pts.shape[1])
+    wsb = single_call_workspace_bytes(B, Ci, out_channels, w_last.shape[1], Ni, No, pair_row.shape[0], out_pts.shape[1],
+                                      tuple(int(w.shape[0]) for w in hidden_ws))
     return features.new_empty((B, out_channels, No)), features.new_empty(wsb, dtype=torch.uint8)
 
 
@@ -773,12 +793,12 @@ def _(grad_out, ws, out_pts, in_pts, quad_w, hidden_ws, w_last, pair_row, pair_c
             e(_flat_layout(shapes)[2])]
 
 
-def _single_call_ok(B, Ci, Co, H, Ni, No, P, d, mlp_bf16) -> bool:
+def _single_call_ok(B, Ci, Co, H, Ni, No, P, d, mlp_bf16, hidden=()) -> bool:
     if mlp_bf16 or P <= 0 or SINGLE_CALL_MAX_BYTES <= 0 or H > 32:
         return False
     if _use_wide(Ci, Co, H, _hp(H), B, max(No, Ni)):
         return False
-    return single_call_workspace_bytes(B, Ci, Co, H, Ni, No, P, d) <= SINGLE_CALL_MAX_BYTES
+    return single_call_workspace_bytes(B, Ci, Co, H, Ni, No, P, d, hidden) <= SINGLE_CALL_MAX_BYTES
 
 
 class _QuadConvFn(torch.autograd.Function):
@@ -795,7 +815,7 @@ class _QuadConvFn(torch.autograd.Function):
             # the tensor-core backward reads the bf16 packed features; shapes it does not serve re-pack the fp32 input
             ctx.save_for_backward(xh if tc.get("bwd") is not None else features, phi, quad_w, w_last, *hidden_ws)
         elif _single_call_ok(features.shape[0], Ci, Co, w_last.shape[1], in_pts.shape[0], out_pts.shape[0],
-                             pair_row.numel(), out_pts.shape[1], mlp_bf16):
+                             pair_row.numel(), out_pts.shape[1], mlp_bf16, tuple(int(w.shape[0]) for w in hidden_ws)):
             out, ws = _call(layer_forward, features, out_pts, in_pts, quad_w, list(hidden_ws), w_last, bias, pair_row, pair_col,
                                     row_ptr, csc_ptr, csc_pair, csc_row, order_out, order_in, Ci, Co)
             ctx.save_for_backward(ws, quad_w, w_last, *hidden_ws)
@@ -929,8 +949,10 @@ def weight_map_bwd(grad_w: Tensor, points: Tensor, adj32: Tensor, params: Sequen
     shapes = [tuple(p.shape) for p in params]
     flat = torch.zeros(_flat_layout(shapes)[2], dtype=torch.float32, device=grad_w.device)
     grads = _carve(flat, shapes)
-    C.check(C.lib().qc_weight_map_bwd(C.ptr(points), C.ptr(adj32), M, E, points.shape[1], _ptr_array(params),
-                                      C.ptr(grad_w), _ptr_array(grads), C.stream()), "qc_weight_map_bwd")
+    wsb = C.lib().qc_weight_map_bwd_workspace_bytes(M)     # per-block partial sums, added in block order (bit-reproducible)
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=grad_w.device)
+    C.check(C.lib().qc_weight_map_bwd_ws(C.ptr(points), C.ptr(adj32), M, E, points.shape[1], _ptr_array(params),
+                                         C.ptr(grad_w), _ptr_array(grads), C.ptr(ws), wsb, C.stream()), "qc_weight_map_bwd_ws")
     return flat
 
 

@@ -632,3 +632,48 @@ def test_custom_ops_pass_opcheck():
     torch.library.opcheck(ops.weight_map, (p, adj32, inc_ptr, inc_idx, wm), test_utils=utils)
     torch.library.opcheck(ops.weight_map_bwd, (torch.ones(n, device=dev), p, adj32, wm), test_utils=utils)
     torch.library.opcheck(ops.pairs_to_tables, (layer.eval_indices.data, n, n), test_utils=utils)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fs,ci,co,B", [([8, 8], 16, 16, 8), ([32, 32], 8, 8, 8), ([8, 8], 4, 8, 64)])
+def test_fp32_training_step_is_bit_reproducible(fs, ci, co, B):
+    """The output and every gradient of an fp32 step but one -- features, hidden filter layers, bias, quadrature-weight
+    network -- are bit-identical run to run: block partial sums and per-pair terms are combined in fixed orders
+    (qc_pair_phi_bwd_ws, qc_weight_map_bwd_ws, the two-pass reduction of the dW_last slots), never with float atomics.
+    The exception is d W_last: inside the fused backward kernel the two row blocks of a CTA take the dW operand buffer
+    in lock-acquisition order, so the TMEM accumulation order (and the last bits) vary; it is checked to 1e-6.
+    Covers the scalar and the tensor-core filter-MLP kernels, the single-call path and a folded layer."""
+    import pytorch_quadconv_b200 as q
+    torch.manual_seed(9)
+    dev = torch.device("cuda:0")
+    n = 3000
+    pts = torch.rand(n, 2)
+    mesh = q.MeshHandler(pts).construct([n, 0], mirror=True, quad_map="mfnus").to(dev)
+    n1 = mesh.point_seq[1]
+    enc = q.QuadConv(spatial_dim=2, in_points=n, out_points=n, in_channels=ci, out_channels=co, filter_seq=fs,
+                     output_same=True, bias=True, decay_param=0.06).to(dev)
+    dec = q.QuadConv(spatial_dim=2, in_points=n, out_points=n, in_channels=co, out_channels=ci, filter_seq=fs,
+                     output_same=True, bias=True, decay_param=0.06).to(dev)
+    pool, up = q.Mesh_MaxPool(activation='sin'), q.Mesh_MaxPool(adjoint=True)
+    x = torch.randn(B, ci, n, device=dev)
+    named = ([("enc." + k, p) for k, p in enc.named_parameters()] + [("dec." + k, p) for k, p in dec.named_parameters()] +
+             [("mesh." + k, p) for k, p in mesh.named_parameters()])
+    last = f"filter.{2 * len(fs)}.weight"
+    runs = []
+    for _ in range(3):
+        mesh.reset()
+        for _, p in named:
+            p.grad = None
+        xi = x.clone().requires_grad_()
+        y = dec(mesh, up(mesh, pool(mesh, enc(mesh, xi))))
+        torch.nn.functional.mse_loss(y, x).backward()
+        torch.cuda.synchronize()
+        runs.append([("y", y.detach().clone()), ("dx", xi.grad.clone())] +
+                    [(k, p.grad.clone()) for k, p in named if p.grad is not None])
+    assert len(runs[0]) >= 2 + 8
+    for other in runs[1:]:
+        for (k, a), (_, b) in zip(runs[0], other):
+            if k.endswith(last):
+                assert relerr(a.cpu(), b.cpu()) < 1e-6, k
+            else:
+                assert torch.equal(a, b), k
