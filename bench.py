@@ -593,13 +593,15 @@ def run_ours(args, w, rank, local_rank, world, dev, sub=False, tc_table=False):
     if rank == 0:
         launches = 0
         if is_ae:
-            launches = 8 * 14 + 8 * 2      # 8 QuadConv layers x 14 kernels (fwd+bwd) + 8 pool layers x 2
+            launches = 8 * 17 + 8 * 2 + 4 * 4      # 8 QuadConv layers x 17 kernels (fwd+bwd), 8 pool layers x 2, 4 weight maps x 4
         if table and sub:
-            launches = calls_per_step + 3
+            launches = calls_per_step + 4
         elif table:
             # every timed C-ABI call launches one of our kernels (csrc/*.cu); the dW variant of qc_contract adds
-            # k_dw_reduce, the fused weight map (MeshHandler.weights) three more per step; memsets are not counted
-            launches = calls_per_step + (1 if "qc_contract.bwd" in table else 0) + 3
+            # k_dw_reduce + k_dw_sum_ctas, qc_pair_phi_bwd_ws its finishing kernel, the fused weight map
+            # (MeshHandler.weights: k_wm_fwd, k_vertex_sum, k_wm_bwd, k_wm_finish) four more per step; memsets are not counted
+            launches = (calls_per_step + (2 if "qc_contract.bwd" in table else 0) +
+                        (1 if "qc_pair_phi_bwd_ws.bwd" in table else 0) + 4)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
