@@ -178,7 +178,7 @@ int qc_dphi(const float* Xp, int Nsrc, int Cx, const float* Gp, int Cg, const in
 
 /* Wide layers (last hidden width H > 8, or more than 32 channels on the dense side): the same
  * factorised evaluation of quadconv.py:213-227 with the intermediate written to HBM once, so that the
- * dense stage is a plain row-major GEMM done by the caller (cuBLAS / torch.matmul in fp32):
+ * dense stage is a plain row-major GEMM (qc_gemm_nt_tf32x3 / qc_gemm_tn_tf32x3 below, or any fp32 GEMM of the caller):
  *     T[b][t][c*H + h]   = sum_{q in S(t)} phi[phi_idx[q]][h] * Xp[src_idx[q]][c][b]     (accumulate)
  *     Y[b][t][:]         = T[b][t][:] * W2            W2[(c*H+h)][j] = W_last[c*Co+j][h]
  * and, backward, dT = G * W2^T followed by

@@ -8,7 +8,7 @@
 //     Y  = T  * W2^T   (A = T   [B*No x Ci*H], B = W2^T [Co   x Ci*H])      output transposed per batch
 //     dT = G^T * W2    (A = G^T [B*No x Co],   B = W2   [Ci*H x Co])        output row-major
 //     dX = T' * W2t^T  (A = T'  [B*Ni x Co*H], B = W2t^T[Ci   x Co*H])      output transposed per batch
-// (the fourth GEMM of the path, dW = X * T', reduces over the ROW index of T' and stays on cuBLAS.)
+// (the fourth GEMM of the path, dW = X * T', reduces over the ROW index of T': k_gemm_tn_tf32x3* further down.)
 //
 // One CTA = 8 warps = a 128-row x BN-column tile with the accumulator in TMEM.  The 32-wide K chunks of
 // A and B arrive by cp.async (two chunks ahead; FIFO commit groups, because register prefetching is serialised
