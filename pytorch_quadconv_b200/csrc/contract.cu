@@ -420,7 +420,7 @@ int qc_contract(const float* Xp, int Nsrc, int Cx, const int* seg_ptr, const int
     const int CXC = 64 / HP;
     const int NKC = qc_ceil_div(Cx, CXC);
     ContractArgs a;
-    a.X = Xp; a.Y = Yp; a.Z = Zp; a.dW2 = dW2; a.dW_scratch = nullptr; a.dW_counts = nullptr;
+    a.X = Xp; a.Y = Yp; a.Z = Zp; a.dW2 = dW2; a.dW_scratch = nullptr; a.dW_counts = nullptr; a.dw_ordered = 0;
     a.ws = workspace; a.ws_bytes = workspace_bytes;
     a.seg_ptr = seg_ptr; a.src_idx = src_idx; a.phi_idx = phi_idx; a.phi = phi; a.W2 = W2; a.order = order;
     a.Nsrc = Nsrc; a.Ndst = Ndst; a.Cx = Cx; a.Cy = Cy; a.CyP = (Cy + 3) & ~3; a.CyS = (Cy + 31) & ~31;

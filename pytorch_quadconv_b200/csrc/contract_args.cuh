@@ -19,6 +19,7 @@ struct ContractArgs {
     const float* W2;
     const int* order;
     int Nsrc, Ndst, Cx, Cy, CyP, CyS, H, LB, LWK, KSPLIT;
+    int dw_ordered;      // tcgen05 dW variant: the row blocks of a CTA take the dW operand buffer in strict alternation
 };
 
 struct DphiArgs {

@@ -318,7 +318,17 @@ k_contract_tc(const ContractArgs a, const int nkc, const int dw_nslots, const in
             int commits = 0;
             if (DW && leader) {
                 // take the operand buffer: lock, then wait until the previous user's MMAs have read it
-                while (atomicCAS(&lockw[0], 0, 1) != 0) __nanosleep(64);
+                // dw_ordered: the two row blocks alternate strictly (use 2u of the buffer is block 0's u-th, use 2u + 1
+                // block 1's -- both make one use per tile and chunk), which fixes the order of the TMEM accumulations
+                // and makes d W_last bit-reproducible; otherwise first come, first served
+                for (;;) {
+                    if (a.dw_ordered && ((*reinterpret_cast<volatile int*>(&lockw[1]) & 1) != rb)) {
+                        __nanosleep(32);
+                        continue;
+                    }
+                    if (atomicCAS(&lockw[0], 0, 1) == 0) break;
+                    __nanosleep(64);
+                }
                 __threadfence_block();
                 commits = *reinterpret_cast<volatile int*>(&lockw[1]);
                 if (commits > 0) tc::mbar_wait(opbar, (commits - 1) & 1);
@@ -538,6 +548,7 @@ int launch_tc(const ContractArgs& a, int B, cudaStream_t st)
         if (own) QC_CUDA(cudaMallocAsync((void**)&buf, fbytes + (size_t)nctas * sizeof(int), st));
         a2.dW_scratch = reinterpret_cast<float*>(buf);
         a2.dW_counts = reinterpret_cast<int*>(buf + fbytes);
+        a2.dw_ordered = getenv("QC_DW_FREE_ORDER") == nullptr ? 1 : 0;
         k_contract_tc<HP, KCH, LB, DW, NW><<<grid, NW * 32, smem, st>>>(a2, nkc, nslots, DW_FLUSH);
         cudaError_t le = cudaGetLastError();
         if (le == cudaSuccess) {
