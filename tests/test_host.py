@@ -134,3 +134,38 @@ def test_union_tile_tables_host_logic():
                 assert seg[m] <= e < seg[m + 1] and got[slot] == src[e] and not seen[e]
                 seen[e] = True
         assert seen.all()
+
+
+def test_fold_factor_rules():
+    """Batch folding (ops.fold_factor): largest power of two s with s*max(Ci,Co) <= 32, B % s == 0 and B/s >= 32;
+    never for wide filters (H > 8)."""
+    from pytorch_quadconv_b200 import ops
+    assert ops.fold_factor(256, 4, 8, 8) == 4        # 4 -> 8 channels, batch 256: [64, 16 -> 32]
+    assert ops.fold_factor(256, 8, 4, 8) == 4
+    assert ops.fold_factor(256, 16, 32, 8) == 1      # already 32 channels on one side
+    assert ops.fold_factor(128, 4, 8, 8) == 4 and ops.fold_factor(64, 4, 8, 8) == 2 and ops.fold_factor(32, 4, 8, 8) == 1
+    assert ops.fold_factor(96, 3, 5, 8) == 2         # 96 / 4 = 24 lanes would fall below 32
+    assert ops.fold_factor(72, 4, 4, 8) == 2         # 72 % 4 == 0 but 72 / 4 = 18 < 32
+    assert ops.fold_factor(256, 4, 8, 32) == 1       # wide filter: the wide path is not folded
+    saved = ops.FOLD_MIN_BATCH
+    try:
+        ops.FOLD_MIN_BATCH = 0
+        assert ops.fold_factor(256, 4, 8, 8) == 1    # switch
+    finally:
+        ops.FOLD_MIN_BATCH = saved
+
+
+def test_flat_gradient_layout_roundtrip():
+    """ops._flat_layout / _carve: 16-byte aligned pieces of one flat buffer, shapes preserved, no overlap."""
+    import torch
+    from pytorch_quadconv_b200 import ops
+    shapes = [(8, 3), (8, 8), (100,), (1024, 8), ()]
+    offs, sizes, total = ops._flat_layout(shapes)
+    assert all(o % 4 == 0 for o in offs) and total >= sum(sizes)
+    for (o, n), (o2, _) in zip(zip(offs, sizes), list(zip(offs, sizes))[1:]):
+        assert o + n <= o2
+    flat = torch.arange(total, dtype=torch.float32)
+    views = ops._carve(flat, shapes)
+    assert [tuple(v.shape) for v in views] == [tuple(s) for s in shapes]
+    for v, o in zip(views, offs):
+        assert v.data_ptr() == flat.data_ptr() + 4 * o
