@@ -106,11 +106,31 @@ int qc_layer_backward(const qc_layer_t* L, const float* grad_out, int B, float* 
     if ((rc = qc_dphi(pl.xp, L->Ni, L->Ci, pl.gp, L->Co, L->row_ptr, L->pair_col, pl.w3, L->H, pl.HP, L->order_out, L->No, B, L->P,
                       pl.dphi, stream)) != 0)
         return rc;
-    for (int l = 0; l < L->mlp.n_hidden; ++l) {
-        if (d_hidden == nullptr || d_hidden[l] == nullptr) return QC_EINVAL;
-        QC_CUDA(cudaMemsetAsync(d_hidden[l], 0, (size_t)L->mlp.dims[l] * L->mlp.dims[l + 1] * sizeof(float), st));
+    // zero the accumulated outputs.  A host that carves them out of one buffer (the Python modules do: pieces in
+    // ascending order, at most 16-byte alignment gaps) gets ONE fill instead of one per piece -- a small-mesh layer step
+    // is launch bound.  (A gap below 64 bytes cannot hold anybody else's data: device allocators hand out blocks of at
+    // least 256 bytes.)
+    {
+        struct Span { char* p; size_t n; };
+        Span sp[QC_MAX_MLP_LAYERS + 2];
+        int ns = 0;
+        for (int l = 0; l < L->mlp.n_hidden; ++l) {
+            if (d_hidden == nullptr || d_hidden[l] == nullptr) return QC_EINVAL;
+            sp[ns++] = {reinterpret_cast<char*>(d_hidden[l]), (size_t)L->mlp.dims[l] * L->mlp.dims[l + 1] * sizeof(float)};
+        }
+        if (d_quad_w != nullptr) sp[ns++] = {reinterpret_cast<char*>(d_quad_w), (size_t)L->Ni * sizeof(float)};
+        sp[ns++] = {reinterpret_cast<char*>(d_w_last), (size_t)L->Ci * L->Co * L->H * sizeof(float)};
+        bool one = true;
+        for (int i = 1; i < ns; ++i) {
+            const char* prev_end = sp[i - 1].p + sp[i - 1].n;
+            if (sp[i].p < prev_end || sp[i].p - prev_end > 64) one = false;
+        }
+        if (one) {
+            QC_CUDA(cudaMemsetAsync(sp[0].p, 0, (size_t)(sp[ns - 1].p + sp[ns - 1].n - sp[0].p), st));
+        } else {
+            for (int i = 0; i < ns; ++i) QC_CUDA(cudaMemsetAsync(sp[i].p, 0, sp[i].n, st));
+        }
     }
-    if (d_quad_w != nullptr) QC_CUDA(cudaMemsetAsync(d_quad_w, 0, (size_t)L->Ni * sizeof(float), st));
     if (L->P > 0 &&
         (rc = qc_pair_phi_bwd_ws(L->out_pts, L->in_pts, L->quad_w, L->pair_row, L->pair_col, L->P, L->d, &L->mlp, pl.HP, pl.dphi,
                                  pl.nsl, d_hidden, d_quad_w, L->csc_ptr, L->csc_pair, L->Ni, pl.mws, pl.mws_bytes, stream)) != 0)
@@ -121,7 +141,6 @@ int qc_layer_backward(const qc_layer_t* L, const float* grad_out, int B, float* 
     if ((rc = qc_contract(pl.gp, L->No, L->Co, L->csc_ptr, L->csc_row, L->csc_pair, pl.phi, L->H, pl.HP, pl.w2t, L->Ci,
                           L->order_in, L->Ni, B, pl.dxp, pl.xp, pl.dw2, pl.cws, pl.cws_bytes, stream)) != 0)
         return rc;
-    QC_CUDA(cudaMemsetAsync(d_w_last, 0, (size_t)L->Ci * L->Co * L->H * sizeof(float), st));
     if ((rc = qc_unpack_dwlast(pl.dw2, L->Ci, L->Co, L->H, d_w_last, stream)) != 0) return rc;
     return qc_unpack_features(pl.dxp, B, L->Ci, L->Ni, nullptr, d_features, stream);
 }
